@@ -1,0 +1,280 @@
+// Embedding (dnpy/layers/core.py:54-65) and SimpleRNN (dnpy/layers/recurrent.py:12-23,153-266).
+//
+// Embedding.backward, literal (Q15): mean over the batch first, then NumPy's fancy-index "+="
+// (gather, add, scatter), so for every vocabulary row the LAST (b,l) position in row-major order
+// decides which sequence slot's mean-delta is added — reproduced with an atomicMax over positions.
+//
+// SimpleRNN: both directions are persistent kernels — a CTA owns a tile of samples, keeps Waa/Wax
+// in shared memory and walks all T timesteps (and, in backward, the (trunc+1)-step inner BPTT
+// loop) without returning to the host.  Backward is the reference's literal recurrence (Q16):
+// full-length dh chain PLUS a truncated inner loop at every t, (1-h^2) applied before the Waa
+// product, gradients summed (not averaged) over the batch.
+#include "common.cuh"
+
+namespace dnb {
+
+__global__ void __launch_bounds__(256) embedding_fwd_kernel(const int32_t* __restrict__ idx, const float* __restrict__ w,
+                                                            float* __restrict__ y, long n_tok, int V, int D) {
+    const long total = n_tok * D;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long tok = i / D; int d = (int)(i % D);
+        int v = idx[tok];
+        y[i] = (v >= 0 && v < V) ? w[(long)v * D + d] : 0.f;
+    }
+}
+// meand[l,d] = inv_m * sum_b dy[b,l,d]
+__global__ void __launch_bounds__(256) embedding_mean_kernel(const float* __restrict__ dy, float* __restrict__ meand,
+                                                             int B, long LD, float inv_m) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= LD) return;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += dy[(long)b * LD + i];
+    meand[i] = acc * inv_m;
+}
+__global__ void __launch_bounds__(256) embedding_last_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ last,
+                                                             long n_tok, int V) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_tok; i += (long)gridDim.x * blockDim.x) {
+        int v = idx[i];
+        if (v >= 0 && v < V) atomicMax(last + v, (int)i);
+    }
+}
+__global__ void __launch_bounds__(256) embedding_apply_kernel(const int32_t* __restrict__ last, const float* __restrict__ meand,
+                                                              float* __restrict__ gw, int V, int L, int D) {
+    long total = (long)V * D;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int v = (int)(i / D), d = (int)(i % D);
+        int pos = last[v];
+        if (pos >= 0) gw[i] += meand[(long)(pos % L) * D + d];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// SimpleRNN forward: thread (s, j) owns hidden unit j of sample s of the CTA's tile.
+// ------------------------------------------------------------------------------------------
+__global__ void rnn_fwd_kernel(const float* __restrict__ x, const float* __restrict__ waa, const float* __restrict__ wax,
+                               const float* __restrict__ ba, float* __restrict__ states, float* __restrict__ y,
+                               int B, int T, int D, int H, int SB) {
+    extern __shared__ float sm[];
+    float* s_waaT = sm;                    // [k][j]  (transposed: conflict-free across j)
+    float* s_waxT = s_waaT + H * H;        // [d][j]
+    float* s_h = s_waxT + D * H;           // [SB][H]
+    float* s_x = s_h + SB * H;             // [SB][D]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < H * H; e += nt) { int j = e / H, k = e % H; s_waaT[k * H + j] = waa[e]; }
+    for (int e = tid; e < H * D; e += nt) { int j = e / D, d = e % D; s_waxT[d * H + j] = wax[e]; }
+    for (int e = tid; e < SB * H; e += nt) s_h[e] = 0.f;
+    const int s = tid / H, j = tid % H;
+    const int b = blockIdx.x * SB + s;
+    const bool act = (s < SB) && (b < B);
+    const float bj = act ? ba[j] : 0.f;
+    for (int t = 0; t < T; ++t) {
+        __syncthreads();
+        for (int e = tid; e < SB * D; e += nt) {
+            int ss = e / D, d = e % D, bb = blockIdx.x * SB + ss;
+            s_x[e] = (bb < B) ? x[((long)bb * T + t) * D + d] : 0.f;
+        }
+        __syncthreads();
+        float hn = 0.f;
+        if (act) {
+            float a = bj;
+            const float* hp = s_h + s * H;
+            for (int k = 0; k < H; ++k) a = fmaf(hp[k], s_waaT[k * H + j], a);
+            const float* xp = s_x + s * D;
+            for (int d = 0; d < D; ++d) a = fmaf(xp[d], s_waxT[d * H + j], a);
+            hn = tanhf(a);
+        }
+        __syncthreads();
+        if (act) {
+            s_h[s * H + j] = hn;
+            states[((long)b * T + t) * H + j] = hn;
+            if (t == T - 1) y[(long)b * H + j] = hn;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// SimpleRNN backward (literal truncated BPTT)
+// ------------------------------------------------------------------------------------------
+__global__ void rnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ states, const float* __restrict__ dy,
+                               const float* __restrict__ waa, const float* __restrict__ wax,
+                               float* __restrict__ dx, float* __restrict__ gwaa, float* __restrict__ gwax, float* __restrict__ gba,
+                               int B, int T, int D, int H, int SB, int trunc) {
+    extern __shared__ float sm[];
+    float* s_waa = sm;                     // [j][j']
+    float* s_wax = s_waa + H * H;          // [j][d]
+    float* a_waa = s_wax + H * D;          // accumulators
+    float* a_wax = a_waa + H * H;
+    float* a_ba = a_wax + H * D;
+    float* s_S = a_ba + H;                 // [SB][H] running inner-loop vector
+    float* s_S2 = s_S + SB * H;
+    float* s_pre = s_S2 + SB * H;
+    float* s_dh = s_pre + SB * H;
+    float* s_hp = s_dh + SB * H;           // h_{k-1}
+    float* s_xk = s_hp + SB * H;           // [SB][D]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < H * H; e += nt) { s_waa[e] = waa[e]; a_waa[e] = 0.f; }
+    for (int e = tid; e < H * D; e += nt) { s_wax[e] = wax[e]; a_wax[e] = 0.f; }
+    for (int e = tid; e < H; e += nt) a_ba[e] = 0.f;
+    for (int e = tid; e < SB * H; e += nt) s_dh[e] = 0.f;
+    const int s = tid / H, j = tid % H;
+    const int b0 = blockIdx.x * SB;
+    const int b = b0 + s;
+    const bool act = (s < SB) && (b < B);
+    __syncthreads();
+
+    for (int t = T - 1; t >= 0; --t) {
+        // pre_t = (dy*[t==T-1] + dh) * (1 - h_t^2)
+        if (act) {
+            float h = states[((long)b * T + t) * H + j];
+            float d = (t == T - 1) ? dy[(long)b * H + j] : 0.f;
+            float pre = (d + s_dh[s * H + j]) * (1.f - h * h);
+            s_pre[s * H + j] = pre;
+            s_S[s * H + j] = pre;
+        } else if (s < SB) { s_pre[s * H + j] = 0.f; s_S[s * H + j] = 0.f; }
+        __syncthreads();
+        const int k_lo = max(0, t - trunc);
+        for (int k = t; k >= k_lo; --k) {
+            // stage h_{k-1} and x_k for the tile
+            for (int e = tid; e < SB * H; e += nt) {
+                int ss = e / H, jj = e % H, bb = b0 + ss;
+                s_hp[e] = (k > 0 && bb < B) ? states[((long)bb * T + (k - 1)) * H + jj] : 0.f;
+            }
+            for (int e = tid; e < SB * D; e += nt) {
+                int ss = e / D, d = e % D, bb = b0 + ss;
+                s_xk[e] = (bb < B) ? x[((long)bb * T + k) * D + d] : 0.f;
+            }
+            __syncthreads();
+            // gradient accumulation: every accumulator entry is owned by exactly one thread
+            for (int e = tid; e < H * H; e += nt) {
+                int jj = e / H, kk = e % H;
+                float acc = a_waa[e];
+                for (int ss = 0; ss < SB; ++ss) acc = fmaf(s_S[ss * H + jj], s_hp[ss * H + kk], acc);
+                a_waa[e] = acc;
+            }
+            for (int e = tid; e < H * D; e += nt) {
+                int jj = e / D, d = e % D;
+                float acc = a_wax[e];
+                for (int ss = 0; ss < SB; ++ss) acc = fmaf(s_S[ss * H + jj], s_xk[ss * D + d], acc);
+                a_wax[e] = acc;
+            }
+            for (int e = tid; e < H; e += nt) {
+                float acc = a_ba[e];
+                for (int ss = 0; ss < SB; ++ss) acc += s_S[ss * H + e];
+                a_ba[e] = acc;
+            }
+            // S <- (S * (1 - h_{k-1}^2)) . Waa      (recurrent.py:240)
+            if (s < SB) {
+                float acc = 0.f;
+                for (int q = 0; q < H; ++q) {
+                    float hp = s_hp[s * H + q];
+                    acc = fmaf(s_S[s * H + q] * (1.f - hp * hp), s_waa[q * H + j], acc);
+                }
+                s_S2[s * H + j] = acc;
+            }
+            __syncthreads();
+            if (s < SB) s_S[s * H + j] = s_S2[s * H + j];
+            __syncthreads();
+        }
+        // dh <- pre . Waa ; dx_t = pre . Wax
+        if (s < SB) {
+            float acc = 0.f;
+            for (int q = 0; q < H; ++q) acc = fmaf(s_pre[s * H + q], s_waa[q * H + j], acc);
+            s_dh[s * H + j] = acc;
+        }
+        for (int e = tid; e < SB * D; e += nt) {
+            int ss = e / D, d = e % D, bb = b0 + ss;
+            if (bb < B) {
+                float acc = 0.f;
+                for (int q = 0; q < H; ++q) acc = fmaf(s_pre[ss * H + q], s_wax[q * D + d], acc);
+                dx[((long)bb * T + t) * D + d] = acc;
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < H * H; e += nt) atomicAdd(gwaa + e, a_waa[e]);
+    for (int e = tid; e < H * D; e += nt) atomicAdd(gwax + e, a_wax[e]);
+    for (int e = tid; e < H; e += nt) atomicAdd(gba + e, a_ba[e]);
+}
+
+static int rnn_tile(int H, int* SB, int* threads) {
+    int sb = 256 / H;
+    if (sb < 1) sb = 1;
+    if (sb > 8) sb = 8;
+    *SB = sb;
+    *threads = ((sb * H + 31) / 32) * 32;
+    return 0;
+}
+
+}  // namespace dnb
+
+using namespace dnb;
+
+extern "C" {
+
+int dnb_embedding_fwd(const int32_t* idx, const float* w, float* y, int B, int L, int V, int D, dnb_stream_t stream) {
+    DNB_CHECK_ARG(B >= 0 && L > 0 && V > 0 && D > 0, "embedding_fwd: bad shape");
+    if (B == 0) return DNB_OK;
+    DNB_CHECK_ARG(idx && w && y, "embedding_fwd: null pointer");
+    long n_tok = (long)B * L;
+    embedding_fwd_kernel<<<ew_grid((size_t)n_tok * D, 256), 256, 0, S(stream)>>>(idx, w, y, n_tok, V, D);
+    DNB_LAUNCH_CHECK("embedding_fwd");
+    return DNB_OK;
+}
+
+size_t dnb_embedding_bwd_ws_bytes(int L, int V, int D) { return ((size_t)V + (size_t)L * D) * sizeof(float); }
+
+int dnb_embedding_bwd(const int32_t* idx, const float* dy, float* gw, int B, int L, int V, int D,
+                      float inv_m, void* ws, dnb_stream_t stream) {
+    DNB_CHECK_ARG(B >= 0 && L > 0 && V > 0 && D > 0, "embedding_bwd: bad shape");
+    if (B == 0) return DNB_OK;
+    DNB_CHECK_ARG(idx && dy && gw && ws, "embedding_bwd: null pointer");
+    cudaStream_t st = S(stream);
+    int32_t* last = static_cast<int32_t*>(ws);
+    float* meand = reinterpret_cast<float*>(last + V);
+    cudaError_t e = cudaMemsetAsync(last, 0xff, (size_t)V * sizeof(int32_t), st);
+    if (e != cudaSuccess) return set_err(DNB_ERR_CUDA, "embedding_bwd: %s", cudaGetErrorString(e));
+    long LD = (long)L * D, n_tok = (long)B * L;
+    embedding_mean_kernel<<<(unsigned)((LD + 255) / 256), 256, 0, st>>>(dy, meand, B, LD, inv_m);
+    DNB_LAUNCH_CHECK("embedding_bwd_mean");
+    embedding_last_kernel<<<ew_grid((size_t)n_tok, 256), 256, 0, st>>>(idx, last, n_tok, V);
+    DNB_LAUNCH_CHECK("embedding_bwd_last");
+    embedding_apply_kernel<<<ew_grid((size_t)V * D, 256), 256, 0, st>>>(last, meand, gw, V, L, D);
+    DNB_LAUNCH_CHECK("embedding_bwd_apply");
+    return DNB_OK;
+}
+
+int dnb_rnn_fwd(const float* x, const float* waa, const float* wax, const float* ba,
+                float* states, float* y, int B, int T, int D, int H, dnb_stream_t stream) {
+    DNB_CHECK_ARG(B >= 0 && T > 0 && D > 0 && H > 0, "rnn_fwd: bad shape");
+    if (B == 0) return DNB_OK;
+    DNB_CHECK_ARG(x && waa && wax && ba && states && y, "rnn_fwd: null pointer");
+    if (H > 256) return set_err(DNB_ERR_UNSUPPORTED, "rnn_fwd: hidden_dim %d > 256 not supported", H);
+    int SB, threads;
+    rnn_tile(H, &SB, &threads);
+    size_t smem = ((size_t)H * H + (size_t)D * H + (size_t)SB * H + (size_t)SB * D) * sizeof(float);
+    if (smem > 200 * 1024) return set_err(DNB_ERR_UNSUPPORTED, "rnn_fwd: H=%d D=%d exceed shared memory", H, D);
+    cudaFuncSetAttribute(rnn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    rnn_fwd_kernel<<<(B + SB - 1) / SB, threads, smem, S(stream)>>>(x, waa, wax, ba, states, y, B, T, D, H, SB);
+    DNB_LAUNCH_CHECK("rnn_fwd");
+    return DNB_OK;
+}
+
+int dnb_rnn_bwd(const float* x, const float* states, const float* dy, const float* waa, const float* wax,
+                float* dx, float* gwaa, float* gwax, float* gba,
+                int B, int T, int D, int H, int trunc, dnb_stream_t stream) {
+    DNB_CHECK_ARG(B >= 0 && T > 0 && D > 0 && H > 0 && trunc >= 0, "rnn_bwd: bad shape");
+    if (B == 0) return DNB_OK;
+    DNB_CHECK_ARG(x && states && dy && waa && wax && dx && gwaa && gwax && gba, "rnn_bwd: null pointer");
+    if (H > 256) return set_err(DNB_ERR_UNSUPPORTED, "rnn_bwd: hidden_dim %d > 256 not supported", H);
+    int SB, threads;
+    rnn_tile(H, &SB, &threads);
+    size_t smem = (2 * ((size_t)H * H + (size_t)H * D) + H + 5 * (size_t)SB * H + (size_t)SB * D) * sizeof(float);
+    if (smem > 200 * 1024) return set_err(DNB_ERR_UNSUPPORTED, "rnn_bwd: H=%d D=%d exceed shared memory", H, D);
+    cudaFuncSetAttribute(rnn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    rnn_bwd_kernel<<<(B + SB - 1) / SB, threads, smem, S(stream)>>>(x, states, dy, waa, wax, dx, gwaa, gwax, gba,
+                                                                     B, T, D, H, SB, trunc);
+    DNB_LAUNCH_CHECK("rnn_bwd");
+    return DNB_OK;
+}
+
+}  // extern "C"

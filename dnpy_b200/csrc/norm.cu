@@ -1,0 +1,160 @@
+// BatchNorm (dnpy/layers/regularization.py:94-156), literal semantics:
+//   * statistics over axis 0 ONLY: x is viewed as [B, n_feat], one (mu, var) per feature, so for
+//     conv inputs gamma/beta/moving_* are (C,H,W)-shaped (Q8);
+//   * biased variance, std = sqrt(var + eps); moving = momentum*moving + (1-momentum)*stat;
+//   * backward (Q7): dgamma = sum_b dy*MU (not x_hat), dX = (1/m)*STD*(m*dy*g - sum(dy*g) - x_hat*sum(dy*g*x_hat)).
+// Column reductions: a CTA owns 32 adjacent features (128-byte coalesced rows) and 8 row lanes;
+// per-lane Welford partials are merged with Chan's formula.  x_hat is recomputed in backward from
+// (x, mu, std) instead of being cached, saving one full tensor write + read.  Roofline: HBM.
+#include "common.cuh"
+
+namespace dnb {
+
+constexpr int BN_COLS = 32, BN_ROWS = 8;
+
+__global__ void __launch_bounds__(256) bn_fwd_train_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ mmu,
+                                                           float* __restrict__ mvar, float* __restrict__ smu,
+                                                           float* __restrict__ sstd, float* __restrict__ y,
+                                                           int B, size_t N, float momentum, float eps) {
+    __shared__ float s_cnt[BN_ROWS][BN_COLS], s_mean[BN_ROWS][BN_COLS], s_m2[BN_ROWS][BN_COLS];
+    __shared__ float s_mu[BN_COLS], s_rstd[BN_COLS];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const size_t col = (size_t)blockIdx.x * BN_COLS + tx;
+    const bool ok = col < N;
+    float cnt = 0.f, mean = 0.f, m2 = 0.f;
+    if (ok)
+        for (int r = ty; r < B; r += BN_ROWS) {
+            float v = x[(size_t)r * N + col];
+            cnt += 1.f;
+            float d = v - mean;
+            mean += d / cnt;
+            m2 = fmaf(d, v - mean, m2);
+        }
+    s_cnt[ty][tx] = cnt; s_mean[ty][tx] = mean; s_m2[ty][tx] = m2;
+    __syncthreads();
+    if (ty == 0 && ok) {
+        float n = s_cnt[0][tx], mu = s_mean[0][tx], M2 = s_m2[0][tx];
+#pragma unroll
+        for (int r = 1; r < BN_ROWS; ++r) {
+            float nb = s_cnt[r][tx];
+            if (nb > 0.f) {
+                float d = s_mean[r][tx] - mu, nt = n + nb;
+                mu += d * (nb / nt);
+                M2 += s_m2[r][tx] + d * d * (n * nb / nt);
+                n = nt;
+            }
+        }
+        float var = M2 / (float)B;
+        float sd = sqrtf(var + eps);
+        smu[col] = mu; sstd[col] = sd;
+        mmu[col] = momentum * mmu[col] + (1.0f - momentum) * mu;
+        mvar[col] = momentum * mvar[col] + (1.0f - momentum) * var;
+        s_mu[tx] = mu; s_rstd[tx] = 1.0f / sd;
+    }
+    __syncthreads();
+    if (ok) {
+        const float mu = s_mu[tx], rs = s_rstd[tx], g = gamma[col], bt = beta[col];
+        for (int r = ty; r < B; r += BN_ROWS) {
+            size_t i = (size_t)r * N + col;
+            y[i] = fmaf(g, (x[i] - mu) * rs, bt);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_fwd_test_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ mmu,
+                                                          const float* __restrict__ mvar, float* __restrict__ smu,
+                                                          float* __restrict__ sstd, float* __restrict__ y,
+                                                          int B, size_t N, float eps) {
+    const size_t total = (size_t)B * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t col = i % N;
+        float mu = mmu[col], sd = sqrtf(mvar[col] + eps);
+        if (i < N) { smu[col] = mu; sstd[col] = sd; }
+        y[i] = fmaf(gamma[col], (x[i] - mu) / sd, beta[col]);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ smu, const float* __restrict__ sstd,
+                                                     const float* __restrict__ dy, float* __restrict__ dx,
+                                                     float* __restrict__ ggamma, float* __restrict__ gbeta, int B, size_t N) {
+    __shared__ float s_a[BN_ROWS][BN_COLS], s_b[BN_ROWS][BN_COLS];
+    __shared__ float s_sdy[BN_COLS], s_sdyx[BN_COLS];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const size_t col = (size_t)blockIdx.x * BN_COLS + tx;
+    const bool ok = col < N;
+    float mu = 0.f, sd = 1.f, g = 0.f;
+    if (ok) { mu = smu[col]; sd = sstd[col]; g = gamma[col]; }
+    const float rs = 1.0f / sd;
+    float sdy = 0.f, sdyx = 0.f;
+    if (ok)
+        for (int r = ty; r < B; r += BN_ROWS) {
+            size_t i = (size_t)r * N + col;
+            float d = dy[i];
+            sdy += d;
+            sdyx = fmaf(d, (x[i] - mu) * rs, sdyx);
+        }
+    s_a[ty][tx] = sdy; s_b[ty][tx] = sdyx;
+    __syncthreads();
+    if (ty == 0) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int r = 0; r < BN_ROWS; ++r) { a += s_a[r][tx]; b += s_b[r][tx]; }
+        s_sdy[tx] = a; s_sdyx[tx] = b;
+        if (ok) {
+            ggamma[col] += a * mu;      // literal: sum_b dy * mu (regularization.py:144,155)
+            gbeta[col] += a;
+        }
+    }
+    __syncthreads();
+    if (ok && dx) {
+        const float m = (float)B, inv_m = 1.0f / m;
+        const float s1 = g * s_sdy[tx], s2 = g * s_sdyx[tx];
+        for (int r = ty; r < B; r += BN_ROWS) {
+            size_t i = (size_t)r * N + col;
+            float xn = (x[i] - mu) * rs;
+            dx[i] = inv_m * sd * (m * dy[i] * g - s1 - xn * s2);
+        }
+    }
+}
+
+}  // namespace dnb
+
+using namespace dnb;
+
+extern "C" {
+
+int dnb_batchnorm_fwd(const float* x, const float* gamma, const float* beta,
+                      float* moving_mu, float* moving_var, float* save_mu, float* save_std,
+                      float* y, int B, size_t n_feat, float momentum, float eps, int training,
+                      dnb_stream_t stream) {
+    DNB_CHECK_ARG(B >= 0, "batchnorm_fwd: negative batch");
+    if ((size_t)B * n_feat == 0) return DNB_OK;
+    DNB_CHECK_ARG(x && gamma && beta && moving_mu && moving_var && save_mu && save_std && y, "batchnorm_fwd: null pointer");
+    if (training) {
+        unsigned grid = (unsigned)((n_feat + BN_COLS - 1) / BN_COLS);
+        bn_fwd_train_kernel<<<grid, 256, 0, S(stream)>>>(x, gamma, beta, moving_mu, moving_var, save_mu, save_std, y,
+                                                         B, n_feat, momentum, eps);
+    } else {
+        bn_fwd_test_kernel<<<ew_grid((size_t)B * n_feat, 256), 256, 0, S(stream)>>>(x, gamma, beta, moving_mu, moving_var,
+                                                                                     save_mu, save_std, y, B, n_feat, eps);
+    }
+    DNB_LAUNCH_CHECK("batchnorm_fwd");
+    return DNB_OK;
+}
+
+int dnb_batchnorm_bwd(const float* x, const float* gamma, const float* save_mu, const float* save_std,
+                      const float* dy, float* dx, float* ggamma, float* gbeta,
+                      int B, size_t n_feat, dnb_stream_t stream) {
+    DNB_CHECK_ARG(B >= 0, "batchnorm_bwd: negative batch");
+    if ((size_t)B * n_feat == 0) return DNB_OK;
+    DNB_CHECK_ARG(x && gamma && save_mu && save_std && dy && ggamma && gbeta, "batchnorm_bwd: null pointer");
+    unsigned grid = (unsigned)((n_feat + BN_COLS - 1) / BN_COLS);
+    bn_bwd_kernel<<<grid, 256, 0, S(stream)>>>(x, gamma, save_mu, save_std, dy, dx, ggamma, gbeta, B, n_feat);
+    DNB_LAUNCH_CHECK("batchnorm_bwd");
+    return DNB_OK;
+}
+
+}  // extern "C"

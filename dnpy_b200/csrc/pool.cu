@@ -1,0 +1,223 @@
+// MaxPool2D / AvgPool2D (dnpy/layers/pooling.py:43-99, 118-174), literal semantics:
+//   * the input is ZERO padded and the pads take part in max / mean (Q6);
+//   * argmax = first maximum of the row-major flattened window (np.argmax), stored as the
+//     window offset in [0, py*px) — bit-exact integer work;
+//   * MaxPool2D.backward LITERAL route (Q5): the flat index addresses the (B,py,px) window view,
+//     so every sample's delta lands in sample 0's window and the LAST sample that selected an
+//     offset wins; PER_SAMPLE is the intended scatter-add (identical when B == 1);
+//   * AvgPool2D.backward ASSIGNS delta/(py*px) to the window, later windows overwrite.
+// All kernels are gather-style (no atomics on the data path), coalesced along x.  Roofline: HBM.
+#include "common.cuh"
+
+namespace dnb {
+
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                          int32_t* __restrict__ idx, dnb_win_t g) {
+    const long n = (long)g.B * g.C * g.OH * g.OW;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        int ox = (int)(i % g.OW); long t = i / g.OW; int oy = (int)(t % g.OH); long bc = t / g.OH;
+        const float* xp = x + bc * g.H * g.W;
+        float best = 0.f; int bi = 0; bool first = true;
+        for (int ii = 0; ii < g.kh; ++ii) {
+            int iy = oy * g.sy + ii - g.pt;
+            bool rowin = (iy >= 0 && iy < g.H);
+            for (int jj = 0; jj < g.kw; ++jj) {
+                int ix = ox * g.sx + jj - g.pl;
+                float v = (rowin && ix >= 0 && ix < g.W) ? __ldg(xp + (long)iy * g.W + ix) : 0.f;   // zero pad
+                // np.argmax semantics: first maximum wins; NaN propagates as the maximum
+                if (first || v > best || (v != v && best == best)) { best = v; bi = ii * g.kw + jj; first = false; }
+            }
+        }
+        y[i] = best;
+        idx[i] = bi;
+    }
+}
+
+// PER_SAMPLE: dx[b,c,iy,ix] = sum over windows covering it whose argmax points here.
+__global__ void __launch_bounds__(256) maxpool_bwd_per_sample_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx,
+                                                                     float* __restrict__ dx, dnb_win_t g) {
+    const long n = (long)g.B * g.C * g.H * g.W;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        int ix = (int)(i % g.W); long t = i / g.W; int iy = (int)(t % g.H); long bc = t / g.H;
+        const float* dp = dy + bc * g.OH * g.OW;
+        const int32_t* ip = idx + bc * g.OH * g.OW;
+        const int py = iy + g.pt, px = ix + g.pl;          // padded coordinates
+        float acc = 0.f;
+        // windows (oy,ox) with oy*sy <= py < oy*sy+kh, in the reference's (y,x) accumulation order
+        int oy_lo = max(0, (py - g.kh + g.sy) / g.sy), oy_hi = min(g.OH - 1, py / g.sy);
+        int ox_lo = max(0, (px - g.kw + g.sx) / g.sx), ox_hi = min(g.OW - 1, px / g.sx);
+        for (int oy = oy_lo; oy <= oy_hi; ++oy)
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                int off = (py - oy * g.sy) * g.kw + (px - ox * g.sx);
+                if (ip[oy * g.OW + ox] == off) acc += dp[oy * g.OW + ox];
+            }
+        dx[i] = acc;
+    }
+}
+
+// LITERAL step 1: last[c,oy,ox,p] = max b with idx[b,c,oy,ox] == p  (int32, pre-filled with -1)
+__global__ void __launch_bounds__(256) maxpool_last_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ last,
+                                                           dnb_win_t g, int bchunk) {
+    const long npos = (long)g.C * g.OH * g.OW;
+    const long pos = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= npos) return;
+    const int P = g.kh * g.kw;
+    const int b_hi = min(g.B, (int)(blockIdx.y + 1) * bchunk) - 1, b_lo = blockIdx.y * bchunk;
+    // walk this chunk from its last sample down; the first hit per offset is the chunk's last
+    unsigned long long seen_lo = 0ull;      // offsets 0..63 tracked in a bitmask, the rest go straight to atomicMax
+    for (int b = b_hi; b >= b_lo; --b) {
+        int p = idx[(long)b * npos + pos];
+        if (p < 64) {
+            if (seen_lo >> p & 1ull) continue;
+            seen_lo |= 1ull << p;
+        }
+        atomicMax(last + pos * P + p, b);
+    }
+}
+// LITERAL step 2: dx[0,c,iy,ix] = sum over covering windows of dy[last, c, oy, ox]; dx[b>0] = 0
+__global__ void __launch_bounds__(256) maxpool_bwd_literal_kernel(const float* __restrict__ dy, const int32_t* __restrict__ last,
+                                                                  float* __restrict__ dx, dnb_win_t g) {
+    const long n0 = (long)g.C * g.H * g.W;
+    const long npos = (long)g.C * g.OH * g.OW;
+    const int P = g.kh * g.kw;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n0; i += (long)gridDim.x * blockDim.x) {
+        int ix = (int)(i % g.W); long t = i / g.W; int iy = (int)(t % g.H); int c = (int)(t / g.H);
+        const int py = iy + g.pt, px = ix + g.pl;
+        float acc = 0.f;
+        int oy_lo = max(0, (py - g.kh + g.sy) / g.sy), oy_hi = min(g.OH - 1, py / g.sy);
+        int ox_lo = max(0, (px - g.kw + g.sx) / g.sx), ox_hi = min(g.OW - 1, px / g.sx);
+        for (int oy = oy_lo; oy <= oy_hi; ++oy)
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                int off = (py - oy * g.sy) * g.kw + (px - ox * g.sx);
+                long pos = ((long)c * g.OH + oy) * g.OW + ox;
+                int b = last[pos * P + off];
+                if (b >= 0) acc += dy[(long)b * npos + pos];
+            }
+        dx[i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, dnb_win_t g) {
+    const long n = (long)g.B * g.C * g.OH * g.OW;
+    const float inv = 1.0f / (float)(g.kh * g.kw);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        int ox = (int)(i % g.OW); long t = i / g.OW; int oy = (int)(t % g.OH); long bc = t / g.OH;
+        const float* xp = x + bc * g.H * g.W;
+        float acc = 0.f;
+        for (int ii = 0; ii < g.kh; ++ii) {
+            int iy = oy * g.sy + ii - g.pt;
+            if (iy < 0 || iy >= g.H) continue;
+            for (int jj = 0; jj < g.kw; ++jj) {
+                int ix = ox * g.sx + jj - g.pl;
+                if (ix >= 0 && ix < g.W) acc += __ldg(xp + (long)iy * g.W + ix);
+            }
+        }
+        y[i] = acc * inv;
+    }
+}
+
+// assignment semantics: the LAST window in (oy,ox) loop order that covers the pixel wins
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, dnb_win_t g) {
+    const long n = (long)g.B * g.C * g.H * g.W;
+    const float inv = 1.0f / (float)(g.kh * g.kw);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        int ix = (int)(i % g.W); long t = i / g.W; int iy = (int)(t % g.H); long bc = t / g.H;
+        const int py = iy + g.pt, px = ix + g.pl;
+        int oy_lo = max(0, (py - g.kh + g.sy) / g.sy), oy_hi = min(g.OH - 1, py / g.sy);
+        int ox_lo = max(0, (px - g.kw + g.sx) / g.sx), ox_hi = min(g.OW - 1, px / g.sx);
+        float v = 0.f;
+        if (oy_lo <= oy_hi && ox_lo <= ox_hi) v = dy[bc * g.OH * g.OW + (long)oy_hi * g.OW + ox_hi] * 1.0f * inv;
+        dx[i] = v;
+    }
+}
+
+static int check_pool(const char* name, const dnb_win_t* g) {
+    DNB_CHECK_ARG(g, "%s: null geometry", name);
+    DNB_CHECK_ARG(g->B >= 0 && g->C > 0 && g->H > 0 && g->W > 0 && g->OH > 0 && g->OW > 0 && g->kh > 0 && g->kw > 0 &&
+                  g->sy > 0 && g->sx > 0, "%s: non-positive dimension", name);
+    DNB_CHECK_ARG(g->pt >= 0 && g->pb >= 0 && g->pl >= 0 && g->pr >= 0, "%s: negative padding", name);
+    DNB_CHECK_ARG(g->F == g->C, "%s: pooling keeps the channel count (F == C)", name);
+    return DNB_OK;
+}
+
+}  // namespace dnb
+
+using namespace dnb;
+
+extern "C" {
+
+int dnb_maxpool2d_fwd(const float* x, float* y, int32_t* idx, const dnb_win_t* g, dnb_stream_t stream) {
+    int rc = check_pool("maxpool2d_fwd", g);
+    if (rc) return rc;
+    long n = (long)g->B * g->C * g->OH * g->OW;
+    if (n == 0) return DNB_OK;
+    DNB_CHECK_ARG(x && y && idx, "maxpool2d_fwd: null pointer");
+    maxpool_fwd_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(x, y, idx, *g);
+    DNB_LAUNCH_CHECK("maxpool2d_fwd");
+    return DNB_OK;
+}
+
+size_t dnb_maxpool2d_bwd_ws_bytes(const dnb_win_t* g, int route) {
+    if (!g || route != DNB_ROUTE_LITERAL) return 0;
+    return (size_t)g->C * g->OH * g->OW * g->kh * g->kw * sizeof(int32_t);
+}
+
+int dnb_maxpool2d_bwd(const float* dy, const int32_t* idx, float* dx, const dnb_win_t* g,
+                      int route, void* ws, dnb_stream_t stream) {
+    int rc = check_pool("maxpool2d_bwd", g);
+    if (rc) return rc;
+    long n = (long)g->B * g->C * g->H * g->W;
+    if (n == 0) return DNB_OK;
+    DNB_CHECK_ARG(dy && idx && dx, "maxpool2d_bwd: null pointer");
+    cudaStream_t st = S(stream);
+    if (route == DNB_ROUTE_PER_SAMPLE || g->B == 1) {
+        maxpool_bwd_per_sample_kernel<<<ew_grid(n, 256), 256, 0, st>>>(dy, idx, dx, *g);
+        DNB_LAUNCH_CHECK("maxpool2d_bwd");
+        return DNB_OK;
+    }
+    DNB_CHECK_ARG(route == DNB_ROUTE_LITERAL, "maxpool2d_bwd: unknown route %d", route);
+    DNB_CHECK_ARG(ws, "maxpool2d_bwd: the literal route needs a workspace");
+    const long npos = (long)g->C * g->OH * g->OW;
+    const int P = g->kh * g->kw;
+    int32_t* last = static_cast<int32_t*>(ws);
+    cudaError_t e = cudaMemsetAsync(last, 0xff, (size_t)npos * P * sizeof(int32_t), st);     // -1
+    if (e != cudaSuccess) return set_err(DNB_ERR_CUDA, "maxpool2d_bwd: %s", cudaGetErrorString(e));
+    const int bchunk = 64;
+    dim3 grid((unsigned)((npos + 255) / 256), (g->B + bchunk - 1) / bchunk);
+    maxpool_last_kernel<<<grid, 256, 0, st>>>(idx, last, *g, bchunk);
+    DNB_LAUNCH_CHECK("maxpool2d_bwd_last");
+    const long n0 = (long)g->C * g->H * g->W;
+    if (g->B > 1) {
+        e = cudaMemsetAsync(dx + n0, 0, (size_t)(n - n0) * sizeof(float), st);               // samples 1..B-1 get no delta
+        if (e != cudaSuccess) return set_err(DNB_ERR_CUDA, "maxpool2d_bwd: %s", cudaGetErrorString(e));
+    }
+    maxpool_bwd_literal_kernel<<<ew_grid(n0, 256), 256, 0, st>>>(dy, last, dx, *g);
+    DNB_LAUNCH_CHECK("maxpool2d_bwd_literal");
+    return DNB_OK;
+}
+
+int dnb_avgpool2d_fwd(const float* x, float* y, const dnb_win_t* g, dnb_stream_t stream) {
+    int rc = check_pool("avgpool2d_fwd", g);
+    if (rc) return rc;
+    long n = (long)g->B * g->C * g->OH * g->OW;
+    if (n == 0) return DNB_OK;
+    DNB_CHECK_ARG(x && y, "avgpool2d_fwd: null pointer");
+    avgpool_fwd_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(x, y, *g);
+    DNB_LAUNCH_CHECK("avgpool2d_fwd");
+    return DNB_OK;
+}
+
+int dnb_avgpool2d_bwd(const float* dy, float* dx, const dnb_win_t* g, dnb_stream_t stream) {
+    int rc = check_pool("avgpool2d_bwd", g);
+    if (rc) return rc;
+    // pooling.py:169 tiles the delta exactly 4 times: any other window size raises in the reference
+    DNB_CHECK_ARG(g->kh * g->kw == 4, "avgpool2d_bwd: the reference backward only supports 4-element pools (got %dx%d)", g->kh, g->kw);
+    long n = (long)g->B * g->C * g->H * g->W;
+    if (n == 0) return DNB_OK;
+    DNB_CHECK_ARG(dy && dx, "avgpool2d_bwd: null pointer");
+    avgpool_bwd_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(dy, dx, *g);
+    DNB_LAUNCH_CHECK("avgpool2d_bwd");
+    return DNB_OK;
+}
+
+}  // extern "C"

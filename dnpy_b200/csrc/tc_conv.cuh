@@ -1,0 +1,17 @@
+// Interface of the tcgen05/TMEM implicit-GEMM convolution kernels (tc_conv.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/dnpy_b200.h"
+
+namespace dnb {
+
+enum { TC_CONV_FWD = 0, TC_CONV_DGRAD = 1, TC_CONV_WGRAD = 2 };
+
+size_t tc_conv_ws_bytes(const dnb_win_t* g);
+bool tc_conv_supported(const dnb_win_t* g, int kind);
+int tc_conv_fwd(const float* x, const float* w, const float* b, float* y, const dnb_win_t* g, void* ws, cudaStream_t st);
+int tc_conv_dgrad(const float* dy, const float* w, float* dx, const dnb_win_t* g, void* ws, cudaStream_t st);
+int tc_conv_wgrad(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, void* ws,
+                  cudaStream_t st);
+
+}  // namespace dnb

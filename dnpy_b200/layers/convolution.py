@@ -1,0 +1,166 @@
+"""Conv2D, PointwiseConv2D, DepthwiseConv2D (dnpy/layers/convolution.py).
+
+Shape logic (output size first, then "same" padding, floor-half before / rest
+after) is the reference's, computed once on the host.  The arithmetic is the
+CUDA implicit convolution behind dnb_conv2d_* / dnb_dwconv2d_*: the padded
+copy ``in_fmap`` the reference builds is never materialised.
+"""
+import numpy as np
+
+from .base import Layer
+from .. import initializers, utils, _lib
+from ..darray import ParamDict
+from ..regularizers import reg_coeffs
+from ..runtime import config
+from .._lib import Reg, Win
+
+
+class Conv(Layer):
+    """Constructor logic of convolution.py:7-71."""
+
+    def __init__(self, l_in, filters, kernel_size, strides, padding, dilation_rate,
+                 kernel_initializer=None, bias_initializer=None,
+                 kernel_regularizer=None, bias_regularizer=None, name="Conv"):
+        super().__init__(name=name)
+        self.parents.append(l_in)
+
+        if len(kernel_size) == len(l_in.oshape):
+            input_size = l_in.oshape
+            self.kernel_size = kernel_size
+        else:
+            input_size = l_in.oshape[1:]
+            self.kernel_size = (l_in.oshape[0], *kernel_size)
+
+        self.filters = filters
+        self.strides = strides
+        self.padding = padding
+        self.dilation_rate = dilation_rate
+        if tuple(dilation_rate) != (1,) * len(tuple(dilation_rate)):
+            # Q20: the reference changes oshape but not the arithmetic — unsupported rather than wrong
+            raise NotImplementedError("dilation_rate != 1 is not supported")
+
+        _oshape = utils.get_output(input_size=input_size, kernel_size=kernel_size, strides=strides,
+                                   padding=padding, dilation_rate=dilation_rate)
+        _pads = utils.get_padding(padding=padding, input_size=input_size, output_size=_oshape,
+                                  kernel_size=kernel_size, strides=strides)
+        self.pads = tuple(_pads)
+        self.oshape = tuple([self.filters] + _oshape.tolist())
+
+        self.params = ParamDict(w1=np.zeros((self.filters, *self.kernel_size)), b1=np.zeros((self.filters,)))
+        self.grads = ParamDict(w1=np.zeros((self.filters, *self.kernel_size)), b1=np.zeros((self.filters,)))
+
+        self.kernel_initializer = kernel_initializer if kernel_initializer is not None else initializers.RandomUniform()
+        # Q3 (convolution.py:52-55)
+        self.bias_initializer = initializers.Zeros() if bias_initializer is None else kernel_initializer
+        self.kernel_regularizer = kernel_regularizer
+        self.bias_regularizer = bias_regularizer
+
+        self.shape_pad_in = None
+        self.in_fmap = None
+
+    def initialize(self, optimizer=None):
+        super().initialize(optimizer=optimizer)
+        self.kernel_initializer.apply(self.params, ['w1'])
+        self.bias_initializer.apply(self.params, ['b1'])
+
+    def _win(self, batch):
+        c, h, w = self.parents[0].oshape
+        f, oh, ow = self.oshape
+        kh, kw = self.kernel_size[-2], self.kernel_size[-1]
+        if min(self.pad_top, self.pad_bottom, self.pad_left, self.pad_right) < 0:
+            raise ValueError(f"{self.name}: negative padding (kernel smaller than stride with 'same')")
+        return Win(batch, c, h, w, f, oh, ow, kh, kw, self.strides[0], self.strides[1],
+                   self.pad_top, self.pad_bottom, self.pad_left, self.pad_right)
+
+
+class Conv2D(Conv):
+    """convolution.py:175-273 (the live, second definition — Q21)."""
+
+    def __init__(self, l_in, filters, kernel_size, strides=(1, 1), padding="same", dilation_rate=(1, 1),
+                 kernel_initializer=None, bias_initializer=None,
+                 kernel_regularizer=None, bias_regularizer=None, name="Conv2D"):
+        super().__init__(l_in, filters=filters, kernel_size=kernel_size, strides=strides, padding=padding,
+                         dilation_rate=dilation_rate, kernel_initializer=kernel_initializer,
+                         bias_initializer=bias_initializer, kernel_regularizer=kernel_regularizer,
+                         bias_regularizer=bias_regularizer, name=name)
+        (self.pad_top, self.pad_bottom), (self.pad_left, self.pad_right) = utils.get_side_paddings(self.pads)
+        assert len(self.kernel_size) == 3
+        assert len(self.strides) == 2
+
+    def forward(self):
+        x = self._in()
+        b = x.shape[0]
+        g = self._win(b)
+        out = self._buf('out', (b, *self.oshape))
+        ws = self._raw('ws', _lib.load().dnb_conv2d_ws_bytes(g, config.math))
+        self._call("dnb_conv2d_fwd", x.ptr(), self.params['w1'].ptr(), self.params['b1'].ptr(), out.ptr(),
+                   g, ws, config.math)
+        self.output = out
+
+    def backward(self):
+        x, dy = self._in(), self._delta()
+        b = x.shape[0]
+        g = self._win(b)
+        dx = self._buf('dx', x.shape)
+        ws = self._raw('ws', _lib.load().dnb_conv2d_ws_bytes(g, config.math))
+        self._call("dnb_conv2d_bwd", x.ptr(), self.params['w1'].ptr(), self.params['b1'].ptr(), dy.ptr(),
+                   dx.ptr(), self.grads['w1'].ptr(), self.grads['b1'].ptr(), g, self._inv_m(b),
+                   Reg(*reg_coeffs(self.kernel_regularizer)), Reg(*reg_coeffs(self.bias_regularizer)),
+                   config.reg_scale, ws, config.math)
+        self.grads['w1'].written()
+        self.grads['b1'].written()
+        self.parents[0].delta = dx
+
+
+class PointwiseConv2D(Conv2D):
+    """convolution.py:276-284: 1x1, stride 1, no padding."""
+
+    def __init__(self, l_in, filters, kernel_initializer=None, bias_initializer=None,
+                 kernel_regularizer=None, bias_regularizer=None, name="PointwiseConv2D"):
+        super().__init__(l_in, filters, kernel_size=(1, 1), strides=(1, 1), dilation_rate=(1, 1), padding="none",
+                         kernel_initializer=kernel_initializer, bias_initializer=bias_initializer,
+                         kernel_regularizer=kernel_regularizer, bias_regularizer=bias_regularizer, name=name)
+
+
+class DepthwiseConv2D(Conv):
+    """convolution.py:287-388; ``depth_multiplier`` is stored but unused, as in the reference."""
+
+    def __init__(self, l_in, kernel_size, strides=(1, 1), padding="same", dilation_rate=(1, 1), depth_multiplier=1,
+                 kernel_initializer=None, bias_initializer=None,
+                 kernel_regularizer=None, bias_regularizer=None, name="DepthwiseConv2D"):
+        if len(l_in.oshape) != 3:
+            raise ValueError(f"Expected a 3D layer ({name})")
+        filters = l_in.oshape[0]
+        self.depth_multiplier = int(depth_multiplier)
+        super().__init__(l_in, filters=filters, kernel_size=kernel_size, strides=strides, padding=padding,
+                         dilation_rate=dilation_rate, kernel_initializer=kernel_initializer,
+                         bias_initializer=bias_initializer, kernel_regularizer=kernel_regularizer,
+                         bias_regularizer=bias_regularizer, name=name)
+        (self.pad_top, self.pad_bottom), (self.pad_left, self.pad_right) = utils.get_side_paddings(self.pads)
+        assert len(self.kernel_size) == 3
+        assert len(self.strides) == 2
+        self.kernel_size = (1, *list(self.kernel_size)[1:])
+        self.params = ParamDict(w1=np.zeros((self.filters, *self.kernel_size)), b1=np.zeros((self.filters,)))
+        self.grads = ParamDict(w1=np.zeros((self.filters, *self.kernel_size)), b1=np.zeros((self.filters,)))
+
+    def forward(self):
+        x = self._in()
+        b = x.shape[0]
+        out = self._buf('out', (b, *self.oshape))
+        self._call("dnb_dwconv2d_fwd", x.ptr(), self.params['w1'].ptr(), self.params['b1'].ptr(), out.ptr(),
+                   self._win(b))
+        self.output = out
+
+    def backward(self):
+        if self.kernel_regularizer:
+            # the reference raises here too (shape bug at convolution.py:380)
+            raise ValueError("non-broadcastable output operand: DepthwiseConv2D does not support a kernel_regularizer")
+        x, dy = self._in(), self._delta()
+        b = x.shape[0]
+        dx = self._buf('dx', x.shape)
+        self._call("dnb_dwconv2d_bwd", x.ptr(), self.params['w1'].ptr(), self.params['b1'].ptr(), dy.ptr(),
+                   dx.ptr(), self.grads['w1'].ptr(), self.grads['b1'].ptr(), self._win(b), self._inv_m(b),
+                   Reg(*reg_coeffs(self.bias_regularizer)), config.reg_scale)
+        self.grads['w1'].written()
+        self.grads['b1'].written()
+        self.parents[0].delta = dx

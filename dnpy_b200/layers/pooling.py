@@ -1,0 +1,100 @@
+"""MaxPool2D, GlobalMaxPool2D, AvgPool2D, GlobalAvgPool2D (dnpy/layers/pooling.py)."""
+import numpy as np
+
+from .base import Layer
+from .. import utils, _lib
+from ..runtime import config
+from .._lib import Win
+
+
+class Pool(Layer):
+    """pooling.py:7-28, including Q4: the padding is derived from ``_oshape[1:]`` (width only)."""
+
+    def __init__(self, l_in, pool_size, strides, padding, name="Pool"):
+        super().__init__(name=name)
+        self.parents.append(l_in)
+        input_size = l_in.oshape[1:]
+        self.pool_size = pool_size
+        self.strides = strides
+        self.padding = padding
+        _oshape = utils.get_output(input_size=input_size, kernel_size=pool_size, strides=strides,
+                                   padding=padding, dilation_rate=None)
+        _pads = utils.get_padding(padding=padding, input_size=input_size, output_size=_oshape[1:],
+                                  kernel_size=pool_size, strides=strides)
+        self.pads = tuple(_pads)
+        self.oshape = tuple([l_in.oshape[0]] + _oshape.tolist())
+        (self.pad_top, self.pad_bottom), (self.pad_left, self.pad_right) = utils.get_side_paddings(self.pads)
+
+    def _win(self, batch):
+        c, h, w = self.parents[0].oshape
+        _, oh, ow = self.oshape
+        if min(self.pad_top, self.pad_bottom, self.pad_left, self.pad_right) < 0:
+            raise ValueError(f"{self.name}: negative padding")
+        if (oh - 1) * self.strides[0] + self.pool_size[0] > h + self.pad_top + self.pad_bottom or \
+                (ow - 1) * self.strides[1] + self.pool_size[1] > w + self.pad_left + self.pad_right:
+            # Q4: for non-square inputs the width-derived padding is too small and NumPy would raise/mis-slice
+            raise ValueError(f"{self.name}: pooling windows exceed the padded input (non-square 'same' pooling)")
+        return Win(batch, c, h, w, c, oh, ow, self.pool_size[0], self.pool_size[1], self.strides[0], self.strides[1],
+                   self.pad_top, self.pad_bottom, self.pad_left, self.pad_right)
+
+
+class MaxPool2D(Pool):
+    """pooling.py:31-99.  ``output_idxs`` keeps the reference's meaning: the row-major offset of
+    the first maximum inside the zero-padded window."""
+
+    def __init__(self, l_in, pool_size, strides=(2, 2), padding="none", name="MaxPool2D"):
+        super().__init__(l_in, pool_size=pool_size, strides=strides, padding=padding, name=name)
+        self.output_idxs = None
+
+    def forward(self):
+        x = self._in()
+        b = x.shape[0]
+        out = self._buf('out', (b, *self.oshape))
+        idx = self._buf('idx', (b, *self.oshape), is_int=True)
+        self._call("dnb_maxpool2d_fwd", x.ptr(), out.ptr(), idx.ptr(), self._win(b))
+        self.output = out
+        self.output_idxs = idx
+
+    def backward(self):
+        x, dy = self._in(), self._delta()
+        b = x.shape[0]
+        g = self._win(b)
+        dx = self._buf('dx', x.shape)
+        route = config.maxpool_route
+        ws = self._raw('ws', _lib.load().dnb_maxpool2d_bwd_ws_bytes(g, route))
+        self._call("dnb_maxpool2d_bwd", dy.ptr(), self.output_idxs.ptr(), dx.ptr(), g, route, ws)
+        self.parents[0].delta = dx
+
+
+class GlobalMaxPool2D(MaxPool2D):
+    """pooling.py:102-106."""
+
+    def __init__(self, l_in, name="GlobalMaxPool2D"):
+        super().__init__(l_in, pool_size=l_in.oshape[1:], strides=(1, 1), padding="none", name=name)
+
+
+class AvgPool2D(Pool):
+    """pooling.py:109-174 (backward only exists for 4-element windows, as in the reference)."""
+
+    def __init__(self, l_in, pool_size, strides=(2, 2), padding="none", name="AvgPool2D"):
+        super().__init__(l_in, pool_size=pool_size, strides=strides, padding=padding, name=name)
+
+    def forward(self):
+        x = self._in()
+        b = x.shape[0]
+        out = self._buf('out', (b, *self.oshape))
+        self._call("dnb_avgpool2d_fwd", x.ptr(), out.ptr(), self._win(b))
+        self.output = out
+
+    def backward(self):
+        x, dy = self._in(), self._delta()
+        dx = self._buf('dx', x.shape)
+        self._call("dnb_avgpool2d_bwd", dy.ptr(), dx.ptr(), self._win(x.shape[0]))
+        self.parents[0].delta = dx
+
+
+class GlobalAvgPool2D(AvgPool2D):
+    """pooling.py:177-181."""
+
+    def __init__(self, l_in, name="GlobalAvgPool2D"):
+        super().__init__(l_in, pool_size=l_in.oshape[1:], strides=(1, 1), padding="none", name=name)

@@ -1,0 +1,115 @@
+"""Losses (dnpy/losses.py).  MSE, BinaryCrossEntropy and CrossEntropy run as ONE fused kernel that
+produces the scalar loss, the delta tensor and the NaN/Inf flags Net.compute_losses checks
+(net.py:342-350).  ``compute_loss`` and ``compute_delta`` keep the reference's two-call protocol:
+the first call on a (y_pred, y_target) pair runs the kernel, the second reuses its result.
+
+RMSE / MAE / NLL / Hinge have no config and no kernel."""
+import numpy as np
+
+from . import _lib
+from .darray import DArray, dev_empty, stream_ptr
+from .runtime import config
+
+
+class Loss:
+    """Returns a scalar per batch (losses.py:4-14)."""
+    _kernel = None
+
+    def __init__(self, name="Base loss"):
+        self.name = name
+        self.epsilon = 10e-8
+        self._memo = None       # (id(y_pred), id(y_target), loss, delta, flags)
+        self._bufs = {}
+
+    def _extra(self):
+        return ()
+
+    def _run(self, y_pred, y_target, who):
+        """Run the fused kernel, or hand over the result the OTHER method of the pair just produced
+        for the same (y_pred, y_target) objects — a result is never reused twice, so a re-filled
+        output buffer can not be served stale."""
+        if self._kernel is None:
+            raise NotImplementedError(f"{type(self).__name__}: no CUDA kernel (out of scope, SURVEY §8f)")
+        memo, self._memo = self._memo, None
+        if memo is not None and memo[0] is y_pred and memo[1] is y_target and memo[4] != who:
+            return memo
+        p = DArray.wrap(y_pred)
+        t = DArray.wrap(y_target)
+        if p.ndim != 2:
+            raise ValueError(f"{self.name}: expected (batch, outputs) predictions, got {p.shape}")
+        if p.shape != t.shape:
+            raise ValueError(f"{self.name}: predictions {p.shape} and targets {t.shape} differ in shape")
+        b, n = p.shape
+        key = (b, n)
+        bufs = self._bufs.get(key)
+        if bufs is None:
+            ws_bytes = _lib.load().dnb_loss_ws_bytes(b)
+            bufs = (DArray.device(dev_empty((b, n))), dev_empty((2,)), dev_empty(((ws_bytes + 3) // 4,)))
+            self._bufs = {key: bufs}
+        delta, out, ws = bufs
+        # mean over the GLOBAL batch when the minibatch is sharded across ranks
+        scale = config.inv_world / float(b)
+        _lib.call(self._kernel, p.ptr(), t.ptr(), delta.ptr(), out.data_ptr(), b, n, *self._extra(), scale,
+                  ws.data_ptr(), stream_ptr())
+        delta.written()
+        self._memo = (y_pred, y_target, out, delta, who)
+        return self._memo
+
+    def result_tensor(self, y_pred, y_target):
+        """Device tensor [loss, flags] without synchronising (used by Net's fused step)."""
+        return self._run(y_pred, y_target, "loss")[2]
+
+    def compute_loss(self, y_pred, y_target):
+        out = self._run(y_pred, y_target, "loss")[2]
+        return float(out[0].item())
+
+    def compute_delta(self, y_pred, y_target):
+        return self._run(y_pred, y_target, "delta")[3]
+
+
+class MSE(Loss):
+    """losses.py:17-26."""
+    _kernel = "dnb_loss_mse"
+
+    def __init__(self, name="MSE"):
+        super().__init__(name=name)
+
+
+class BinaryCrossEntropy(Loss):
+    """losses.py:60-73."""
+    _kernel = "dnb_loss_bce"
+
+    def __init__(self, name="BinaryCrossEntropy"):
+        super().__init__(name=name)
+
+
+class CrossEntropy(Loss):
+    """losses.py:76-94; ``softmax_output`` is set by Net.build(smart_derivatives=True)."""
+    _kernel = "dnb_loss_ce"
+
+    def __init__(self, name="CrossEntropy"):
+        super().__init__(name=name)
+        self.softmax_output = False
+
+    def _extra(self):
+        return (int(bool(self.softmax_output)),)
+
+
+class RMSE(Loss):
+    def __init__(self, name="RMSE"):
+        super().__init__(name=name)
+
+
+class MAE(Loss):
+    def __init__(self, name="MAE"):
+        super().__init__(name=name)
+
+
+class NLL(Loss):
+    def __init__(self, name="NLL"):
+        super().__init__(name=name)
+
+
+class Hinge(Loss):
+    def __init__(self, name="Hinge"):
+        super().__init__(name=name)

@@ -1,0 +1,513 @@
+"""Net — the orchestrator with dnpy's API (dnpy/net.py) driving CUDA kernels.
+
+Public surface and print strings are the reference's: ``build / fit / evaluate /
+set_mode / feed_input / forward / compute_losses / compute_metrics / reset_grads /
+do_delta / backward / apply_grads / summary / get_params / set_params / get_grads /
+set_grads / save / load``.  What changes underneath:
+
+* after ``build`` the trainable parameters, their gradients and the optimizer state
+  live in FLAT fp32 arenas (one allocation each), so ``reset_grads`` is one memset,
+  ``apply_grads`` is one fused optimizer launch for the whole net, and the
+  data-parallel exchange is one all-reduce on the gradient arena;
+* ``fit`` can replay a captured CUDA graph of the whole step (forward -> loss ->
+  reset -> backward -> [all-reduce] -> optimizer) instead of ~40 Python-driven launches;
+* with ``dnpy_b200.parallel`` initialised (one process per GPU), ``fit`` shards every
+  minibatch over the ranks.
+"""
+import copy
+import math
+import os
+import pickle
+
+import numpy as np
+
+from . import _lib
+from .darray import DArray, ParamDict, dev_empty, dev_zeros, require_cuda, stream_ptr, torch
+from .layers import Softmax
+from .losses import CrossEntropy
+from .optimizers import Adam, RMSProp, SGD
+from .runtime import config
+
+_ALIGN = 32     # floats: every arena slot starts on a 128-byte boundary (TMA / float4 friendly)
+
+
+def check_datasets(x_train, y_train, x_test, y_test):
+    """net.py:10-35."""
+    if x_train and y_train and x_test and y_test:
+        assert len(x_train) == len(x_test)
+        assert len(y_train) == len(y_test)
+        for a, b in zip(x_train, x_test):
+            assert a.shape[1:] == b.shape[1:]
+        for a, b in zip(y_train, y_test):
+            assert a.shape[1:] == b.shape[1:]
+    if x_train and y_train:
+        for a, b in zip(x_train, y_train):
+            assert len(a) == len(b)
+    if x_test and y_test:
+        for a, b in zip(x_test, y_test):
+            assert len(a) == len(b)
+
+
+def _visit(node, temp, done, order):
+    """Depth-first post-order with cycle detection (net.py:38-58): parents first, then the node is
+    pushed to the FRONT, so ``order`` ends up outputs-first."""
+    key = id(node)
+    if key in done:
+        return
+    if key in temp:
+        raise RecursionError("Not a DAG")
+    temp.add(key)
+    for parent in node.parents:
+        _visit(parent, temp, done, order)
+    temp.remove(key)
+    done.add(key)
+    order.insert(0, node)
+
+
+class Net:
+
+    def __init__(self):
+        self.l_in = None
+        self.l_out = None
+        self.fts_layers = None
+        self.bts_layers = None
+        self.optimizer = None
+        self.losses = None
+        self.metrics = None
+        self.debug = False
+        self.mode = 'test'
+        self.smart_derivatives = None
+        # device state
+        self._arena = None
+        self.use_graph = os.environ.get("DNPY_B200_GRAPH", "1") != "0"
+        self._graphs = {}
+        self._pending_flags = []
+
+    # ------------------------------------------------------------------ build
+    def build(self, l_in, l_out, optimizer, losses, metrics, debug=False, smart_derivatives=False):
+        self.l_in = l_in
+        self.l_out = l_out
+        self.fts_layers = []
+        self.bts_layers = []
+        self.optimizer = optimizer
+        self.losses = losses
+        self.metrics = metrics
+        self.debug = debug
+        self.smart_derivatives = smart_derivatives
+        self.bts()
+        self.fts()
+        self.initialize()
+        self._arena = None
+        self._graphs = {}
+
+    def fts(self):
+        self.fts_layers = list(self.bts_layers)
+        self.fts_layers.reverse()
+
+    def bts(self):
+        self.bts_layers = []
+        temp, done = set(), set()
+        for node in self.l_out:
+            if id(node) not in done:
+                _visit(node, temp, done, self.bts_layers)
+        assert not temp
+
+    def initialize(self):
+        """net.py:277-293: initialise in forward order (this fixes the order in which the global
+        NumPy stream is consumed, hence the weights), then wire the CE(Softmax) shortcut."""
+        batch_size = self.fts_layers[0].batch_size
+        for l in self.fts_layers:
+            l.debug = self.debug
+            l.initialize(optimizer=self.optimizer)
+            l.batch_size = batch_size
+        if self.smart_derivatives:
+            for l in self.l_out:
+                for lo in self.losses:           # all (output, loss) pairs, like the reference (Q19)
+                    if isinstance(l, Softmax) and isinstance(lo, CrossEntropy):
+                        print("[INFO] Using derivative speed-up: 'CrossEntropy(Softmax(z))'")
+                        lo.softmax_output = True
+                        l.ce_loss = True
+
+    # ------------------------------------------------------------------ arenas
+    def _trainable(self):
+        out = []
+        for l in self.bts_layers:
+            for k in l.params.keys():
+                if k in l.grads:
+                    out.append((l, k))
+        return out
+
+    def _bind_arenas(self):
+        """Lay every trainable tensor out in flat fp32 arenas: params P, grads G and the optimizer
+        state (V and/or S).  Idempotent; re-run after ``set_params`` replaced the dicts."""
+        require_cuda()
+        slots = self._trainable()
+        if self._arena is not None and self._arena["keys"] == [(id(l.params[k]), id(l.grads[k])) for l, k in slots]:
+            return self._arena
+        t = torch()
+        offs, pos = [], 0
+        for l, k in slots:
+            offs.append(pos)
+            pos += (l.params[k].size + _ALIGN - 1) // _ALIGN * _ALIGN
+        total = max(pos, _ALIGN)
+        P, G = dev_zeros((total,)), dev_zeros((total,))
+        states = {}
+        kind = type(self.optimizer).__name__
+        for name in ("V", "S"):
+            if hasattr(self.optimizer, name):
+                states[name] = dev_zeros((total,))
+        uniform = True
+        for (l, k), o in zip(slots, offs):
+            n = l.params[k].size
+            shape = l.params[k].shape
+            l.params[k].bind(P[o:o + n].view(*shape))
+            l.grads[k].bind(G[o:o + n].view(*shape))
+            opt = l.optimizer
+            if opt is None or type(opt).__name__ != kind:
+                uniform = False
+                continue
+            for name, arena in states.items():
+                st = getattr(opt, name)
+                if k in st:
+                    st[k].bind(arena[o:o + n].view(*shape))
+        self._arena = dict(P=P, G=G, states=states, total=total, uniform=uniform,
+                           keys=[(id(l.params[k]), id(l.grads[k])) for l, k in slots], slots=slots)
+        self._graphs = {}
+        return self._arena
+
+    # ------------------------------------------------------------------ step primitives (net.py:295-364)
+    def do_delta(self, deltas):
+        for i in range(len(self.l_out)):
+            self.l_out[i].delta = deltas[i]
+
+    def reset_grads(self):
+        if self._device_ready():
+            a = self._bind_arenas()
+            _lib.call("dnb_fill_f32", a["G"].data_ptr(), a["total"], 0.0, stream_ptr())
+            for l, k in a["slots"]:
+                l.grads[k].written()
+            bound = {id(l.grads[k]) for l, k in a["slots"]}
+            for l in self.fts_layers:
+                for k in l.grads.keys():
+                    if id(l.grads[k]) not in bound:
+                        l.grads[k].fill(0.0)
+            return
+        for l in self.fts_layers:
+            for k in l.grads.keys():
+                l.grads[k].fill(0.0)
+
+    def feed_input(self, x):
+        for j in range(len(self.l_in)):
+            self.l_in[j].output = x[j]
+
+    def forward(self):
+        for l in self.fts_layers:
+            l.forward()
+            if self.debug:
+                l.print_stats()
+
+    def backward(self):
+        for l in self.bts_layers:
+            l.backward()
+            if self.debug:
+                l.print_stats()
+        if config.world > 1:
+            from . import parallel
+            parallel.allreduce_grads(self)
+
+    def apply_grads(self):
+        a = self._bind_arenas() if self._device_ready() else None
+        if a is not None and a["uniform"] and not any(l.frozen for l in self.bts_layers):
+            self._apply_fused(a)
+            return
+        for l in self.bts_layers:
+            if not l.frozen:
+                l.optimizer.apply(l.params, l.grads)
+
+    def _apply_fused(self, a):
+        """One optimizer launch over the whole arena: legal because every layer's optimizer copy
+        carries identical hyper-parameters (base.py:34)."""
+        o = self.optimizer
+        p, g, n = a["P"].data_ptr(), a["G"].data_ptr(), a["total"]
+        if isinstance(o, Adam):
+            if o.bias_correction:
+                raise TypeError("unsupported operand type(s) for ** or pow(): 'float' and 'NoneType'")
+            o.launch(p, g, a["states"]["V"].data_ptr(), a["states"]["S"].data_ptr(), n)
+        elif isinstance(o, RMSProp):
+            o.launch(p, g, a["states"]["S"].data_ptr(), n)
+        elif isinstance(o, SGD):
+            if o.bias_correction and o.momentum != 0.0:
+                raise TypeError("unsupported operand type(s) for ** or pow(): 'float' and 'NoneType'")
+            o.launch(p, g, a["states"]["V"].data_ptr(), n)
+        else:
+            raise NotImplementedError(type(o).__name__)
+        for l, k in a["slots"]:
+            l.params[k].written()
+
+    def compute_losses(self, y_target):
+        losses, deltas = [], []
+        for i in range(len(self.losses)):
+            y_pred_i = self.l_out[i].output
+            y_target_i = y_target[i]
+            loss = self.losses[i].compute_loss(y_pred_i, y_target_i)
+            losses.append(loss)
+            delta = self.losses[i].compute_delta(y_pred_i, y_target_i)
+            deltas.append(delta)
+            self._raise_on_flags(loss, self.losses[i], y_pred_i, y_target_i)
+        return losses, deltas
+
+    @staticmethod
+    def _raise_on_flags(loss, loss_obj, y_pred, y_target, flags=None):
+        """net.py:342-350, same messages."""
+        if math.isnan(loss):
+            raise ValueError("NaNs in the loss function")
+        elif math.isinf(loss):
+            raise ValueError("Inf in the loss function")
+        if flags is None:
+            memo = loss_obj._memo
+            flags = int(memo[2][1].item()) if memo is not None else 0
+        if flags & 4:
+            raise ValueError("NaNs in the delta")
+        elif flags & 8:
+            raise ValueError("Info in the delta")
+
+    def compute_metrics(self, y_target):
+        metrics = []
+        for i in range(len(self.l_out)):
+            row = []
+            for me in self.metrics[i]:
+                row.append(me.compute_metric(self.l_out[i].output, y_target[i]))
+            metrics.append(row)
+        return metrics
+
+    def set_mode(self, mode="train"):
+        self.mode = mode
+        for l in self.fts_layers:
+            if self.mode == "train":
+                l.training = True
+            elif self.mode == "test":
+                l.training = False
+            else:
+                raise KeyError("Unknown mode")
+
+    # ------------------------------------------------------------------ fused training step
+    def _device_ready(self):
+        t = torch()
+        return t.cuda.is_available()
+
+    def train_step(self, x_mb, y_mb):
+        """One iteration of net.py:176-195 without host synchronisation.  Returns the per-loss
+        device tensors ``[loss, flags]``; nothing is read back here."""
+        self.feed_input(x_mb)
+        self.forward()
+        outs, deltas = [], []
+        for i, lo in enumerate(self.losses):
+            outs.append(lo.result_tensor(self.l_out[i].output, y_mb[i]))
+            deltas.append(lo.compute_delta(self.l_out[i].output, y_mb[i]))
+        self.reset_grads()
+        self.do_delta(deltas)
+        self.backward()
+        self.apply_grads()
+        return outs
+
+    # ------------------------------------------------------------------ fit / evaluate
+    def _format_eval(self, losses=None, metrics=None):
+        str_l, str_m = [], []
+        if losses is not None:
+            assert len(self.l_out) == len(self.losses) == len(losses)
+            for i in range(len(self.losses)):
+                str_l += ["{}={:.5f}".format(self.losses[i].name, float(losses[i]))]
+        if metrics is not None:
+            assert len(self.l_out) == len(metrics)
+            for i in range(len(self.l_out)):
+                tmp = []
+                for j in range(len(self.metrics[i])):
+                    tmp += ["{}={:.5f}".format(self.metrics[i][j].name, float(metrics[i][j]))]
+                str_m += ["{}: ({})".format(self.l_out[i].name, ", ".join(tmp))]
+        return [str_l, str_m]
+
+    def get_minibatch(self, x_train, y_train, batch_i, batch_size):
+        """net.py:115-125, then this rank's row block when the batch is sharded."""
+        x_mb, y_mb = [], []
+        lo = batch_i * batch_size
+        for j in range(len(self.l_in)):
+            x_mb += [x_train[j][lo:lo + batch_size]]
+            y_mb += [y_train[j][lo:lo + batch_size]]
+        if config.world > 1:
+            from . import parallel
+            x_mb = [parallel.shard_rows(a) for a in x_mb]
+            y_mb = [parallel.shard_rows(a) for a in y_mb]
+        return x_mb, y_mb
+
+    def fit(self, x_train, y_train, batch_size, epochs, x_test=None, y_test=None, evaluate_epoch=True, print_rate=1):
+        assert isinstance(x_train, list)
+        assert isinstance(y_train, list)
+        assert isinstance(x_test, list) or x_test is None
+        assert isinstance(y_test, list) or y_test is None
+        assert len(self.l_in) == len(x_train)
+        assert len(self.l_out) == len(self.losses) == len(y_train)
+        check_datasets(x_train, y_train, x_test, y_test)
+
+        batch_size = int(batch_size)
+        num_samples = len(x_train[0])
+        num_batches = int(num_samples / batch_size)
+        verbose = config.rank == 0
+
+        for i in range(epochs):
+            printing = (i % print_rate) == 0
+            if printing and verbose:
+                print(f"Epoch {i+1}/{epochs}...")
+            if self.mode != "train":
+                self.set_mode('train')
+            for b in range(num_batches):
+                x_mb, y_mb = self.get_minibatch(x_train, y_train, b, batch_size)
+                if printing:
+                    # reference order: forward, losses (+guards), metrics, print, then the update
+                    self.feed_input(x_mb)
+                    self.forward()
+                    b_losses, b_deltas = self.compute_losses(y_target=y_mb)
+                    b_metrics = self.compute_metrics(y_target=y_mb)
+                    str_eval = self._format_eval(b_losses, b_metrics)
+                    if verbose:
+                        print(f"\t - Batch {b+1}/{num_batches} - Losses[{', '.join(str_eval[0])}]; Metrics[{'; '.join(str_eval[1])}]")
+                    self.reset_grads()
+                    self.do_delta(b_deltas)
+                    self.backward()
+                    self.apply_grads()
+                else:
+                    self._pending_flags.append(self.train_step(x_mb, y_mb))
+                    if len(self._pending_flags) >= 64:
+                        self._check_pending()
+            self._check_pending()
+            if evaluate_epoch and printing:
+                self.set_mode('test')
+                lo, me = self.evaluate(x_train, y_train, batch_size=1)
+                str_eval = self._format_eval(lo, me)
+                if verbose:
+                    print(f"\t - Training losses[{', '.join(str_eval[0])}]; Training metrics[{'; '.join(str_eval[1])}];")
+                if x_test is not None and y_test is not None:
+                    lo, me = self.evaluate(x_test, y_test, batch_size=1)
+                    str_eval = self._format_eval(lo, me)
+                    if verbose:
+                        print(f"\t - Validation losses[{', '.join(str_eval[0])}]; Validation metrics[{'; '.join(str_eval[1])}];")
+
+    def _check_pending(self):
+        """Deferred NaN/Inf guard for the non-printing steps (one sync per 64 steps, not per step)."""
+        pend, self._pending_flags = self._pending_flags, []
+        for outs in pend:
+            for o in outs:
+                v = o.tolist()
+                self._raise_on_flags(v[0], None, None, None, flags=int(v[1]))
+
+    def evaluate(self, x_test, y_test, batch_size=1):
+        assert isinstance(x_test, list)
+        assert isinstance(y_test, list)
+        assert len(self.l_in) == len(x_test)
+        assert len(self.l_out) == len(self.losses) == len(y_test)
+        check_datasets(None, None, x_test, y_test)
+        num_samples = len(x_test[0])
+        num_batches = int(num_samples / batch_size)
+        assert batch_size <= num_samples
+        if self.mode != "test":
+            print("[WARNING] Setting net mode to 'test'")
+            self.set_mode('test')
+        losses, metrics = [], []
+        for b in range(num_batches):
+            x_mb, y_mb = [], []
+            lo_i = b * batch_size
+            for j in range(len(self.l_in)):
+                x_mb += [x_test[j][lo_i:lo_i + batch_size]]
+                y_mb += [y_test[j][lo_i:lo_i + batch_size]]
+            self.feed_input(x_mb)
+            self.forward()
+            lo, de = self.compute_losses(y_target=y_mb)
+            losses.append(lo)
+            metrics.append(self.compute_metrics(y_target=y_mb))
+        losses = np.array(losses)
+        metrics = [np.array(row) for row in list(zip(*metrics))]
+        losses = np.mean(losses, axis=0)
+        metrics = [np.mean(me, axis=0) for me in metrics]
+        assert len(losses) == len(self.losses)
+        assert len(metrics) == len(self.losses)
+        return losses, metrics
+
+    # ------------------------------------------------------------------ summary / params / checkpoint
+    def summary(self):
+        total_params = total_tr = total_notr = 0
+        width = 75
+        print('=' * width)
+        print("Model summary")
+        print('=' * width)
+        print("{:<20} {:<20} {:<20} {:<10}".format("Layer (type)", "Input Shape/s", "Output Shape", "Param #"))
+        print('-' * width)
+        for l in self.fts_layers:
+            ishapes = [p.oshape for p in l.parents]
+            ishapes = ishapes if len(ishapes) > 1 else l.oshape
+            tr, notr = l.get_num_params()
+            total_tr += tr
+            total_notr += notr
+            total_params += tr + notr
+            print("{:<20} {:<20} {:<20} {:<10}".format(str(l.name), str(ishapes), str(l.oshape), str(tr + notr)))
+        print('-' * width)
+        print('Total params: {:,}'.format(total_params))
+        print('Trainable params: {:,}'.format(total_tr))
+        print('Non-trainable params: {:,}'.format(total_notr))
+        print('-' * width)
+        print('')
+
+    def get_params(self, only_trainable=False):
+        """net.py:403-411 — host (float64 ndarray) copies, D2H at the boundary."""
+        params = []
+        for l in self.fts_layers:
+            params.append({k: np.array(np.asarray(v)) for k, v in l.params.items()
+                           if (not only_trainable) or (k in l.grads)})
+        return params
+
+    def set_params(self, params, only_trainable=False):
+        """net.py:413-422 — values are uploaded into the existing (arena) slots."""
+        assert len(self.fts_layers) == len(params)
+        for i, l in enumerate(self.fts_layers):
+            if only_trainable:
+                for k in l.params.keys():
+                    if k in params[i]:
+                        l.params[k] = self._fit_shape(l.params[k], params[i][k])
+            else:
+                assert len(l.params) == len(params[i])
+                for k, v in params[i].items():
+                    l.params[k] = self._fit_shape(l.params.get(k), v)
+
+    @staticmethod
+    def _fit_shape(cur, value):
+        v = np.asarray(value)
+        if cur is not None and tuple(v.shape) != cur.shape and v.size == cur.size:
+            v = v.reshape(cur.shape)       # e.g. BatchNorm moving stats pickled as (1, *oshape) by the reference
+        return v
+
+    def get_grads(self):
+        return [{k: np.array(np.asarray(v)) for k, v in l.grads.items()} for l in self.fts_layers]
+
+    def set_grads(self, grads):
+        assert len(self.fts_layers) == len(grads)
+        for i, l in enumerate(self.fts_layers):
+            assert len(l.grads) == len(grads[i])
+            for k, v in grads[i].items():
+                l.grads[k] = self._fit_shape(l.grads.get(k), v)
+
+    def load(self, filename):
+        with open(filename, 'rb') as fp:
+            data = pickle.load(fp)
+        self.set_params(data['params'])
+        grads = data.get('grads')
+        if grads:
+            self.set_grads(grads)
+        print("Model loaded!")
+
+    def save(self, filename, save_grads=False):
+        """Same pickle layout as net.py:449-460 (dicts of float64 ndarrays): files are interchangeable
+        with the reference's."""
+        data = {'params': self.get_params()}
+        if save_grads:
+            data['grads'] = self.get_grads()
+        with open(filename, 'wb') as fp:
+            pickle.dump(data, fp)
+        print("Model saved!")

@@ -1,0 +1,58 @@
+"""Process-wide execution settings of the backend (one process drives one GPU).
+
+``math``          "fp32" — SIMT fp32 FMA kernels, parity rel 1e-5 vs the float64 reference;
+                  "tf32" — tcgen05 tensor-core kernels for Dense / Conv2D / Pointwise (fp32
+                  storage, TF32 operands, fp32 accumulation in TMEM), parity rel 2e-2.
+                  Chosen once, before ``Net.build`` (env DNPY_B200_MATH or ``set_math``).
+``maxpool_route`` "literal" (default) reproduces dnpy/layers/pooling.py:95 exactly;
+                  "per_sample" is the intended scatter-add.
+``world``/``rank`` data-parallel layout (set by dnpy_b200.parallel.init); gradients that the
+                  reference averages over the batch are scaled by 1/world so that the all-reduced
+                  sum equals the single-process value.
+"""
+import os
+
+from . import _lib
+
+
+class _Config:
+    def __init__(self):
+        self.math = _lib.MATH_TF32 if os.environ.get("DNPY_B200_MATH", "fp32").lower() == "tf32" else _lib.MATH_FP32
+        self.maxpool_route = (_lib.ROUTE_PER_SAMPLE if os.environ.get("DNPY_B200_MAXPOOL", "literal").lower() == "per_sample"
+                              else _lib.ROUTE_LITERAL)
+        self.world = 1
+        self.rank = 0
+
+    @property
+    def inv_world(self):
+        return 1.0 / float(self.world)
+
+    @property
+    def reg_scale(self):
+        # regulariser terms are batch independent: contribute 1/world per rank so the sum is exact
+        return 1.0 / float(self.world)
+
+
+config = _Config()
+
+
+def set_math(mode):
+    mode = str(mode).lower()
+    if mode not in ("fp32", "tf32"):
+        raise ValueError("math must be 'fp32' or 'tf32'")
+    config.math = _lib.MATH_TF32 if mode == "tf32" else _lib.MATH_FP32
+
+
+def get_math():
+    return "tf32" if config.math == _lib.MATH_TF32 else "fp32"
+
+
+def set_maxpool_route(route):
+    route = str(route).lower()
+    if route not in ("literal", "per_sample"):
+        raise ValueError("maxpool route must be 'literal' or 'per_sample'")
+    config.maxpool_route = _lib.ROUTE_PER_SAMPLE if route == "per_sample" else _lib.ROUTE_LITERAL
+
+
+def get_maxpool_route():
+    return "per_sample" if config.maxpool_route == _lib.ROUTE_PER_SAMPLE else "literal"

@@ -1,0 +1,197 @@
+/*
+ * dnpy_b200 — C ABI of the B200 (sm_100a) execution backend for the dnpy hot path.
+ *
+ * The reference (salvacarrion/dnpy) is pure Python/NumPy and has no FFI of its
+ * own; the boundary it exposes is the duck-typed Layer / Loss / Optimizer
+ * protocol (dnpy/layers/base.py:6-41, dnpy/losses.py:4-14,
+ * dnpy/optimizers.py:4-12) driven by Net.fit (dnpy/net.py:174-195).  Each entry
+ * point below is what a ctypes binding for one of those methods calls; the
+ * reference method it replaces is cited next to it (paths relative to the
+ * reference root).  INTEGRATION.md shows the reference-side stub for each.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to dense row-major fp32 (int32 where
+ *     stated), NCHW for images, exactly the reference's array layouts;
+ *   - no hidden allocation, no host synchronisation: work is enqueued on
+ *     `stream` (a cudaStream_t passed as void*; NULL = legacy default stream),
+ *     so a whole training step can be captured in a CUDA graph;
+ *   - workspaces are caller-provided; `*_ws_bytes` functions return the size;
+ *   - return value: 0 on success, <0 on error (DNB_ERR_*).  The message is
+ *     available from dnb_last_error() (thread-local).  The Python host maps
+ *     DNB_ERR_INVALID -> ValueError, DNB_ERR_UNSUPPORTED -> NotImplementedError,
+ *     DNB_ERR_CUDA -> RuntimeError — the reference's own exception types;
+ *   - `math`: DNB_MATH_FP32 = SIMT fp32 FMA path (parity rel 1e-5 vs the float64
+ *     reference); DNB_MATH_TF32 = tcgen05 tensor-core path, fp32 storage, TF32
+ *     operands, fp32 accumulate in TMEM (parity rel 2e-2).  Chosen once per net.
+ *   - there is NO CPU fallback anywhere behind this ABI.
+ */
+#ifndef DNPY_B200_H
+#define DNPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DNB_OK               0
+#define DNB_ERR_INVALID     (-1)
+#define DNB_ERR_CUDA        (-2)
+#define DNB_ERR_UNSUPPORTED (-3)
+
+#define DNB_MATH_FP32 0
+#define DNB_MATH_TF32 1
+
+/* MaxPool2D.backward batch routing (dnpy/layers/pooling.py:95) */
+#define DNB_ROUTE_LITERAL    0   /* every sample's delta lands in sample 0, last sample wins */
+#define DNB_ROUTE_PER_SAMPLE 1   /* intended per-sample scatter-add (== literal when B == 1) */
+
+typedef void* dnb_stream_t;
+
+/* Regulariser term lambda_l1*sign(p) + lambda_l2*2p (dnpy/regularizers.py:25-53); zeros = none. */
+typedef struct { float l1; float l2; } dnb_reg_t;
+
+/* 2-D window geometry shared by conv and pool (dnpy/utils.py:52-109 computes these on the host). */
+typedef struct {
+    int B, C, H, W;        /* input  (batch, channels, height, width)            */
+    int F, OH, OW;         /* output (filters/channels, height, width)           */
+    int kh, kw;            /* window                                             */
+    int sy, sx;            /* strides                                            */
+    int pt, pb, pl, pr;    /* zero padding: top, bottom, left, right             */
+} dnb_win_t;
+
+/* ---- library ---------------------------------------------------------------- */
+int         dnb_version(void);
+const char* dnb_last_error(void);
+/* sm count, compute capability, whether the tcgen05 path is usable on this device */
+int dnb_device_query(int* sm_count, int* cc_major, int* cc_minor, int* has_tcgen05);
+
+/* ---- Net.reset_grads (net.py:299-302) / generic fills ----------------------- */
+int dnb_fill_f32(float* p, size_t n, float value, dnb_stream_t stream);
+int dnb_fill_i32(int32_t* p, size_t n, int32_t value, dnb_stream_t stream);
+
+/* ---- Dense (layers/core.py:116-135) ----------------------------------------- */
+/* y[B,out] = x[B,in] @ w[in,out] + b[out] */
+int dnb_dense_fwd(const float* x, const float* w, const float* b, float* y,
+                  int B, int in, int out, int math, dnb_stream_t stream);
+/* dx[B,in] = dy @ w^T (dx may be NULL);  gw += (x^T @ dy + reg_w'(w)) * inv_m;
+ * gb += (sum_b dy + reg_b'(b)) * inv_m.  inv_m = 1/B single-GPU, 1/B_global when
+ * the batch is sharded (regulariser then scaled by reg_scale = 1/world so the
+ * all-reduced sum matches the single-process value). */
+int dnb_dense_bwd(const float* x, const float* w, const float* b, const float* dy,
+                  float* dx, float* gw, float* gb, int B, int in, int out, float inv_m,
+                  dnb_reg_t reg_w, dnb_reg_t reg_b, float reg_scale, int math, dnb_stream_t stream);
+
+/* ---- Conv2D / PointwiseConv2D (layers/convolution.py:193-273, 276-284) ------ */
+size_t dnb_conv2d_ws_bytes(const dnb_win_t* g, int math);
+/* y[B,F,OH,OW] = sum_{c,i,j} xpad * w[F,C,kh,kw] + (C*kh*kw) * b[F]   (bias quirk Q1) */
+int dnb_conv2d_fwd(const float* x, const float* w, const float* b, float* y,
+                   const dnb_win_t* g, void* ws, int math, dnb_stream_t stream);
+/* dx[B,C,H,W] (cropped) ; gw += mean_b-sum_yx(dy * xpad) + OH*OW*reg_w'(w)*reg_scale ;
+ * gb += inv_m * sum dy + OH*OW*reg_b'(b)*reg_scale  (Q2).  dx may be NULL. */
+int dnb_conv2d_bwd(const float* x, const float* w, const float* b, const float* dy,
+                   float* dx, float* gw, float* gb, const dnb_win_t* g, float inv_m,
+                   dnb_reg_t reg_w, dnb_reg_t reg_b, float reg_scale,
+                   void* ws, int math, dnb_stream_t stream);
+
+/* ---- DepthwiseConv2D (layers/convolution.py:323-388); w is [C,1,kh,kw] ------- */
+int dnb_dwconv2d_fwd(const float* x, const float* w, const float* b, float* y,
+                     const dnb_win_t* g, dnb_stream_t stream);
+int dnb_dwconv2d_bwd(const float* x, const float* w, const float* b, const float* dy,
+                     float* dx, float* gw, float* gb, const dnb_win_t* g, float inv_m,
+                     dnb_reg_t reg_b, float reg_scale, dnb_stream_t stream);
+
+/* ---- MaxPool2D / AvgPool2D (layers/pooling.py:43-99, 118-174) --------------- */
+/* idx[B,C,OH,OW] int32: first max of the zero-padded row-major window (bit-exact vs np.argmax) */
+int dnb_maxpool2d_fwd(const float* x, float* y, int32_t* idx, const dnb_win_t* g, dnb_stream_t stream);
+size_t dnb_maxpool2d_bwd_ws_bytes(const dnb_win_t* g, int route);
+int dnb_maxpool2d_bwd(const float* dy, const int32_t* idx, float* dx, const dnb_win_t* g,
+                      int route, void* ws, dnb_stream_t stream);
+int dnb_avgpool2d_fwd(const float* x, float* y, const dnb_win_t* g, dnb_stream_t stream);
+int dnb_avgpool2d_bwd(const float* dy, float* dx, const dnb_win_t* g, dnb_stream_t stream);
+
+/* ---- Activations (layers/activations.py) ------------------------------------ */
+int dnb_leakyrelu_fwd(const float* x, float* y, size_t n, float alpha, dnb_stream_t stream);      /* :17-19 */
+int dnb_leakyrelu_bwd(const float* x, const float* dy, float* dx, size_t n, float alpha, dnb_stream_t stream); /* :21-22 */
+/* alpha[n_feat] broadcast over the batch; galpha += inv_m * sum_b dy*(x<=0)        :59-66 */
+int dnb_prelu_fwd(const float* x, const float* alpha, float* y, int B, size_t n_feat, dnb_stream_t stream);
+int dnb_prelu_bwd(const float* x, const float* alpha, const float* dy, float* dx, float* galpha,
+                  int B, size_t n_feat, float inv_m, dnb_stream_t stream);
+int dnb_sigmoid_fwd(const float* x, float* y, size_t n, dnb_stream_t stream);                      /* :77-78 */
+int dnb_sigmoid_bwd(const float* y, const float* dy, float* dx, size_t n, dnb_stream_t stream);    /* :80-81 */
+int dnb_tanh_fwd(const float* x, float* y, size_t n, dnb_stream_t stream);                         /* :92-95 */
+int dnb_tanh_bwd(const float* y, const float* dy, float* dx, size_t n, dnb_stream_t stream);       /* :97-98 */
+int dnb_softmax_fwd(const float* x, float* y, int B, int n, int stable, dnb_stream_t stream);      /* :116-124 */
+int dnb_softmax_bwd(const float* y, const float* dy, float* dx, int B, int n, dnb_stream_t stream);/* :130-135 */
+int dnb_logsoftmax_fwd(const float* x, float* y, int B, int n, int stable, dnb_stream_t stream);   /* :152-160 */
+
+/* ---- Dropout / BatchNorm / Add (layers/regularization.py, merge.py) --------- */
+/* y = x * gate (training; gate drawn on the host from NumPy's global stream for bit-exact
+ * masks) — the same kernel serves Dropout.backward (regularization.py:17-25) */
+int dnb_mul(const float* a, const float* b, float* y, size_t n, dnb_stream_t stream);
+int dnb_scale(const float* x, float* y, size_t n, float s, dnb_stream_t stream);
+/* y = sum of n_in inputs (merge.py:13-16 with np.add) */
+int dnb_add_n(const float* const* xs, int n_in, float* y, size_t n, dnb_stream_t stream);
+/* BatchNorm over axis 0 of x[B, n_feat] (regularization.py:94-136).  training: computes
+ * mu/var (biased) into save_mu/save_std (std = sqrt(var+eps)) and updates moving_* in place
+ * with `momentum`; test: uses moving_*.  stat_sync, when non-NULL, is unused here (reserved
+ * for the host-driven cross-GPU statistics exchange). */
+int dnb_batchnorm_fwd(const float* x, const float* gamma, const float* beta,
+                      float* moving_mu, float* moving_var, float* save_mu, float* save_std,
+                      float* y, int B, size_t n_feat, float momentum, float eps, int training,
+                      dnb_stream_t stream);
+/* literal backward (Q7): ggamma += sum_b dy*mu ; gbeta += sum_b dy ;
+ * dx = (1/m) * std * (m*dy*gamma - sum_b(dy*gamma) - xn * sum_b(dy*gamma*xn)) */
+int dnb_batchnorm_bwd(const float* x, const float* gamma, const float* save_mu, const float* save_std,
+                      const float* dy, float* dx, float* ggamma, float* gbeta,
+                      int B, size_t n_feat, dnb_stream_t stream);
+
+/* ---- Embedding (layers/core.py:54-65) --------------------------------------- */
+int dnb_embedding_fwd(const int32_t* idx, const float* w, float* y, int B, int L, int V, int D, dnb_stream_t stream);
+/* gw[v] += mean_b(dy)[l*] where (b*,l*) is the LAST row-major position with idx == v (Q15).
+ * ws: (V + L*D) * 4 bytes. */
+size_t dnb_embedding_bwd_ws_bytes(int L, int V, int D);
+int dnb_embedding_bwd(const int32_t* idx, const float* dy, float* gw, int B, int L, int V, int D,
+                      float inv_m, void* ws, dnb_stream_t stream);
+
+/* ---- SimpleRNN (layers/recurrent.py:12-23, 153-266) ------------------------- */
+/* states[B,T,H]: h_t = tanh(h_{t-1} waa^T + x_t wax^T + ba), h_0 = 0; y[B,H] = states[:, T-1] */
+int dnb_rnn_fwd(const float* x, const float* waa, const float* wax, const float* ba,
+                float* states, float* y, int B, int T, int D, int H, dnb_stream_t stream);
+/* literal truncated BPTT (Q16): gradients are batch SUMS; dx[B,T,D] */
+int dnb_rnn_bwd(const float* x, const float* states, const float* dy, const float* waa, const float* wax,
+                float* dx, float* gwaa, float* gwax, float* gba,
+                int B, int T, int D, int H, int trunc, dnb_stream_t stream);
+
+/* ---- Losses (dnpy/losses.py) + the NaN/Inf guard of net.py:342-350 ---------- */
+/* out[0] = loss, out[1] = flag bits: 1 NaN loss, 2 Inf loss, 4 NaN delta, 8 Inf delta.
+ * Deltas are never divided by the batch (Q17).  loss_scale = 1/B (1/B_global when sharded).
+ * ws: dnb_loss_ws_bytes(B) bytes. */
+size_t dnb_loss_ws_bytes(int B);
+int dnb_loss_ce(const float* p, const float* t, float* delta, float* out, int B, int n,
+                int softmax_output, float loss_scale, void* ws, dnb_stream_t stream);   /* :82-94 */
+int dnb_loss_bce(const float* p, const float* t, float* delta, float* out, int B, int n,
+                 float loss_scale, void* ws, dnb_stream_t stream);                        /* :65-73 */
+int dnb_loss_mse(const float* p, const float* t, float* delta, float* out, int B, int n,
+                 float loss_scale, void* ws, dnb_stream_t stream);                        /* :22-26 */
+/* metrics.py:44-80: out[0] = number of correct rows (host divides) */
+int dnb_metric_categorical(const float* p, const float* t, float* out, int B, int n, dnb_stream_t stream);
+int dnb_metric_binary(const float* p, const float* t, float* out, int B, int n, float thr, dnb_stream_t stream);
+
+/* ---- Optimizers over the flat parameter arena (dnpy/optimizers.py) ----------- */
+/* grad_scale multiplies g first (1 single-GPU; folds the data-parallel 1/N where needed). */
+int dnb_opt_adam(float* p, const float* g, float* v, float* s, size_t n, float lr,
+                 float beta1, float beta2, float eps, dnb_stream_t stream);               /* :106-126 */
+int dnb_opt_rmsprop(float* p, const float* g, float* s, size_t n, float lr, float rho, float eps,
+                    dnb_stream_t stream);                                                  /* :73-84 */
+int dnb_opt_sgd(float* p, const float* g, float* v, size_t n, float lr, float momentum, int nesterov,
+                dnb_stream_t stream);                                                      /* :31-55 */
+
+/* ---- Tensor-core GEMM exposed for testing: C[M,N] = A[M,K] @ B[N,K]^T (TF32 tcgen05) */
+int dnb_gemm_tf32_nt(const float* A, const float* Bm, float* C, int M, int N, int K, dnb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DNPY_B200_H */

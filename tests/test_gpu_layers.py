@@ -1,0 +1,197 @@
+"""GPU parity tests proper (-m gpu): every §8a row through the dnpy-API layer classes -> ctypes ->
+C ABI -> CUDA kernels, compared with (a) the fixtures recorded from the real reference and (b) the
+oracle on larger seeded inputs.
+
+Tolerances (FP32 path, math="fp32"): rel 1e-5 in the tensor-level metric of conftest.rel_err
+(max|a-b| / max|b|); integer work (pool argmax, embedding gather, dropout masks) is bit-exact.
+"""
+import numpy as np
+import pytest
+
+from tests.conftest import rel_err, has_cuda
+from tests.golden import cases, drive
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-5
+
+
+@pytest.fixture(autouse=True)
+def _fp32_mode():
+    import dnpy_b200
+    dnpy_b200.set_math("fp32")
+    dnpy_b200.set_maxpool_route("literal")
+    yield
+
+
+def test_native_library_is_the_compute_path():
+    import torch
+    from dnpy_b200 import _lib
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    lib = _lib.load()
+    import ctypes as C
+    sm, maj, mnr, tc = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    _lib.check(lib.dnb_device_query(C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(tc)))
+    assert sm.value > 0 and maj.value >= 9
+    loaded = open("/proc/self/maps").read()
+    assert "libdnpy_b200.so" in loaded
+
+
+@pytest.mark.parametrize("case", cases.LAYER_CASES, ids=[c["name"] for c in cases.LAYER_CASES])
+def test_layer_cases_vs_reference_fixtures(case, golden, ns):
+    g = golden("layer_cases.npz")
+    rec = drive.run_layer_case(ns, case)
+    n = case["name"]
+    for k in [k.split("/", 1)[1] for k in g.files if k.startswith(n + "/")]:
+        want = g[f"{n}/{k}"]
+        if k.startswith(("x", "pin_", "delta")):
+            continue
+        got = np.asarray(rec[k])
+        if k == "idx":
+            assert np.array_equal(got, want), "argmax indices must be bit-exact"
+        elif case["kind"] == "Embedding" and k == "out":
+            assert np.array_equal(got.astype(np.float32), want.astype(np.float32)), "gather must be bit-exact"
+        elif case["kind"] == "Dropout" and k == "out":
+            assert np.array_equal(got == 0, want == 0), "dropout mask must be bit-exact"
+            assert rel_err(got, want) <= TOL32
+        else:
+            assert rel_err(got.reshape(want.shape), want) <= TOL32, (k, rel_err(got.reshape(want.shape), want))
+
+
+@pytest.mark.parametrize("case", cases.LOSS_CASES, ids=[c["name"] for c in cases.LOSS_CASES])
+def test_loss_cases(case, golden, ns):
+    g = golden("loss_cases.npz")
+    rec = drive.run_loss_case(ns, case)
+    n = case["name"]
+    assert abs(float(rec["loss"]) - float(g[f"{n}/loss"])) <= TOL32 * max(1.0, abs(float(g[f"{n}/loss"])))
+    assert rel_err(rec["delta"], g[f"{n}/delta"]) <= TOL32
+
+
+@pytest.mark.parametrize("case", cases.OPT_CASES, ids=[c["name"] for c in cases.OPT_CASES])
+def test_opt_cases(case, golden, ns):
+    g = golden("opt_cases.npz")
+    rec = drive.run_opt_case(ns, case)
+    n = case["name"]
+    for k in ("w1", "b1", "frozen_stat"):
+        assert rel_err(rec[f"p_{k}"], g[f"{n}/p_{k}"]) <= TOL32, k
+
+
+def test_reference_unit_kats_exact(golden, ns):
+    """The reference's own unit tests (all-ones kernels, integer images): exact ``==`` like the
+    reference asserts (tests/coverage/test_layers.py:78,82)."""
+    import json
+    L = ns.L
+    g = golden("ref_unit_kat.npz")
+    for i in range(int(g["n"])):
+        cfg = json.loads(str(g[f"{i}_cfg"]))
+        kind = cfg["kind"]
+        if kind == "Softmax":
+            continue
+        l0 = L.Input(shape=tuple(cfg["in_shape"]))
+        l0.output = g[f"{i}_x"]
+        if kind == "Conv2D":
+            l1 = L.Conv2D(l0, cfg["filters"], kernel_size=tuple(cfg["kernel_size"][-2:]), strides=tuple(cfg["strides"]),
+                          padding=cfg["padding"], kernel_initializer=ns.init.Constant(fill_value=1))
+        elif kind == "DepthwiseConv2D":
+            l1 = L.DepthwiseConv2D(l0, kernel_size=tuple(cfg["kernel_size"][-2:]), strides=tuple(cfg["strides"]),
+                                   padding=cfg["padding"], kernel_initializer=ns.init.Constant(fill_value=1))
+        else:
+            l1 = getattr(L, kind)(l0, pool_size=tuple(cfg["pool_size"]), strides=tuple(cfg["strides"]), padding=cfg["padding"])
+        l1.initialize()
+        l1.forward()
+        assert np.all(g[f"{i}_out"] == l1.output), (i, kind)
+        l1.delta = g[f"{i}_delta"]
+        l1.backward()
+        assert np.all(g[f"{i}_dx"] == l0.delta), (i, kind)
+
+
+def _oracle_pair(ns, case, route="literal"):
+    import dnpy_b200
+    dnpy_b200.set_maxpool_route(route)
+    got = drive.run_layer_case(ns, case)
+    want = drive.run_layer_case_oracle(ns, case, maxpool_route=route)
+    return got, want
+
+
+BIG_CASES = [
+    dict(name="big_dense", kind="Dense", in_shape=(784,), batch=256, kw=dict(units=512)),
+    dict(name="big_dense_head", kind="Dense", in_shape=(1600,), batch=128, kw=dict(units=10, kernel_regularizer=["L2", 0.01])),
+    dict(name="big_conv1", kind="Conv2D", in_shape=(1, 28, 28), batch=64,
+         kw=dict(filters=32, kernel_size=(3, 3), strides=(1, 1), padding="none")),
+    dict(name="big_conv2", kind="Conv2D", in_shape=(32, 12, 12), batch=48,
+         kw=dict(filters=64, kernel_size=(3, 3), strides=(1, 1), padding="same")),
+    dict(name="big_conv_s2", kind="Conv2D", in_shape=(32, 16, 16), batch=16,
+         kw=dict(filters=64, kernel_size=(3, 3), strides=(2, 2), padding="same")),
+    dict(name="big_conv_c3", kind="Conv2D", in_shape=(3, 32, 32), batch=16,
+         kw=dict(filters=32, kernel_size=(3, 3), strides=(1, 1), padding="same")),
+    dict(name="big_pointwise", kind="PointwiseConv2D", in_shape=(32, 16, 16), batch=16, kw=dict(filters=32)),
+    dict(name="big_depthwise", kind="DepthwiseConv2D", in_shape=(32, 16, 16), batch=16,
+         kw=dict(kernel_size=(3, 3), strides=(1, 1), padding="same")),
+    dict(name="big_maxpool", kind="MaxPool2D", in_shape=(32, 26, 26), batch=130,
+         kw=dict(pool_size=(3, 3), strides=(2, 2), padding="none")),
+    dict(name="big_maxpool_ties", kind="MaxPool2D", in_shape=(8, 12, 12), batch=200, quantize=True,
+         kw=dict(pool_size=(3, 3), strides=(2, 2), padding="none")),
+    dict(name="big_avgpool", kind="AvgPool2D", in_shape=(16, 16, 16), batch=32,
+         kw=dict(pool_size=(2, 2), strides=(2, 2), padding="none")),
+    dict(name="big_batchnorm", kind="BatchNorm", in_shape=(8, 9, 9), batch=257, kw=dict(), training=True),
+    dict(name="big_relu", kind="Relu", in_shape=(32, 12, 12), batch=67, kw=dict()),
+    dict(name="big_softmax", kind="Softmax", in_shape=(10,), batch=1000, kw=dict()),
+    dict(name="big_softmax_wide", kind="Softmax", in_shape=(100,), batch=33, kw=dict()),
+    dict(name="big_embedding", kind="Embedding", in_shape=(64,), batch=32, int_input=100,
+         kw=dict(input_dim=100, output_dim=8, input_length=64)),
+    dict(name="big_rnn", kind="SimpleRNN", in_shape=(40, 8), batch=19, kw=dict(hidden_dim=32, bptt_truncate=4)),
+    dict(name="big_dropout", kind="Dropout", in_shape=(1000,), batch=16, kw=dict(rate=0.25), training=True, seed=3),
+]
+
+
+@pytest.mark.parametrize("case", BIG_CASES, ids=[c["name"] for c in BIG_CASES])
+def test_config_shapes_vs_oracle(case, ns):
+    got, want = _oracle_pair(ns, case)
+    for k, w in want.items():
+        if k not in got:
+            continue
+        gk = np.asarray(got[k])
+        if k == "idx":
+            assert np.array_equal(gk, w)
+        else:
+            e = rel_err(gk.reshape(np.shape(w)), w)
+            assert e <= TOL32, (k, e)
+
+
+@pytest.mark.parametrize("case", [c for c in cases.LAYER_CASES + BIG_CASES if c["kind"] in ("MaxPool2D", "GlobalMaxPool2D")],
+                         ids=lambda c: c["name"])
+def test_maxpool_per_sample_route(case, ns):
+    got, want = _oracle_pair(ns, case, route="per_sample")
+    assert np.array_equal(np.asarray(got["idx"]), want["idx"])
+    assert rel_err(got["dx0"], want["dx0"]) <= TOL32
+
+
+def test_empty_batch_is_a_noop(ns):
+    L = ns.L
+    l0 = L.Input(shape=(5,))
+    l0.output = np.zeros((0, 5))
+    l1 = L.Relu(l0)
+    l1.forward()
+    assert np.asarray(l1.output).shape == (0, 5)
+
+
+def test_bad_arguments_raise_reference_exception_types(ns):
+    from dnpy_b200 import _lib
+    from dnpy_b200.darray import dev_empty, stream_ptr
+    buf = dev_empty((16,))
+    with pytest.raises(ValueError):
+        _lib.call("dnb_loss_bce", buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), 4, 2, 0.25,
+                  buf.data_ptr(), stream_ptr())
+    g = _lib.Win(1, 1, 6, 6, 1, 2, 2, 3, 3, 2, 2, 0, 0, 0, 0)
+    with pytest.raises(ValueError):      # the reference's AvgPool backward also raises for 3x3 pools
+        _lib.call("dnb_avgpool2d_bwd", buf.data_ptr(), buf.data_ptr(), g, stream_ptr())
+
+
+def test_nan_guard(ns):
+    lo = ns.losses.CrossEntropy()
+    net = ns.Net()
+    p = np.array([[0.5, 0.5], [np.nan, 1.0]])
+    t = np.array([[1.0, 0.0], [0.0, 1.0]])
+    net.losses, net.l_out = [lo], [type("O", (), {"output": p})()]
+    with pytest.raises(ValueError, match="NaNs in the loss function"):
+        net.compute_losses([t])

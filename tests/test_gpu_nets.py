@@ -1,0 +1,177 @@
+"""GPU parity of whole training steps (-m gpu): the five BASELINE configs through Net.build /
+feed_input / forward / compute_losses / reset_grads / backward / apply_grads and through Net.fit.
+
+* small variants against the fixtures recorded from the real reference (tests/golden/net_*.npz);
+* config-sized variants against the oracle, including loss-curve agreement over 100 steps.
+Tolerances: losses rel 1e-5; first-step gradients rel 1e-5; parameters after several Adam steps
+rel 1e-4 (Adam's 1/sqrt(S+eps) amplifies fp32 round-off of tiny gradients).
+"""
+import numpy as np
+import pytest
+
+from oracle.oracle_net import OracleNet
+from tests import topologies
+from tests.conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fp32_mode():
+    import dnpy_b200
+    dnpy_b200.set_math("fp32")
+    dnpy_b200.set_maxpool_route("literal")
+    yield
+
+
+def _manual_step(net, xb, yb):
+    net.feed_input(xb)
+    net.forward()
+    lo, de = net.compute_losses(y_target=yb)
+    net.reset_grads()
+    net.do_delta(de)
+    net.backward()
+    return lo
+
+
+@pytest.mark.parametrize("name", list(topologies.GOLDEN_NETS))
+def test_small_nets_vs_reference_fixtures(name, golden, ns):
+    kw, batch, steps = topologies.GOLDEN_NETS[name]
+    g = golden(f"net_{name}.npz")
+    np.random.seed(42)
+    net = topologies.BUILDERS[name](ns, **kw)
+    net.set_mode("train")
+    x, y = g["x"], g["y"]
+    np.random.seed(777)
+    losses = []
+    for s in range(steps):
+        xb, yb = [x[s * batch:(s + 1) * batch]], [y[s * batch:(s + 1) * batch]]
+        losses.append(_manual_step(net, xb, yb)[0])
+        if s == 0:
+            for li, l in enumerate(net.fts_layers):
+                for k, gr in l.grads.items():
+                    want = g[f"grad0/{li}/{k}"]
+                    e = rel_err(np.asarray(gr).reshape(want.shape), want)
+                    assert e <= 1e-5, (li, l.name, k, e)
+                if f"out0/{li}" in g.files and l.output is not None and not isinstance(l.output, np.ndarray):
+                    assert rel_err(np.asarray(l.output), g[f"out0/{li}"]) <= 1e-5, (li, l.name)
+        net.apply_grads()
+    assert rel_err(np.array(losses), g["losses"]) <= 1e-5
+    for li, l in enumerate(net.fts_layers):
+        for k, v in l.params.items():
+            want = g[f"final/{li}/{k}"]
+            e = rel_err(np.asarray(v).reshape(want.shape), want, floor=1e-3)
+            assert e <= 1e-4, (li, l.name, k, e)
+
+
+CURVES = [
+    ("mnist_cnn", dict(f1=2, f2=4), 32, 100),
+    ("mnist_cnn", dict(f1=8, f2=16), 16, 30),
+    ("mnist_mlp", dict(h1=64, h2=32), 64, 100),
+    ("iris_mlp", dict(), 24, 100),
+    ("res_conv", dict(size=16, c1=8, c2=16), 8, 20),
+    ("rnn_sentiment", dict(vocab=100, emb=8, seq=24, hidden=32, trunc=4), 16, 30),
+]
+
+
+@pytest.mark.parametrize("name,kw,batch,steps", CURVES, ids=[f"{c[0]}-{i}" for i, c in enumerate(CURVES)])
+def test_loss_curve_vs_oracle(name, kw, batch, steps, ns):
+    """Loss-curve agreement over up to 100 steps via the public fused step (Net.train_step)."""
+    np.random.seed(42)
+    net = topologies.BUILDERS[name](ns, **kw)
+    onet = OracleNet.mirror(net)
+    net.set_mode("train")
+    onet.set_mode("train")
+    rs = np.random.RandomState(1234)
+    n_data = batch * 4
+    x, y = topologies.make_data(name, n_data, rs, **kw)
+    got, want = [], []
+    np.random.seed(99)
+    for s in range(steps):
+        lo = (s % 4) * batch
+        outs = net.train_step([x[lo:lo + batch]], [y[lo:lo + batch]])
+        got.append(float(outs[0][0].item()))
+    np.random.seed(99)
+    for s in range(steps):
+        lo = (s % 4) * batch
+        want.append(onet.step([x[lo:lo + batch]], [y[lo:lo + batch]])[0])
+    got, want = np.array(got), np.array(want)
+    assert np.all(np.isfinite(got))
+    # the curve is a chaotic function of round-off after many Adam steps: tight early, looser late
+    assert rel_err(got[:10], want[:10]) <= 1e-4, rel_err(got[:10], want[:10])
+    assert rel_err(got, want) <= 5e-3, rel_err(got, want)
+
+
+def test_fit_evaluate_api(ns, capsys):
+    """Net.fit / Net.evaluate end to end with the reference's print strings."""
+    np.random.seed(42)
+    net = topologies.mnist_cnn(ns, f1=2, f2=4)
+    rs = np.random.RandomState(0)
+    x, y = topologies.make_data("mnist_cnn", 32, rs)
+    net.fit([x], [y], batch_size=8, epochs=2, evaluate_epoch=False, print_rate=1)
+    out = capsys.readouterr().out
+    assert "Epoch 1/2..." in out and "Batch 4/4 - Losses[CrossEntropy=" in out and "CategoricalAccuracy=" in out
+    net.set_mode("test")
+    lo, me = net.evaluate([x], [y], batch_size=8)
+    assert np.isfinite(lo[0]) and 0.0 <= float(me[0][0]) <= 1.0
+    # fit(print_rate=2) exercises the sync-free fused step on the non-printing epochs
+    net.fit([x], [y], batch_size=8, epochs=3, evaluate_epoch=True, print_rate=2, x_test=[x], y_test=[y])
+
+
+def test_save_load_roundtrip_device(tmp_path, ns):
+    np.random.seed(1)
+    net = topologies.mnist_cnn(ns, f1=2, f2=4)
+    rs = np.random.RandomState(0)
+    x, y = topologies.make_data("mnist_cnn", 16, rs)
+    net.set_mode("train")
+    for _ in range(3):
+        net.train_step([x], [y])
+    f = str(tmp_path / "m.pkl")
+    net.save(f, save_grads=True)
+    np.random.seed(2)
+    net2 = topologies.mnist_cnn(ns, f1=2, f2=4)
+    net2.load(f)
+    net.set_mode("test"); net2.set_mode("test")
+    a, _ = net.evaluate([x], [y], batch_size=16)
+    b, _ = net2.evaluate([x], [y], batch_size=16)
+    assert abs(a[0] - b[0]) <= 1e-6
+
+
+def test_full_size_properties(ns):
+    """BASELINE-size tensors (B=8192, 32x26x26): size-independent properties instead of the oracle.
+    * conv linearity: conv(x1 + x2) - K*b == (conv(x1) - K*b) + (conv(x2) - K*b)
+    * pool: output == gather of the input at the recorded argmax; idx in range; checksum of the
+      per-sample backward == checksum of the incoming delta (every delta lands exactly once)."""
+    import dnpy_b200
+    L = ns.L
+    B = 8192
+    rs = np.random.RandomState(0)
+    x1, x2 = rs.rand(B, 1, 28, 28), rs.rand(B, 1, 28, 28)
+    outs = []
+    for xin in (x1, x2, x1 + x2):
+        l0 = L.Input(shape=(1, 28, 28)); l0.output = xin
+        np.random.seed(5)
+        c = L.Conv2D(l0, 32, kernel_size=(3, 3), strides=(1, 1), padding="none")
+        c.initialize()
+        c.forward()
+        outs.append(c.output.dev().clone())
+    assert float((outs[2] - outs[0] - outs[1]).abs().max()) <= 1e-5 * float(outs[2].abs().max())
+    l0 = L.Input(shape=(32, 26, 26))
+    from dnpy_b200.darray import DArray
+    l0.output = DArray.device(outs[2])
+    p = L.MaxPool2D(l0, pool_size=(3, 3), strides=(2, 2), padding="none")
+    p.forward()
+    idx = p.output_idxs.dev().long()
+    assert int(idx.min()) >= 0 and int(idx.max()) <= 8
+    import torch
+    oy = torch.arange(12, device="cuda").view(1, 1, 12, 1) * 2 + idx // 3
+    ox = torch.arange(12, device="cuda").view(1, 1, 1, 12) * 2 + idx % 3
+    flat = outs[2].view(B, 32, -1)
+    gathered = torch.gather(flat, 2, (oy * 26 + ox).view(B, 32, -1)).view(B, 32, 12, 12)
+    assert torch.equal(gathered, p.output.dev())
+    dnpy_b200.set_maxpool_route("per_sample")
+    d = torch.rand(B, 32, 12, 12, device="cuda")
+    p.delta = DArray.device(d)
+    p.backward()
+    tot_in, tot_out = float(d.double().sum()), float(l0.delta.dev().double().sum())
+    assert abs(tot_in - tot_out) <= 1e-6 * abs(tot_in)
