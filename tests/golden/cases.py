@@ -110,11 +110,11 @@ def case_inputs(case):
     return rs, xs
 
 
-def draw_params(rs, params):
+def draw_params(rs, params, scale=0.5):
     """Seeded non-zero values for every parameter, in sorted key order."""
     out = {}
     for k in sorted(params.keys()):
-        v = rs.randn(*np.shape(params[k])) * 0.5
+        v = rs.randn(*np.shape(params[k])) * scale
         if k == "moving_var":
             v = np.abs(v) + 0.5
         out[k] = v

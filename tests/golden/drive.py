@@ -31,7 +31,7 @@ def _prepare(ns, case):
     rs, xs, ins, l1 = _make_layers(ns, case)
     np.random.seed(case.get("seed", 5))
     l1.initialize()
-    new_params = draw_params(rs, l1.params)
+    new_params = draw_params(rs, l1.params, case.get("pscale", 0.5))
     for k, v in new_params.items():
         l1.params[k] = v
     l1.training = bool(case.get("training", True))

@@ -139,7 +139,10 @@ BIG_CASES = [
     dict(name="big_softmax_wide", kind="Softmax", in_shape=(100,), batch=33, kw=dict()),
     dict(name="big_embedding", kind="Embedding", in_shape=(64,), batch=32, int_input=100,
          kw=dict(input_dim=100, output_dim=8, input_length=64)),
-    dict(name="big_rnn", kind="SimpleRNN", in_shape=(40, 8), batch=19, kw=dict(hidden_dim=32, bptt_truncate=4)),
+    # pscale 0.1: with 0.5*randn recurrent weights (spectral radius ~2.8) the recurrence is chaotic and
+    # amplifies fp32-vs-fp64 round-off exponentially in T — a property of the test weights, not the kernel
+    dict(name="big_rnn", kind="SimpleRNN", in_shape=(40, 8), batch=19, pscale=0.1, kw=dict(hidden_dim=32, bptt_truncate=4)),
+    dict(name="big_rnn_full_bptt", kind="SimpleRNN", in_shape=(12, 5), batch=9, pscale=0.1, kw=dict(hidden_dim=16)),
     dict(name="big_dropout", kind="Dropout", in_shape=(1000,), batch=16, kw=dict(rate=0.25), training=True, seed=3),
 ]
 

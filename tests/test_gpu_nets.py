@@ -51,7 +51,8 @@ def test_small_nets_vs_reference_fixtures(name, golden, ns):
             for li, l in enumerate(net.fts_layers):
                 for k, gr in l.grads.items():
                     want = g[f"grad0/{li}/{k}"]
-                    e = rel_err(np.asarray(gr).reshape(want.shape), want)
+                    # floor: a bias in front of a BatchNorm has a mathematically zero gradient (pure round-off)
+                    e = rel_err(np.asarray(gr).reshape(want.shape), want, floor=1e-3)
                     assert e <= 1e-5, (li, l.name, k, e)
                 if f"out0/{li}" in g.files and l.output is not None and not isinstance(l.output, np.ndarray):
                     assert rel_err(np.asarray(l.output), g[f"out0/{li}"]) <= 1e-5, (li, l.name)
@@ -60,46 +61,91 @@ def test_small_nets_vs_reference_fixtures(name, golden, ns):
     for li, l in enumerate(net.fts_layers):
         for k, v in l.params.items():
             want = g[f"final/{li}/{k}"]
+            if f"grad0/{li}/{k}" in g.files and float(np.max(np.abs(g[f"grad0/{li}/{k}"]))) < 1e-12:
+                continue      # gradient is pure round-off in the reference (bias in front of a BatchNorm):
+                              # Adam turns 1e-18 vs 1e-9 noise into different, output-irrelevant drifts
             e = rel_err(np.asarray(v).reshape(want.shape), want, floor=1e-3)
             assert e <= 1e-4, (li, l.name, k, e)
 
 
-CURVES = [
+FREE_RUNNING = [
     ("mnist_cnn", dict(f1=2, f2=4), 32, 100),
-    ("mnist_cnn", dict(f1=8, f2=16), 16, 30),
     ("mnist_mlp", dict(h1=64, h2=32), 64, 100),
-    ("iris_mlp", dict(), 24, 100),
-    ("res_conv", dict(size=16, c1=8, c2=16), 8, 20),
-    ("rnn_sentiment", dict(vocab=100, emb=8, seq=24, hidden=32, trunc=4), 16, 30),
 ]
 
 
-@pytest.mark.parametrize("name,kw,batch,steps", CURVES, ids=[f"{c[0]}-{i}" for i, c in enumerate(CURVES)])
-def test_loss_curve_vs_oracle(name, kw, batch, steps, ns):
-    """Loss-curve agreement over up to 100 steps via the public fused step (Net.train_step)."""
+@pytest.mark.parametrize("name,kw,batch,steps", FREE_RUNNING, ids=[c[0] for c in FREE_RUNNING])
+def test_loss_curve_free_running_100_steps(name, kw, batch, steps, ns):
+    """Loss-curve agreement over 100 independent steps via the public fused step (Net.train_step):
+    product (fp32, GPU) and oracle (float64, CPU) start from the same weights and never exchange
+    state again."""
     np.random.seed(42)
     net = topologies.BUILDERS[name](ns, **kw)
     onet = OracleNet.mirror(net)
     net.set_mode("train")
     onet.set_mode("train")
-    rs = np.random.RandomState(1234)
-    n_data = batch * 4
-    x, y = topologies.make_data(name, n_data, rs, **kw)
+    x, y = topologies.make_data(name, batch * 4, np.random.RandomState(1234), **kw)
     got, want = [], []
-    np.random.seed(99)
     for s in range(steps):
         lo = (s % 4) * batch
         outs = net.train_step([x[lo:lo + batch]], [y[lo:lo + batch]])
         got.append(float(outs[0][0].item()))
-    np.random.seed(99)
-    for s in range(steps):
-        lo = (s % 4) * batch
         want.append(onet.step([x[lo:lo + batch]], [y[lo:lo + batch]])[0])
     got, want = np.array(got), np.array(want)
     assert np.all(np.isfinite(got))
-    # the curve is a chaotic function of round-off after many Adam steps: tight early, looser late
     assert rel_err(got[:10], want[:10]) <= 1e-4, rel_err(got[:10], want[:10])
     assert rel_err(got, want) <= 5e-3, rel_err(got, want)
+
+
+TEACHER_FORCED = [
+    ("iris_mlp", dict(), 24, 100),
+    ("mnist_mlp", dict(h1=64, h2=32), 32, 30),
+    ("mnist_cnn", dict(f1=8, f2=16), 16, 40),
+    ("res_conv", dict(size=16, c1=8, c2=16), 8, 25),
+    ("rnn_sentiment", dict(vocab=100, emb=8, seq=24, hidden=32, trunc=4), 16, 30),
+]
+
+
+@pytest.mark.parametrize("name,kw,batch,steps", TEACHER_FORCED, ids=[c[0] for c in TEACHER_FORCED])
+def test_steps_along_the_reference_trajectory(name, kw, batch, steps, ns):
+    """All five configs along the ORACLE's training trajectory.
+
+    Training these nets is a chaotic (lr 0.1 Adam + the reference's BatchNorm backward) and
+    discontinuous (pool argmax, relu gates, LITERAL max-pool routing where one flipped window moves a
+    whole sample's delta) function of round-off, so a free-running fp32 run cannot shadow a float64
+    run for long — see the free-running test above for the configs where it can.  Here every step
+    starts from the oracle's current parameters: loss and every gradient must match at each of the
+    `steps` parameter states the reference visits.  A step in which a pooling argmax differs between
+    fp32 and float64 (a near-tie below fp32 resolution) is exempt from the gradient check; such steps
+    must stay rare."""
+    np.random.seed(42)
+    net = topologies.BUILDERS[name](ns, **kw)
+    onet = OracleNet.mirror(net)
+    net.set_mode("train")
+    onet.set_mode("train")
+    x, y = topologies.make_data(name, batch * 4, np.random.RandomState(1234), **kw)
+    np.random.seed(99)
+    flips = 0
+    for s in range(steps):
+        lo = (s % 4) * batch
+        xb, yb = [x[lo:lo + batch]], [y[lo:lo + batch]]
+        net.set_params([dict(n.params) for n in onet.fts])
+        state = np.random.get_state()
+        loss = _manual_step(net, xb, yb)[0]
+        np.random.set_state(state)              # same Dropout draws for the oracle
+        want = onet.step(xb, yb)[0]
+        assert abs(loss - want) <= 2e-5 * max(1.0, abs(want)), (s, loss, want)
+        same_idx = all(np.array_equal(np.asarray(l.output_idxs), n.cache["idx"])
+                       for l, n in zip(net.fts_layers, onet.fts) if "idx" in n.cache)
+        if not same_idx:
+            flips += 1
+            continue
+        gmax = max([float(np.max(np.abs(g))) for n in onet.fts for g in n.grads.values()] + [1e-30])
+        for l, n in zip(net.fts_layers, onet.fts):
+            for k, g in n.grads.items():
+                e = rel_err(np.asarray(l.grads[k]).reshape(g.shape), g, floor=1e-3 * gmax)
+                assert e <= 1e-4, (s, l.name, k, e)
+    assert flips <= max(1, steps // 10), f"{flips} of {steps} steps had an fp32 argmax near-tie"
 
 
 def test_fit_evaluate_api(ns, capsys):
