@@ -32,6 +32,9 @@ SIGNATURES = {
     "dnb_version": (_i, []),
     "dnb_last_error": (C.c_char_p, []),
     "dnb_device_query": (_i, [C.POINTER(_i)] * 4),
+    "dnb_launch_count": (C.c_longlong, []),
+    "dnb_prof_begin": (_i, [_p]),
+    "dnb_prof_end": (_i, [C.c_char_p, _z]),
     "dnb_fill_f32": (_i, [_p, _z, _f, _p]),
     "dnb_fill_i32": (_i, [_p, _z, C.c_int32, _p]),
     "dnb_dense_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),

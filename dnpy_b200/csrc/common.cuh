@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 #include "../../include/dnpy_b200.h"
 
 namespace dnb {
@@ -14,7 +15,14 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in mult
 char* err_buf();
 int set_err(int code, const char* fmt, ...);
 
-inline cudaStream_t S(dnb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+// Every entry point converts its stream handle through S(); the last one is remembered so the launch
+// bookkeeping below (launch counter, optional per-kernel event chain) knows where the kernel went.
+extern thread_local cudaStream_t g_cur_stream;
+inline cudaStream_t S(dnb_stream_t s) { g_cur_stream = reinterpret_cast<cudaStream_t>(s); return g_cur_stream; }
+
+// Called after every kernel launch: counts it and, while profiling (dnb_prof_begin/end), records a
+// CUDA event on the launching stream so consecutive events bracket each kernel.
+void note_launch(const char* name);
 
 #define DNB_CHECK_ARG(cond, ...) \
     do { if (!(cond)) return dnb::set_err(DNB_ERR_INVALID, __VA_ARGS__); } while (0)
@@ -22,6 +30,7 @@ inline cudaStream_t S(dnb_stream_t s) { return reinterpret_cast<cudaStream_t>(s)
 #define DNB_LAUNCH_CHECK(name) \
     do { cudaError_t e_ = cudaGetLastError(); \
          if (e_ != cudaSuccess) return dnb::set_err(DNB_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e_)); \
+         dnb::note_launch(name); \
     } while (0)
 
 // Grid for a grid-stride elementwise kernel: enough CTAs for >= 2 waves at 8 CTAs/SM, capped.

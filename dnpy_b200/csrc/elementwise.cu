@@ -5,6 +5,9 @@
 // with a scalar tail; grids are a multiple of the 148 SMs.  Roofline: HBM, algorithmic bytes
 // are listed per entry point in DESIGN.md §4.
 #include "common.cuh"
+#include <vector>
+#include <map>
+#include <string>
 
 namespace dnb {
 
@@ -16,6 +19,27 @@ int set_err(int code, const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
+}
+
+thread_local cudaStream_t g_cur_stream = nullptr;
+
+// ---- launch bookkeeping ---------------------------------------------------------------------
+static long long g_launches = 0;
+struct ProfState {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> names;      // names[i] labels the interval ev[i] -> ev[i+1]
+};
+static ProfState g_prof;
+
+void note_launch(const char* name) {
+    ++g_launches;
+    if (!g_prof.on || g_prof.ev.size() >= (1u << 20)) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, g_cur_stream);
+    g_prof.ev.push_back(e);
+    g_prof.names.push_back(name);
 }
 
 constexpr int EW_BLOCK = 256;
@@ -181,6 +205,51 @@ extern "C" {
 
 int dnb_version(void) { return 100; }
 const char* dnb_last_error(void) { return err_buf(); }
+
+long long dnb_launch_count(void) { return g_launches; }
+
+int dnb_prof_begin(dnb_stream_t stream) {
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.clear();
+    g_prof.names.clear();
+    cudaEvent_t e;
+    cudaError_t rc = cudaEventCreate(&e);
+    if (rc != cudaSuccess) return set_err(DNB_ERR_CUDA, "prof_begin: %s", cudaGetErrorString(rc));
+    cudaEventRecord(e, S(stream));
+    g_prof.ev.push_back(e);
+    g_prof.on = true;
+    return DNB_OK;
+}
+
+int dnb_prof_end(char* json_out, size_t cap) {
+    g_prof.on = false;
+    if (g_prof.ev.empty()) return set_err(DNB_ERR_INVALID, "prof_end without prof_begin");
+    cudaError_t rc = cudaEventSynchronize(g_prof.ev.back());
+    if (rc != cudaSuccess) return set_err(DNB_ERR_CUDA, "prof_end: %s", cudaGetErrorString(rc));
+    std::map<std::string, std::pair<long long, double>> agg;
+    for (size_t i = 0; i + 1 < g_prof.ev.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]);
+        auto& a = agg[g_prof.names[i]];
+        a.first += 1;
+        a.second += ms;
+    }
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "%s\"%s\": [%lld, %.6f]", first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += buf;
+        first = false;
+    }
+    out += "}";
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.clear();
+    g_prof.names.clear();
+    if (!json_out || out.size() + 1 > cap) return set_err(DNB_ERR_INVALID, "prof_end: buffer too small (%zu needed)", out.size() + 1);
+    memcpy(json_out, out.c_str(), out.size() + 1);
+    return DNB_OK;
+}
 
 int dnb_device_query(int* sm_count, int* cc_major, int* cc_minor, int* has_tcgen05) {
     int dev = 0;

@@ -82,6 +82,7 @@ class Net:
         self.use_graph = os.environ.get("DNPY_B200_GRAPH", "1") != "0"
         self._graphs = {}
         self._pending_flags = []
+        self._stage = {}
 
     # ------------------------------------------------------------------ build
     def build(self, l_in, l_out, optimizer, losses, metrics, debug=False, smart_derivatives=False):
@@ -197,8 +198,41 @@ class Net:
                 l.grads[k].fill(0.0)
 
     def feed_input(self, x):
+        """net.py:304-307.  On a CUDA device this is the H2D boundary: each input minibatch is copied
+        (asynchronously when the source is pinned) into a persistent device buffer, so its address
+        is stable across steps."""
+        ready = self._device_ready()
         for j in range(len(self.l_in)):
-            self.l_in[j].output = x[j]
+            self.l_in[j].output = self._stage_in(("x", j), x[j], self._input_is_int(j)) if ready else x[j]
+
+    def _input_is_int(self, j):
+        from .layers import Embedding
+        return any(isinstance(l, Embedding) and l.parents and l.parents[0] is self.l_in[j] for l in self.fts_layers)
+
+    def _stage_in(self, key, a, is_int=False):
+        """ndarray / torch CPU tensor -> persistent device buffer (fp32, or int32 for token ids)."""
+        if isinstance(a, DArray):
+            return a
+        t = torch()
+        if t.is_tensor(a):
+            src = a
+            if src.is_cuda:
+                return DArray.device(src, is_int=is_int)
+        else:
+            arr = np.asarray(a)
+            want = np.int32 if is_int else np.float32
+            if arr.dtype != want or not arr.flags.c_contiguous:
+                arr = np.ascontiguousarray(arr, dtype=want)
+            src = t.from_numpy(arr)
+        want_t = t.int32 if is_int else t.float32
+        if src.dtype != want_t:
+            src = src.to(want_t)
+        buf = self._stage.get(key)
+        if buf is None or tuple(buf.shape) != tuple(src.shape):
+            buf = dev_empty(tuple(src.shape), int_dtype=is_int)
+            self._stage[key] = buf
+        buf.copy_(src, non_blocking=True)
+        return DArray.device(buf, is_int=is_int)
 
     def forward(self):
         for l in self.fts_layers:
@@ -302,8 +336,9 @@ class Net:
         self.forward()
         outs, deltas = [], []
         for i, lo in enumerate(self.losses):
-            outs.append(lo.result_tensor(self.l_out[i].output, y_mb[i]))
-            deltas.append(lo.compute_delta(self.l_out[i].output, y_mb[i]))
+            y_i = self._stage_in(("y", i), y_mb[i])
+            outs.append(lo.result_tensor(self.l_out[i].output, y_i))
+            deltas.append(lo.compute_delta(self.l_out[i].output, y_i))
         self.reset_grads()
         self.do_delta(deltas)
         self.backward()

@@ -67,6 +67,14 @@ const char* dnb_last_error(void);
 /* sm count, compute capability, whether the tcgen05 path is usable on this device */
 int dnb_device_query(int* sm_count, int* cc_major, int* cc_minor, int* has_tcgen05);
 
+/* ---- launch accounting (bench.py's gpu_launches / per-kernel roofline timing) ---------- */
+/* kernels launched by this library since it was loaded */
+long long dnb_launch_count(void);
+/* between begin and end every kernel launch records a CUDA event on its launching stream; end
+ * synchronises and writes {"kernel name": [launches, total_ms], ...} (JSON) into json_out. */
+int dnb_prof_begin(dnb_stream_t stream);
+int dnb_prof_end(char* json_out, size_t cap);
+
 /* ---- Net.reset_grads (net.py:299-302) / generic fills ----------------------- */
 int dnb_fill_f32(float* p, size_t n, float value, dnb_stream_t stream);
 int dnb_fill_i32(int32_t* p, size_t n, int32_t value, dnb_stream_t stream);
