@@ -79,7 +79,7 @@ SIGNATURES = {
     "dnb_opt_adam": (_i, [_p, _p, _p, _p, _z, _f, _f, _f, _f, _p]),
     "dnb_opt_rmsprop": (_i, [_p, _p, _p, _z, _f, _f, _f, _p]),
     "dnb_opt_sgd": (_i, [_p, _p, _p, _z, _f, _f, _i, _p]),
-    "dnb_gemm_tf32_nt": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "dnb_gemm_tf32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
 }
 
 _lib = None

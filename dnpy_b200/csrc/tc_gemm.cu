@@ -1,12 +1,242 @@
-// placeholder — replaced by the tcgen05 implementation
+// TF32 tensor-core GEMM for the dense contractions of the hot path (Dense fwd / dX / dW and the 1x1
+// convolutions): C[M,N] = A[M,K] · B[K,N] with fp32 storage, TF32 operands and fp32 accumulation.
+//
+// Blackwell-native structure (no mma.sync, no wgmma):
+//   * operands are fetched by TMA (cp.async.bulk.tensor, 128B swizzle, zero fill past the edges)
+//     into a 4-stage shared-memory ring, signalled through mbarrier transaction counts;
+//   * one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8 per instruction) with the
+//     accumulator tile living in TMEM; tcgen05.commit releases ring slots / publishes the tile;
+//   * four epilogue warps read the accumulator with tcgen05.ld (32 lanes x 32 columns) and apply the
+//     fused epilogue: bias add (Dense.forward) or "+= (acc + reg'(W)) / m" (Dense.backward dW);
+//   * both operand orientations are supported without a transpose pass: K-major tiles use the
+//     canonical K-major layout, M/N-contiguous matrices (X^T, W, dY as B operand) are loaded as
+//     32x32 boxes into the canonical MN-major layout and flagged in the instruction descriptor;
+//   * split-K over gridDim.z (atomic accumulate epilogue) for the skinny dW shapes.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "tc_gemm.cuh"
+
 namespace dnb {
-bool tc_gemm_supported(int, int, int, bool, bool) { return false; }
-int tc_gemm(const float*, const float*, float*, int, int, int, int, const float*, const float*, float, float, float, cudaStream_t) {
-    return set_err(DNB_ERR_UNSUPPORTED, "tc_gemm: not built");
+namespace tc {
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
 }
+
+bool make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, bool atom32) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
 }
-extern "C" int dnb_gemm_tf32_nt(const float*, const float*, float*, int, int, int, dnb_stream_t) {
-    return dnb::set_err(DNB_ERR_UNSUPPORTED, "gemm_tf32_nt: not built");
+
+constexpr int BM = 128, BK = 32, STAGES = 4;
+constexpr int GEMM_THREADS = 192;     // warp 0: TMA, warp 1: MMA issue, warps 2-5: epilogue
+
+struct GemmParams {
+    float* C; const float* bias; const float* W;
+    int M, N, K;
+    int a_mn, b_mn;             // operand stored MN-contiguous?
+    int grad;                   // epilogue: 0 store(+bias), 1 accumulate gradient
+    float inv_m, l1, l2;
+    int kb_per_split;           // k-blocks handled by one z-slice
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128B swizzle atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int num_kb_total = (p.K + BK - 1) / BK;
+    const int kb_begin = blockIdx.z * p.kb_per_split;
+    const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+    const int nkb = kb_end - kb_begin;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES, k = (kb_begin + i) * BK;
+            if (i >= STAGES) mbar_wait(&empty[s], ((i / STAGES) - 1) & 1);
+            mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
+            uint8_t* a = sA + s * A_BYTES;
+            uint8_t* b = sB + s * B_BYTES;
+            if (!p.a_mn) tma_load_2d(a, &tmA, k, m0, &full[s]);                       // box {32 k, 128 m}
+            else for (int j = 0; j < BM / 32; ++j) tma_load_2d(a + j * 4096, &tmA, m0 + j * 32, k, &full[s]);   // box {32 m, 32 k}
+            if (!p.b_mn) tma_load_2d(b, &tmB, k, n0, &full[s]);                       // box {32 k, BN n}
+            else for (int j = 0; j < BN / 32; ++j) tma_load_2d(b + j * 4096, &tmB, n0 + j * 32, k, &full[s]);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = make_idesc_tf32(BM, BN, p.a_mn, p.b_mn);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            mbar_wait(&full[s], (i / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t a = smem_u32(sA + s * A_BYTES), b = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+            for (int j = 0; j < BK / 8; ++j) {
+                // K-major: step 32 bytes inside the swizzled 128-byte row; MN-major: next 8-row K group (1024 B)
+                const uint64_t ad = p.a_mn ? make_smem_desc(a + j * 1024, 4096, 512, LAYOUT_SW128_BASE32B)
+                                           : make_smem_desc(a + j * 32, 16, 1024);
+                const uint64_t bd = p.b_mn ? make_smem_desc(b + j * 1024, 4096, 512, LAYOUT_SW128_BASE32B)
+                                           : make_smem_desc(b + j * 32, 16, 1024);
+                mma_tf32(tmem_base, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+            }
+            mma_commit(&empty[s]);          // slot reusable once these MMAs have read it
+        }
+        mma_commit(acc_full);               // accumulator tile complete
+    } else if (warp >= 2) {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int q = warp & 3;             // TMEM lane quadrant this warp may access
+        const int row = m0 + q * 32 + lane;
+        if (nkb > 0) {
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            if (nkb > 0) {
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            if (row < p.M) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = n0 + c0 + j;
+                    if (col < p.N) {
+                        const float acc = __uint_as_float(v[j]);
+                        const size_t o = (size_t)row * p.N + col;
+                        if (!p.grad) {
+                            p.C[o] = acc + (p.bias ? p.bias[col] : 0.f);
+                        } else {
+                            float g = acc * p.inv_m;
+                            if (blockIdx.z == 0 && (p.l1 != 0.f || p.l2 != 0.f)) g += reg_term(p.W[o], p.l1, p.l2) * p.inv_m;
+                            if (gridDim.z == 1) p.C[o] += g; else atomicAdd(p.C + o, g);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int splits, cudaStream_t st) {
+    constexpr size_t smem = STAGES * (BM * BK * 4 + BN * BK * 4) + 256 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
+    tc_gemm_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(ta, tb, p);
+    DNB_LAUNCH_CHECK("tc_gemm_tf32");
+    return DNB_OK;
+}
+
+}  // namespace tc
+
+bool tc_gemm_supported(int M, int N, int K, bool a_kmajor, bool b_kmajor) {
+    if (!tc::get_encode_tiled()) return false;
+    if (M < 1 || N < 32 || K < 8) return false;
+    // TMA: 16-byte aligned row pitch of the stored matrices
+    if (a_kmajor ? (K % 4) : (M % 4)) return false;
+    if (b_kmajor ? (K % 4) : (N % 4)) return false;
+    return true;
+}
+
+int tc_gemm(const float* A, const float* B, float* C, int M, int N, int K, int flags,
+            const float* bias, const float* W, float inv_m, float l1, float l2, cudaStream_t st) {
+    using namespace tc;
+    const int a_mn = (flags & TC_A_MMAJOR) ? 1 : 0, b_mn = (flags & TC_B_NMAJOR) ? 1 : 0, grad = (flags & TC_ACCUM_GRAD) ? 1 : 0;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+        return set_err(DNB_ERR_INVALID, "tc_gemm: operands must be 16-byte aligned");
+    const int BN = N >= 96 ? 128 : (N >= 48 ? 64 : 32);
+    CUtensorMap ta, tb;
+    uint64_t dims[2], str[1];
+    uint32_t box[2];
+    if (!a_mn) { dims[0] = K; dims[1] = M; str[0] = (uint64_t)K * 4; box[0] = BK; box[1] = BM; }
+    else       { dims[0] = M; dims[1] = K; str[0] = (uint64_t)M * 4; box[0] = 32; box[1] = BK; }
+    if (!make_tmap_f32(&ta, A, 2, dims, str, box, a_mn)) return set_err(DNB_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled(A) failed");
+    if (!b_mn) { dims[0] = K; dims[1] = N; str[0] = (uint64_t)K * 4; box[0] = BK; box[1] = (uint32_t)BN; }
+    else       { dims[0] = N; dims[1] = K; str[0] = (uint64_t)N * 4; box[0] = 32; box[1] = BK; }
+    if (!make_tmap_f32(&tb, B, 2, dims, str, box, b_mn)) return set_err(DNB_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled(B) failed");
+
+    const int nkb = (K + BK - 1) / BK;
+    int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int splits = 1;
+    if (grad) {                       // skinny weight-gradient shapes: fill the 148 SMs by splitting K
+        splits = max(1, min(nkb / 4, (kNumSMs + tiles - 1) / tiles));
+    }
+    int per = (nkb + splits - 1) / splits;
+    splits = (nkb + per - 1) / per;
+    GemmParams p{C, bias, W, M, N, K, a_mn, b_mn, grad, inv_m, l1, l2, per};
+    if (BN == 128) return launch<128>(ta, tb, p, splits, st);
+    if (BN == 64) return launch<64>(ta, tb, p, splits, st);
+    return launch<32>(ta, tb, p, splits, st);
+}
+
+}  // namespace dnb
+
+extern "C" int dnb_gemm_tf32(const float* A, const float* B, float* C, int M, int N, int K,
+                             int a_mmajor, int b_nmajor, dnb_stream_t stream) {
+    using namespace dnb;
+    DNB_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "gemm_tf32: bad arguments");
+    if (!tc_gemm_supported(M, N, K, !a_mmajor, !b_nmajor))
+        return set_err(DNB_ERR_UNSUPPORTED, "gemm_tf32: shape M=%d N=%d K=%d not supported by the tensor-core path", M, N, K);
+    return tc_gemm(A, B, C, M, N, K, (a_mmajor ? TC_A_MMAJOR : 0) | (b_nmajor ? TC_B_NMAJOR : 0), nullptr, nullptr,
+                   0.f, 0.f, 0.f, S(stream));
 }

@@ -196,8 +196,10 @@ int dnb_opt_rmsprop(float* p, const float* g, float* s, size_t n, float lr, floa
 int dnb_opt_sgd(float* p, const float* g, float* v, size_t n, float lr, float momentum, int nesterov,
                 dnb_stream_t stream);                                                      /* :31-55 */
 
-/* ---- Tensor-core GEMM exposed for testing: C[M,N] = A[M,K] @ B[N,K]^T (TF32 tcgen05) */
-int dnb_gemm_tf32_nt(const float* A, const float* Bm, float* C, int M, int N, int K, dnb_stream_t stream);
+/* ---- Tensor-core GEMM exposed for testing: C[M,N] = A · B, TF32 tcgen05, fp32 accumulate.
+ * a_mmajor = 0: A stored [M,K] row-major, 1: stored [K,M]; b_nmajor = 0: B stored [N,K], 1: stored [K,N]. */
+int dnb_gemm_tf32(const float* A, const float* Bm, float* C, int M, int N, int K,
+                  int a_mmajor, int b_nmajor, dnb_stream_t stream);
 
 #ifdef __cplusplus
 }
