@@ -1,10 +1,460 @@
-// placeholder — replaced by the tcgen05 implementation
+// Conv2D / PointwiseConv2D on the 5th-generation tensor cores: implicit GEMM, TF32 operands,
+// fp32 accumulation in TMEM.  No im2col / col2im tensor ever exists in global memory.
+//
+//   forward : Y[p, f]   = sum_k col(X)[p, k] * W[f, k]          M = pixels (b,oy,ox), N = F, K = (c,i,j)
+//   dgrad   : dX[p, c]  = sum_k col(dY)[p, k] * W'[c, k]        M = input pixels, N = C, K = (f,i',j')
+//             (correlation of dY with the flipped, channel-transposed filter; strided convs gather
+//              only the taps that land on the dY lattice)
+//   wgrad   : gW^T[k, f] = sum_p col(X)[p, k] * dY[p, f]        M = (c,i,j) (+ a ones row -> gb), N = F, K = pixels
+//
+// One CTA = 128 rows of M.  The A operand (the im2col view) is GATHERED by four producer warps straight
+// from the NCHW fp32 tensor into the canonical K-major 128B-swizzled shared-memory layout (zero padding
+// by predication, fp32 kept as-is and consumed as TF32), fenced to the async proxy and handed to the
+// MMA thread through an mbarrier.  The B operand (filters / dY) arrives by TMA.  One elected thread
+// issues tcgen05.mma.kind::tf32; the producer warps double as epilogue warps (tcgen05.ld, lanes =
+// pixels, so NCHW stores are coalesced along x).
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "tc_conv.cuh"
+#include <algorithm>
+
 namespace dnb {
-size_t tc_conv_ws_bytes(const dnb_win_t*) { return 0; }
-bool tc_conv_supported(const dnb_win_t*, int) { return false; }
-int tc_conv_fwd(const float*, const float*, const float*, float*, const dnb_win_t*, void*, cudaStream_t) { return DNB_ERR_UNSUPPORTED; }
-int tc_conv_dgrad(const float*, const float*, float*, const dnb_win_t*, void*, cudaStream_t) { return DNB_ERR_UNSUPPORTED; }
-int tc_conv_wgrad(const float*, const float*, float*, float*, const dnb_win_t*, float, void*, cudaStream_t) { return DNB_ERR_UNSUPPORTED; }
+namespace tc {
+
+constexpr int CBM = 128, CBK = 32, CSTAGES = 4;
+constexpr int CONV_THREADS = 192;        // warps 0-3: gather producers + epilogue, warp 4: TMA(B), warp 5: MMA
+constexpr int MAX_K = 4608;              // k lookup table capacity (e.g. C=512, 3x3)
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// byte offset of element (row, k) inside a [rows x 32] fp32 K-major tile with 128B swizzle
+__device__ __forceinline__ uint32_t sw128_off(int row, int k) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7)) & 7) << 4) + ((k & 3) << 2));
 }
+
+// ---- weight preparation: [N_pad x K_pad] fp32, zero padded, K-major (TMA friendly) ----------------
+// mode 0: Wp[f][k=(c,i,j)] = W[f][c][i][j]
+// mode 1: Wp[c][k=(f,i,j)] = W[f][c][kh-1-i][kw-1-j]
+__global__ void prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int F, int C, int kh, int kw,
+                                    int n_pad, int k_pad, int mode) {
+    const int total = n_pad * k_pad;
+    const int khw = kh * kw;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        int n = e / k_pad, k = e % k_pad;
+        float v = 0.f;
+        if (mode == 0) {
+            if (n < F && k < C * khw) v = w[(size_t)n * C * khw + k];
+        } else {
+            if (n < C && k < F * khw) {
+                int f = k / khw, t = k % khw, i = t / kw, j = t % kw;
+                v = w[(((size_t)f * C + n) * kh + (kh - 1 - i)) * kw + (kw - 1 - j)];
+            }
+        }
+        wp[e] = v;
+    }
+}
+
+struct ConvGemmParams {
+    const float* src; float* dst; const float* bias;
+    int B, Cs, Hs, Ws;           // gathered tensor
+    int Cd, Hd, Wd;              // produced tensor (M = B*Hd*Wd pixels, N = Cd)
+    int kh, kw, K, Kp;           // K = Cs*kh*kw, Kp = padded to 32
+    int mul_y, mul_x, div_y, div_x, off_y, off_x;
+    float bias_k;
+};
+
+template <int BN, bool STRIDED>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p) {
+    constexpr int A_BYTES = CBM * CBK * 4, B_BYTES = BN * CBK * 4;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + CSTAGES * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + CSTAGES * B_BYTES);
+    uint64_t* empty = full + CSTAGES;
+    uint64_t* acc_full = empty + CSTAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    int* koff = reinterpret_cast<int*>(tmem_slot + 2);      // [Kp] plane offset c*Hs*Ws (+ i*Ws + j when !STRIDED)
+    int* kij = koff + p.Kp;                                  // [Kp] (i << 16) | j, or -1 past K
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const long npix = (long)p.B * p.Hd * p.Wd;
+    const long m0 = (long)blockIdx.x * CBM;
+    const int n0 = blockIdx.y * BN;
+    const int nkb = p.Kp / CBK;
+    const int khw = p.kh * p.kw;
+
+    for (int k = tid; k < p.Kp; k += CONV_THREADS) {
+        if (k < p.K) {
+            int c = k / khw, t = k % khw, i = t / p.kw, j = t % p.kw;
+            koff[k] = c * p.Hs * p.Ws + (STRIDED ? 0 : i * p.Ws + j);
+            kij[k] = (i << 16) | j;
+        } else { koff[k] = 0; kij[k] = -1; }
+    }
+    if (tid == 0) {
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < CSTAGES; ++s) { mbar_init(&full[s], 128 + 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ===== gather producers: thread = one pixel row of the tile =====
+        const int row = tid;                       // 0..127
+        const long pix = m0 + row;
+        const bool valid = pix < npix;
+        int b = 0, y = 0, x = 0;
+        if (valid) { x = (int)(pix % p.Wd); long t = pix / p.Wd; y = (int)(t % p.Hd); b = (int)(t / p.Hd); }
+        const int y0 = y * p.mul_y - p.off_y, x0 = x * p.mul_x - p.off_x;
+        const float* sp = p.src + (long)b * p.Cs * p.Hs * p.Ws;
+        const long base = (long)y0 * p.Ws + x0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % CSTAGES;
+            if (kb >= CSTAGES) mbar_wait(&empty[s], ((kb / CSTAGES) - 1) & 1);
+            uint8_t* a = sA + s * A_BYTES;
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) {
+                float4 v;
+                float* vp = reinterpret_cast<float*>(&v);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = kb * CBK + kc * 4 + e;
+                    const int ij = kij[k];
+                    float val = 0.f;
+                    if (valid && ij >= 0) {
+                        const int i = ij >> 16, j = ij & 0xffff;
+                        if (!STRIDED) {
+                            const int ty = y0 + i, tx = x0 + j;
+                            if (ty >= 0 && ty < p.Hs && tx >= 0 && tx < p.Ws) val = __ldg(sp + base + koff[k]);
+                        } else {
+                            const int ty = y0 + i, tx = x0 + j;
+                            if (ty >= 0 && tx >= 0 && (ty % p.div_y) == 0 && (tx % p.div_x) == 0) {
+                                const int ys = ty / p.div_y, xs = tx / p.div_x;
+                                if (ys < p.Hs && xs < p.Ws) val = __ldg(sp + koff[k] + (long)ys * p.Ws + xs);
+                            }
+                        }
+                    }
+                    vp[e] = val;
+                }
+                *reinterpret_cast<float4*>(a + (row >> 3) * 1024 + (row & 7) * 128 + (((kc ^ (row & 7)) & 7) << 4)) = v;
+            }
+            fence_proxy_async_smem();           // generic-proxy stores -> visible to tcgen05.mma
+            mbar_arrive(&full[s]);
+        }
+        // ===== epilogue =====
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const size_t plane = (size_t)p.Hd * p.Wd;
+        float* dp = p.dst + ((size_t)b * p.Cd) * plane + (size_t)y * p.Wd + x;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int d = n0 + c0 + j;
+                    if (c0 + j < BN && d < p.Cd) {
+                        float r = __uint_as_float(v[j]);
+                        if (p.bias) r += p.bias_k * p.bias[d];
+                        dp[(size_t)d * plane] = r;      // lanes = consecutive pixels -> coalesced per channel plane
+                    }
+                }
+            }
+        }
+    } else if (warp == 4 && lane == 0) {
+        // ===== TMA producer for the filter tile =====
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % CSTAGES;
+            if (kb >= CSTAGES) mbar_wait(&empty[s], ((kb / CSTAGES) - 1) & 1);
+            mbar_arrive_expect_tx(&full[s], B_BYTES);
+            tma_load_2d(sB + s * B_BYTES, &tmB, kb * CBK, n0, &full[s]);
+        }
+    } else if (warp == 5 && lane == 0) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = make_idesc_tf32(CBM, BN, 0, 0);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % CSTAGES;
+            mbar_wait(&full[s], (kb / CSTAGES) & 1);
+            tc_fence_after();
+            const uint32_t a = smem_u32(sA + s * A_BYTES), bq = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+            for (int j = 0; j < CBK / 8; ++j)
+                mma_tf32(tmem_base, make_smem_desc(a + j * 32, 16, 1024), make_smem_desc(bq + j * 32, 16, 1024), idesc,
+                         (kb > 0 || j > 0) ? 1u : 0u);
+            mma_commit(&empty[s]);
+        }
+        mma_commit(acc_full);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- weight gradient ---------------------------------------------------------------------------------
+// rows r = (c,i,j) for r < K, row K = ones (-> gb), M padded to MT*128; columns = filters; reduction over
+// pixels in blocks of 32 inside one image (dY rows are contiguous per (b,f): a 3-D TMA box, zero fill at
+// the image edge).  gridDim.x CTAs split the (image, pixel-block) range and accumulate with red.add.
+struct WgradParams {
+    const float* x; float* gw; float* gb;
+    int B, C, H, W, F, OH, OW, kh, kw, sy, sx, pt, pl;
+    int K;                        // C*kh*kw
+    int pb_per_img;               // ceil(OH*OW / 32)
+    long kb_per_cta;
+    float inv_m;
+};
+
+template <int MT, int BN>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
+    constexpr int ST = (MT == 1) ? 4 : 3;
+    constexpr int A_BYTES = MT * CBM * CBK * 4, B_BYTES = BN * CBK * 4;
+    constexpr uint32_t TMEM_COLS = (MT * BN <= 32) ? 32 : (MT * BN <= 64) ? 64 : (MT * BN <= 128) ? 128 : (MT * BN <= 256) ? 256 : 512;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + ST * A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + ST * B_BYTES);
+    uint64_t* empty = full + ST;
+    uint64_t* acc_full = empty + ST;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    int* rc = reinterpret_cast<int*>(tmem_slot + 2);        // [MT*128] channel of row r, -1 = zero row, -2 = ones row
+    int* ri = rc + MT * CBM;                                 // [MT*128] (i << 16) | j
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int khw = p.kh * p.kw;
+    const int npx = p.OH * p.OW;
+    const long total_kb = (long)p.B * p.pb_per_img;
+    const long kb0 = (long)blockIdx.x * p.kb_per_cta;
+    const long kb1 = min(total_kb, kb0 + p.kb_per_cta);
+    const int nkb = (int)max(0L, kb1 - kb0);
+    const int n0 = blockIdx.y * BN;
+
+    for (int r = tid; r < MT * CBM; r += CONV_THREADS) {
+        if (r < p.K) { rc[r] = r / khw; int t = r % khw; ri[r] = ((t / p.kw) << 16) | (t % p.kw); }
+        else { rc[r] = (r == p.K) ? -2 : -1; ri[r] = 0; }
+    }
+    // rows past K+1 are never written by the producers: clear the ring once
+    for (int e = tid; e < ST * A_BYTES / 16; e += CONV_THREADS) reinterpret_cast<float4*>(sA)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) {
+        tma_prefetch_desc(&tmD);
+        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 4 + 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int rows_used = min(MT * CBM, p.K + 1);
+
+    if (warp < 4) {
+        // ===== gather producers: lane = pixel of the 32-pixel block, warps stride over the rows =====
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % ST;
+            const long kb = kb0 + i;
+            const int b = (int)(kb / p.pb_per_img);
+            const int pix = (int)(kb % p.pb_per_img) * 32 + lane;
+            const bool pv = pix < npx;
+            const int oy = pv ? pix / p.OW : 0, ox = pv ? pix % p.OW : 0;
+            const int y0 = oy * p.sy - p.pt, x0 = ox * p.sx - p.pl;
+            const float* xb = p.x + (size_t)b * p.C * p.H * p.W;
+            if (i >= ST) mbar_wait(&empty[s], ((i / ST) - 1) & 1);
+            uint8_t* a = sA + s * A_BYTES;
+            for (int r = warp; r < rows_used; r += 4) {
+                const int c = rc[r];
+                float val = 0.f;
+                if (c >= 0) {
+                    const int iy = y0 + (ri[r] >> 16), ix = x0 + (ri[r] & 0xffff);
+                    if (pv && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) val = __ldg(xb + ((size_t)c * p.H + iy) * p.W + ix);
+                } else if (c == -2) {
+                    val = 1.0f;                 // ones row: D[K, f] = sum_p dY[p, f]  (dY is zero filled past the image)
+                }
+                *reinterpret_cast<float*>(a + (r >> 7) * (CBM * CBK * 4) + sw128_off(r & 127, lane)) = val;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+        }
+        // ===== epilogue: atomically add the partial gW^T tile =====
+        if (nkb > 0) {
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+                const int r = mt * CBM + warp * 32 + lane;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * BN + c0), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int f = n0 + c0 + j;
+                        if (c0 + j < BN && f < p.F) {
+                            const float g = __uint_as_float(v[j]) * p.inv_m;
+                            if (r < p.K) atomicAdd(p.gw + (size_t)f * p.K + r, g);       // lanes = consecutive k -> coalesced
+                            else if (r == p.K && p.gb) atomicAdd(p.gb + f, g);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 4 && lane == 0) {
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % ST;
+            const long kb = kb0 + i;
+            if (i >= ST) mbar_wait(&empty[s], ((i / ST) - 1) & 1);
+            mbar_arrive_expect_tx(&full[s], B_BYTES);
+            tma_load_3d(sB + s * B_BYTES, &tmD, (int)(kb % p.pb_per_img) * 32, n0, (int)(kb / p.pb_per_img), &full[s]);
+        }
+    } else if (warp == 5 && lane == 0) {
+        const uint32_t idesc = make_idesc_tf32(CBM, BN, 0, 0);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % ST;
+            mbar_wait(&full[s], (i / ST) & 1);
+            tc_fence_after();
+            const uint32_t a = smem_u32(sA + s * A_BYTES), bq = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int j = 0; j < CBK / 8; ++j)
+                    mma_tf32(tmem_base + mt * BN, make_smem_desc(a + mt * (CBM * CBK * 4) + j * 32, 16, 1024),
+                             make_smem_desc(bq + j * 32, 16, 1024), idesc, (i > 0 || j > 0) ? 1u : 0u);
+            mma_commit(&empty[s]);
+        }
+        mma_commit(acc_full);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+static int pick_bn(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128)); }
+
+template <int BN, bool STRIDED>
+static int launch_gather(const char* name, const CUtensorMap& tb, const ConvGemmParams& p, cudaStream_t st) {
+    const size_t smem = CSTAGES * (CBM * CBK * 4 + BN * CBK * 4) + 128 + (size_t)p.Kp * 8 + 1024;
+    cudaFuncSetAttribute(tc_conv_gather_kernel<BN, STRIDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long npix = (long)p.B * p.Hd * p.Wd;
+    dim3 grid((unsigned)((npix + CBM - 1) / CBM), (p.Cd + BN - 1) / BN);
+    tc_conv_gather_kernel<BN, STRIDED><<<grid, CONV_THREADS, smem, st>>>(tb, p);
+    DNB_LAUNCH_CHECK(name);
+    return DNB_OK;
+}
+
+static int run_gather(const char* name, const float* wprep, int n_pad, ConvGemmParams p, cudaStream_t st) {
+    const int bn = pick_bn(p.Cd);
+    CUtensorMap tb;
+    uint64_t dims[2] = {(uint64_t)p.Kp, (uint64_t)n_pad}, str[1] = {(uint64_t)p.Kp * 4};
+    uint32_t box[2] = {CBK, (uint32_t)bn};
+    if (!make_tmap_f32(&tb, wprep, 2, dims, str, box)) return set_err(DNB_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", name);
+    const bool strided = (p.div_y != 1 || p.div_x != 1);
+#define DNB_GO(BN_) (strided ? launch_gather<BN_, true>(name, tb, p, st) : launch_gather<BN_, false>(name, tb, p, st))
+    switch (bn) {
+        case 16: return DNB_GO(16);
+        case 32: return DNB_GO(32);
+        case 64: return DNB_GO(64);
+        default: return DNB_GO(128);
+    }
+#undef DNB_GO
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+// workspace: [fwd filters: pad16(F) x pad32(C*khw)] [dgrad filters: pad16(C) x pad32(F*khw)]
+static size_t ws_fwd_floats(const dnb_win_t* g) { return (size_t)round_up(g->F, 128) * round_up(g->C * g->kh * g->kw, CBK); }
+static size_t ws_dgrad_floats(const dnb_win_t* g) { return (size_t)round_up(g->C, 128) * round_up(g->F * g->kh * g->kw, CBK); }
+
+size_t tc_conv_ws_bytes(const dnb_win_t* g) { return (ws_fwd_floats(g) + ws_dgrad_floats(g)) * sizeof(float) + 256; }
+
+bool tc_conv_supported(const dnb_win_t* g, int kind) {
+    if (!get_encode_tiled()) return false;
+    const int khw = g->kh * g->kw;
+    if (kind == TC_CONV_FWD) return g->C * khw <= MAX_K && g->kh < 256 && g->kw < 256;
+    if (kind == TC_CONV_DGRAD) return g->F * khw <= MAX_K && g->kh < 256 && g->kw < 256;
+    // wgrad: dY rows are read by a 3-D TMA box -> 16-byte aligned plane pitch; M tiles limited by TMEM (512 columns)
+    if ((g->OH * g->OW) % 4) return false;
+    const int mt = (g->C * khw + 1 + CBM - 1) / CBM;
+    const int bn = pick_bn(g->F);
+    return mt <= 3 && mt * bn <= 512 && g->F <= 128 * 8;
+}
+
+int tc_conv_fwd(const float* x, const float* w, const float* b, float* y, const dnb_win_t* g, void* ws, cudaStream_t st) {
+    if (!ws) return set_err(DNB_ERR_INVALID, "conv2d_fwd(tf32): workspace required");
+    const int K = g->C * g->kh * g->kw, Kp = round_up(K, CBK), n_pad = round_up(g->F, 128);
+    float* wp = static_cast<float*>(ws);
+    prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, 0);
+    DNB_LAUNCH_CHECK("conv2d_prep_weights");
+    ConvGemmParams p{x, y, b, g->B, g->C, g->H, g->W, g->F, g->OH, g->OW, g->kh, g->kw, K, Kp,
+                     g->sy, g->sx, 1, 1, g->pt, g->pl, (float)K};
+    return run_gather("tc_conv2d_fwd", wp, n_pad, p, st);
+}
+
+int tc_conv_dgrad(const float* dy, const float* w, float* dx, const dnb_win_t* g, void* ws, cudaStream_t st) {
+    if (!ws) return set_err(DNB_ERR_INVALID, "conv2d_bwd(tf32): workspace required");
+    const int K = g->F * g->kh * g->kw, Kp = round_up(K, CBK), n_pad = round_up(g->C, 128);
+    float* wp = static_cast<float*>(ws) + ws_fwd_floats(g);
+    prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, 1);
+    DNB_LAUNCH_CHECK("conv2d_prep_weights_t");
+    ConvGemmParams p{dy, dx, nullptr, g->B, g->F, g->OH, g->OW, g->C, g->H, g->W, g->kh, g->kw, K, Kp,
+                     1, 1, g->sy, g->sx, g->kh - 1 - g->pt, g->kw - 1 - g->pl, 0.f};
+    return run_gather("tc_conv2d_bwd_data", wp, n_pad, p, st);
+}
+
+template <int MT, int BN>
+static int launch_wgrad(const CUtensorMap& td, WgradParams p, int fb, cudaStream_t st) {
+    constexpr int ST = (MT == 1) ? 4 : 3;
+    const size_t smem = ST * (MT * CBM * CBK * 4 + BN * CBK * 4) + 128 + (size_t)MT * CBM * 8 + 1024;
+    cudaFuncSetAttribute(tc_conv_wgrad_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long total_kb = (long)p.B * p.pb_per_img;
+    long ctas = std::min<long>(total_kb, std::max(1, kNumSMs / fb));
+    p.kb_per_cta = (total_kb + ctas - 1) / ctas;
+    ctas = (total_kb + p.kb_per_cta - 1) / p.kb_per_cta;
+    dim3 grid((unsigned)ctas, fb);
+    tc_conv_wgrad_kernel<MT, BN><<<grid, CONV_THREADS, smem, st>>>(td, p);
+    DNB_LAUNCH_CHECK("tc_conv2d_bwd_weight");
+    return DNB_OK;
+}
+
+int tc_conv_wgrad(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, void* ws,
+                  cudaStream_t st) {
+    (void)ws;
+    const int K = g->C * g->kh * g->kw;
+    const int npx = g->OH * g->OW;
+    const int mt = (K + 1 + CBM - 1) / CBM;
+    const int bn = pick_bn(g->F);
+    const int fb = (g->F + bn - 1) / bn;
+    CUtensorMap td;
+    uint64_t dims[3] = {(uint64_t)npx, (uint64_t)g->F, (uint64_t)g->B};
+    uint64_t str[2] = {(uint64_t)npx * 4, (uint64_t)npx * g->F * 4};
+    uint32_t box[3] = {CBK, (uint32_t)bn, 1};
+    if (!make_tmap_f32(&td, dy, 3, dims, str, box)) return set_err(DNB_ERR_CUDA, "conv2d_bwd_weight(tf32): cuTensorMapEncodeTiled failed");
+    WgradParams p{x, gw, gb, g->B, g->C, g->H, g->W, g->F, g->OH, g->OW, g->kh, g->kw, g->sy, g->sx, g->pt, g->pl,
+                  K, (npx + 31) / 32, 0, inv_m};
+#define DNB_W(MT_, BN_) launch_wgrad<MT_, BN_>(td, p, fb, st)
+    if (mt == 1) { switch (bn) { case 16: return DNB_W(1, 16); case 32: return DNB_W(1, 32); case 64: return DNB_W(1, 64); default: return DNB_W(1, 128); } }
+    if (mt == 2) { switch (bn) { case 16: return DNB_W(2, 16); case 32: return DNB_W(2, 32); case 64: return DNB_W(2, 64); default: return DNB_W(2, 128); } }
+    switch (bn) { case 16: return DNB_W(3, 16); case 32: return DNB_W(3, 32); case 64: return DNB_W(3, 64); default: return DNB_W(3, 128); }
+#undef DNB_W
+}
+
+}  // namespace dnb
