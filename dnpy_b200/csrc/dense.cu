@@ -21,6 +21,7 @@ struct GemmArgs {
     const float* bias;                // EPI_BIAS: length N (may be null)
     const float* W;                   // EPI_GRAD: same layout as C, regulariser argument
     float inv_m, l1, l2;              // EPI_GRAD (l1,l2 already multiplied by reg_scale)
+    int k_per_split;                  // EPI_GRAD: K range of one z-slice (split-K with atomic accumulate)
 };
 
 template <int EPI>
@@ -37,18 +38,20 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < a.K; k0 += GBK) {
+    const int k_begin = (EPI == EPI_GRAD) ? blockIdx.z * a.k_per_split : 0;
+    const int k_end = (EPI == EPI_GRAD) ? min(a.K, k_begin + a.k_per_split) : a.K;
+    for (int k0 = k_begin; k0 < k_end; k0 += GBK) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             int idx = tid + r * 256;
             int k, m;
             if (a_kfast) { k = idx & 15; m = idx >> 4; } else { m = idx & 63; k = idx >> 6; }
             int gm = m0 + m, gk = k0 + k;
-            As[k][m] = (gm < a.M && gk < a.K) ? __ldg(a.A + (long)gm * a.sAm + (long)gk * a.sAk) : 0.f;
+            As[k][m] = (gm < a.M && gk < k_end) ? __ldg(a.A + (long)gm * a.sAm + (long)gk * a.sAk) : 0.f;
             int kk, n;
             if (b_nfast) { n = idx & 63; kk = idx >> 6; } else { kk = idx & 15; n = idx >> 4; }
             int gn = n0 + n, gk2 = k0 + kk;
-            Bs[kk][n] = (gn < a.N && gk2 < a.K) ? __ldg(a.B + (long)gk2 * a.sBk + (long)gn * a.sBn) : 0.f;
+            Bs[kk][n] = (gn < a.N && gk2 < k_end) ? __ldg(a.B + (long)gk2 * a.sBk + (long)gn * a.sBn) : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -74,15 +77,27 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs a) {
             size_t o = (size_t)gm * a.N + gn;
             if (EPI == EPI_STORE) a.C[o] = acc[i][j];
             else if (EPI == EPI_BIAS) a.C[o] = acc[i][j] + (a.bias ? a.bias[gn] : 0.f);
-            else a.C[o] += (acc[i][j] + reg_term(a.W[o], a.l1, a.l2)) * a.inv_m;
+            else {
+                float g = acc[i][j] * a.inv_m;
+                if (blockIdx.z == 0) g += reg_term(a.W[o], a.l1, a.l2) * a.inv_m;
+                if (gridDim.z == 1) a.C[o] += g; else atomicAdd(a.C + o, g);
+            }
         }
     }
 }
 
 template <int EPI>
-static int launch_sgemm(const char* name, const GemmArgs& a, cudaStream_t st) {
+static int launch_sgemm(const char* name, GemmArgs a, cudaStream_t st) {
     if (a.M == 0 || a.N == 0) return DNB_OK;
     dim3 grid((a.N + GBN - 1) / GBN, (a.M + GBM - 1) / GBM);
+    a.k_per_split = a.K;
+    if (EPI == EPI_GRAD) {            // skinny weight-gradient shapes: split the batch reduction over the SMs
+        int tiles = grid.x * grid.y;
+        int splits = max(1, min(a.K / (4 * GBK), (2 * kNumSMs + tiles - 1) / tiles));
+        int per = ((a.K + splits - 1) / splits + GBK - 1) / GBK * GBK;
+        a.k_per_split = per;
+        grid.z = (a.K + per - 1) / per;
+    }
     sgemm_kernel<EPI><<<grid, 256, 0, st>>>(a);
     DNB_LAUNCH_CHECK(name);
     return DNB_OK;
@@ -123,7 +138,7 @@ int dnb_dense_fwd(const float* x, const float* w, const float* b, float* y,
         // Y[B,out] = X[B,in] . W[in,out]: A is K-major, B is N-major (row-major [K,N])
         return tc_gemm(x, w, y, B, out, in, TC_A_KMAJOR | TC_B_NMAJOR, b, nullptr, 0.f, 0.f, 0.f, S(stream));
     }
-    GemmArgs a{x, in, 1, w, out, 1, y, B, out, in, b, nullptr, 0.f, 0.f, 0.f};
+    GemmArgs a{x, in, 1, w, out, 1, y, B, out, in, b, nullptr, 0.f, 0.f, 0.f, 0};
     return launch_sgemm<EPI_BIAS>("dense_fwd", a, S(stream));
 }
 
@@ -140,7 +155,7 @@ int dnb_dense_bwd(const float* x, const float* w, const float* b, const float* d
         if (math == DNB_MATH_TF32 && tc_gemm_supported(B, in, out, true, true)) {
             rc = tc_gemm(dy, w, dx, B, in, out, TC_A_KMAJOR | TC_B_KMAJOR, nullptr, nullptr, 0.f, 0.f, 0.f, st);
         } else {
-            GemmArgs a{dy, out, 1, w, 1, out, dx, B, in, out, nullptr, nullptr, 0.f, 0.f, 0.f};
+            GemmArgs a{dy, out, 1, w, 1, out, dx, B, in, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0};
             rc = launch_sgemm<EPI_STORE>("dense_bwd_dx", a, st);
         }
         if (rc) return rc;
@@ -150,7 +165,7 @@ int dnb_dense_bwd(const float* x, const float* w, const float* b, const float* d
         rc = tc_gemm(x, dy, gw, in, out, B, TC_A_MMAJOR | TC_B_NMAJOR | TC_ACCUM_GRAD, nullptr, w, inv_m,
                      reg_w.l1 * reg_scale, reg_w.l2 * reg_scale, st);
     } else {
-        GemmArgs a{x, 1, in, dy, out, 1, gw, in, out, B, nullptr, w, inv_m, reg_w.l1 * reg_scale, reg_w.l2 * reg_scale};
+        GemmArgs a{x, 1, in, dy, out, 1, gw, in, out, B, nullptr, w, inv_m, reg_w.l1 * reg_scale, reg_w.l2 * reg_scale, 0};
         rc = launch_sgemm<EPI_GRAD>("dense_bwd_dw", a, st);
     }
     if (rc) return rc;

@@ -22,7 +22,6 @@ namespace dnb {
 namespace tc {
 
 constexpr int CBM = 128, CBK = 32, CSTAGES = 4;
-constexpr int CONV_THREADS = 192;        // warps 0-3: gather producers + epilogue, warp 4: TMA(B), warp 5: MMA
 constexpr int MAX_K = 4608;              // k lookup table capacity (e.g. C=512, 3x3)
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -33,21 +32,24 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k) {
 }
 
 // ---- weight preparation: [N_pad x K_pad] fp32, zero padded, K-major (TMA friendly) ----------------
-// mode 0: Wp[f][k=(c,i,j)] = W[f][c][i][j]
-// mode 1: Wp[c][k=(f,i,j)] = W[f][c][kh-1-i][kw-1-j]
+// K is ordered TAP-MAJOR, CHANNEL-MINOR: k = tap * cp + c with cp = channels rounded up to 4, so every
+// 16-byte chunk of the im2col tile (4 consecutive k) belongs to ONE tap: one bounds test per chunk.
+// mode 0 (forward): Wp[f][tap*cp + c]  = W[f][c][i][j]
+// mode 1 (dgrad)  : Wp[c][tap*fp + f]  = W[f][c][kh-1-i][kw-1-j]
 __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int F, int C, int kh, int kw,
-                                    int n_pad, int k_pad, int mode) {
+                                    int n_pad, int k_pad, int cp, int mode) {
     const int total = n_pad * k_pad;
     const int khw = kh * kw;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         int n = e / k_pad, k = e % k_pad;
+        int tap = k / cp, ch = k % cp;
         float v = 0.f;
-        if (mode == 0) {
-            if (n < F && k < C * khw) v = w[(size_t)n * C * khw + k];
-        } else {
-            if (n < C && k < F * khw) {
-                int f = k / khw, t = k % khw, i = t / kw, j = t % kw;
-                v = w[(((size_t)f * C + n) * kh + (kh - 1 - i)) * kw + (kw - 1 - j)];
+        if (tap < khw) {
+            int i = tap / kw, j = tap % kw;
+            if (mode == 0) {
+                if (n < F && ch < C) v = w[(((size_t)n * C + ch) * kh + i) * kw + j];
+            } else {
+                if (n < C && ch < F) v = w[(((size_t)ch * C + n) * kh + (kh - 1 - i)) * kw + (kw - 1 - j)];
             }
         }
         wp[e] = v;
@@ -58,13 +60,16 @@ struct ConvGemmParams {
     const float* src; float* dst; const float* bias;
     int B, Cs, Hs, Ws;           // gathered tensor
     int Cd, Hd, Wd;              // produced tensor (M = B*Hd*Wd pixels, N = Cd)
-    int kh, kw, K, Kp;           // K = Cs*kh*kw, Kp = padded to 32
+    int kh, kw, cp, Kp;          // cp = Cs rounded up to 4; K = kh*kw*cp, Kp = K padded to 32
     int mul_y, mul_x, div_y, div_x, off_y, off_x;
     float bias_k;
 };
 
+constexpr int GATHER_WARPS = 8;                                   // producer warps (also epilogue: warps 0-3)
+constexpr int GATHER_THREADS = (GATHER_WARPS + 2) * 32;            // + TMA warp + MMA warp
+
 template <int BN, bool STRIDED>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(GATHER_THREADS, 1)
 tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p) {
     constexpr int A_BYTES = CBM * CBK * 4, B_BYTES = BN * CBK * 4;
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
@@ -76,8 +81,7 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
     uint64_t* empty = full + CSTAGES;
     uint64_t* acc_full = empty + CSTAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-    int* koff = reinterpret_cast<int*>(tmem_slot + 2);      // [Kp] plane offset c*Hs*Ws (+ i*Ws + j when !STRIDED)
-    int* kij = koff + p.Kp;                                  // [Kp] (i << 16) | j, or -1 past K
+    int* ctab = reinterpret_cast<int*>(tmem_slot + 2);      // [Kp/4] per 16-byte chunk: (i << 24) | (j << 16) | c0, -1 = zero chunk
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const long npix = (long)p.B * p.Hd * p.Wd;
@@ -86,20 +90,17 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
     const int nkb = p.Kp / CBK;
     const int khw = p.kh * p.kw;
 
-    for (int k = tid; k < p.Kp; k += CONV_THREADS) {
-        if (k < p.K) {
-            int c = k / khw, t = k % khw, i = t / p.kw, j = t % p.kw;
-            koff[k] = c * p.Hs * p.Ws + (STRIDED ? 0 : i * p.Ws + j);
-            kij[k] = (i << 16) | j;
-        } else { koff[k] = 0; kij[k] = -1; }
+    for (int ch = tid; ch < p.Kp / 4; ch += GATHER_THREADS) {
+        const int k = ch * 4, tap = k / p.cp, c0 = k % p.cp;
+        ctab[ch] = (tap < khw) ? (((tap / p.kw) << 24) | ((tap % p.kw) << 16) | c0) : -1;
     }
     if (tid == 0) {
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < CSTAGES; ++s) { mbar_init(&full[s], 128 + 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < CSTAGES; ++s) { mbar_init(&full[s], GATHER_WARPS * 32 + 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 4) {
+    if (warp == GATHER_WARPS) {
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
@@ -108,72 +109,74 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        // ===== gather producers: thread = one pixel row of the tile =====
-        const int row = tid;                       // 0..127
+    if (warp < GATHER_WARPS) {
+        // ===== gather producers: thread = (pixel row, half of the 8 chunks of a 128-byte K row) =====
+        const int row = tid & 127, half = tid >> 7;
         const long pix = m0 + row;
         const bool valid = pix < npix;
         int b = 0, y = 0, x = 0;
         if (valid) { x = (int)(pix % p.Wd); long t = pix / p.Wd; y = (int)(t % p.Hd); b = (int)(t / p.Hd); }
         const int y0 = y * p.mul_y - p.off_y, x0 = x * p.mul_x - p.off_x;
-        const float* sp = p.src + (long)b * p.Cs * p.Hs * p.Ws;
-        const long base = (long)y0 * p.Ws + x0;
+        const long plane_s = (long)p.Hs * p.Ws;
+        const float* sp = p.src + (long)b * p.Cs * plane_s;
+        const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+        const int rx = row & 7;
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % CSTAGES;
             if (kb >= CSTAGES) mbar_wait(&empty[s], ((kb / CSTAGES) - 1) & 1);
-            uint8_t* a = sA + s * A_BYTES;
+            uint8_t* a = sA + s * A_BYTES + row_off;
 #pragma unroll
-            for (int kc = 0; kc < 8; ++kc) {
-                float4 v;
-                float* vp = reinterpret_cast<float*>(&v);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = kb * CBK + kc * 4 + e;
-                    const int ij = kij[k];
-                    float val = 0.f;
-                    if (valid && ij >= 0) {
-                        const int i = ij >> 16, j = ij & 0xffff;
-                        if (!STRIDED) {
-                            const int ty = y0 + i, tx = x0 + j;
-                            if (ty >= 0 && ty < p.Hs && tx >= 0 && tx < p.Ws) val = __ldg(sp + base + koff[k]);
-                        } else {
-                            const int ty = y0 + i, tx = x0 + j;
-                            if (ty >= 0 && tx >= 0 && (ty % p.div_y) == 0 && (tx % p.div_x) == 0) {
-                                const int ys = ty / p.div_y, xs = tx / p.div_x;
-                                if (ys < p.Hs && xs < p.Ws) val = __ldg(sp + koff[k] + (long)ys * p.Ws + xs);
-                            }
-                        }
+            for (int q = 0; q < 4; ++q) {
+                const int kc = half * 4 + q;
+                const int e = ctab[kb * 8 + kc];
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid && e >= 0) {
+                    int ty = y0 + (e >> 24), tx = x0 + ((e >> 16) & 0xff);
+                    const int c0 = e & 0xffff;
+                    bool ok = ty >= 0 && tx >= 0;
+                    if (STRIDED) {
+                        ok = ok && (ty % p.div_y) == 0 && (tx % p.div_x) == 0;
+                        ty /= p.div_y; tx /= p.div_x;
                     }
-                    vp[e] = val;
+                    ok = ok && ty < p.Hs && tx < p.Ws;
+                    if (ok) {
+                        const float* g = sp + (long)c0 * plane_s + (long)ty * p.Ws + tx;
+                        v.x = __ldg(g);
+                        if (c0 + 1 < p.Cs) v.y = __ldg(g + plane_s);
+                        if (c0 + 2 < p.Cs) v.z = __ldg(g + 2 * plane_s);
+                        if (c0 + 3 < p.Cs) v.w = __ldg(g + 3 * plane_s);
+                    }
                 }
-                *reinterpret_cast<float4*>(a + (row >> 3) * 1024 + (row & 7) * 128 + (((kc ^ (row & 7)) & 7) << 4)) = v;
+                *reinterpret_cast<float4*>(a + (((kc ^ rx) & 7) << 4)) = v;
             }
             fence_proxy_async_smem();           // generic-proxy stores -> visible to tcgen05.mma
             mbar_arrive(&full[s]);
         }
-        // ===== epilogue =====
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const size_t plane = (size_t)p.Hd * p.Wd;
-        float* dp = p.dst + ((size_t)b * p.Cd) * plane + (size_t)y * p.Wd + x;
+        // ===== epilogue (warps 0-3 own the four TMEM lane quadrants) =====
+        if (warp < 4) {
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            const size_t plane = (size_t)p.Hd * p.Wd;
+            float* dp = p.dst + ((size_t)b * p.Cd) * plane + (size_t)y * p.Wd + x;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld_wait();
-            if (valid) {
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (valid) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int d = n0 + c0 + j;
-                    if (c0 + j < BN && d < p.Cd) {
-                        float r = __uint_as_float(v[j]);
-                        if (p.bias) r += p.bias_k * p.bias[d];
-                        dp[(size_t)d * plane] = r;      // lanes = consecutive pixels -> coalesced per channel plane
+                    for (int j = 0; j < 32; ++j) {
+                        const int d = n0 + c0 + j;
+                        if (c0 + j < BN && d < p.Cd) {
+                            float r = __uint_as_float(v[j]);
+                            if (p.bias) r += p.bias_k * p.bias[d];
+                            dp[(size_t)d * plane] = r;      // lanes = consecutive pixels -> coalesced per channel plane
+                        }
                     }
                 }
             }
         }
-    } else if (warp == 4 && lane == 0) {
+    } else if (warp == GATHER_WARPS && lane == 0) {
         // ===== TMA producer for the filter tile =====
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % CSTAGES;
@@ -181,7 +184,7 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
             mbar_arrive_expect_tx(&full[s], B_BYTES);
             tma_load_2d(sB + s * B_BYTES, &tmB, kb * CBK, n0, &full[s]);
         }
-    } else if (warp == 5 && lane == 0) {
+    } else if (warp == GATHER_WARPS + 1 && lane == 0) {
         // ===== MMA issuer =====
         const uint32_t idesc = make_idesc_tf32(CBM, BN, 0, 0);
         for (int kb = 0; kb < nkb; ++kb) {
@@ -199,13 +202,14 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == GATHER_WARPS) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ---- weight gradient ---------------------------------------------------------------------------------
-// rows r = (c,i,j) for r < K, row K = ones (-> gb), M padded to MT*128; columns = filters; reduction over
-// pixels in blocks of 32 inside one image (dY rows are contiguous per (b,f): a 3-D TMA box, zero fill at
-// the image edge).  gridDim.x CTAs split the (image, pixel-block) range and accumulate with red.add.
+// rows r = tap*C + c for r < K (TAP-MAJOR so the per-tap bounds test and pixel offset are hoisted out of
+// the channel loop), row K = ones (-> gb), M padded to MT*128; columns = filters; reduction over pixels in
+// blocks of 32 inside one image (dY rows are contiguous per (b,f): a 3-D TMA box, zero filled at the image
+// edge).  gridDim.x CTAs split the (image, pixel-block) range and accumulate with red.add.
 struct WgradParams {
     const float* x; float* gw; float* gb;
     int B, C, H, W, F, OH, OW, kh, kw, sy, sx, pt, pl;
@@ -215,8 +219,11 @@ struct WgradParams {
     float inv_m;
 };
 
+constexpr int WG_WARPS = 8;
+constexpr int WGRAD_THREADS = (WG_WARPS + 2) * 32;
+
 template <int MT, int BN>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(WGRAD_THREADS, 1)
 tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
     constexpr int ST = (MT == 1) ? 4 : 3;
     constexpr int A_BYTES = MT * CBM * CBK * 4, B_BYTES = BN * CBK * 4;
@@ -229,8 +236,6 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
     uint64_t* empty = full + ST;
     uint64_t* acc_full = empty + ST;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-    int* rc = reinterpret_cast<int*>(tmem_slot + 2);        // [MT*128] channel of row r, -1 = zero row, -2 = ones row
-    int* ri = rc + MT * CBM;                                 // [MT*128] (i << 16) | j
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int khw = p.kh * p.kw;
@@ -241,19 +246,15 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
     const int nkb = (int)max(0L, kb1 - kb0);
     const int n0 = blockIdx.y * BN;
 
-    for (int r = tid; r < MT * CBM; r += CONV_THREADS) {
-        if (r < p.K) { rc[r] = r / khw; int t = r % khw; ri[r] = ((t / p.kw) << 16) | (t % p.kw); }
-        else { rc[r] = (r == p.K) ? -2 : -1; ri[r] = 0; }
-    }
     // rows past K+1 are never written by the producers: clear the ring once
-    for (int e = tid; e < ST * A_BYTES / 16; e += CONV_THREADS) reinterpret_cast<float4*>(sA)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = tid; e < ST * A_BYTES / 16; e += WGRAD_THREADS) reinterpret_cast<float4*>(sA)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
         tma_prefetch_desc(&tmD);
-        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 4 + 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], WG_WARPS + 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 4) {
+    if (warp == WG_WARPS) {
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
@@ -262,10 +263,10 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int rows_used = min(MT * CBM, p.K + 1);
 
-    if (warp < 4) {
-        // ===== gather producers: lane = pixel of the 32-pixel block, warps stride over the rows =====
+    if (warp < WG_WARPS) {
+        // ===== gather producers: lane = pixel of the 32-pixel block; warp w owns channels c = w, w+8, ... =====
+        const size_t plane = (size_t)p.H * p.W;
         for (int i = 0; i < nkb; ++i) {
             const int s = i % ST;
             const long kb = kb0 + i;
@@ -274,31 +275,36 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
             const bool pv = pix < npx;
             const int oy = pv ? pix / p.OW : 0, ox = pv ? pix % p.OW : 0;
             const int y0 = oy * p.sy - p.pt, x0 = ox * p.sx - p.pl;
-            const float* xb = p.x + (size_t)b * p.C * p.H * p.W;
+            const float* xb = p.x + (size_t)b * p.C * plane;
             if (i >= ST) mbar_wait(&empty[s], ((i / ST) - 1) & 1);
             uint8_t* a = sA + s * A_BYTES;
-            for (int r = warp; r < rows_used; r += 4) {
-                const int c = rc[r];
-                float val = 0.f;
-                if (c >= 0) {
-                    const int iy = y0 + (ri[r] >> 16), ix = x0 + (ri[r] & 0xffff);
-                    if (pv && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) val = __ldg(xb + ((size_t)c * p.H + iy) * p.W + ix);
-                } else if (c == -2) {
-                    val = 1.0f;                 // ones row: D[K, f] = sum_p dY[p, f]  (dY is zero filled past the image)
-                }
+            // rows r = tap*C + c are dealt round-robin to the producer warps (balanced for any C)
+            int tap = warp / p.C, c = warp % p.C;
+#pragma unroll 4
+            for (int r = warp; r < p.K; r += WG_WARPS) {
+                const int iy = y0 + tap / p.kw, ix = x0 + tap % p.kw;
+                const bool ok = pv && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                const float val = ok ? __ldg(xb + ((size_t)c * p.H + iy) * p.W + ix) : 0.f;
                 *reinterpret_cast<float*>(a + (r >> 7) * (CBM * CBK * 4) + sw128_off(r & 127, lane)) = val;
+                c += WG_WARPS;
+                while (c >= p.C) { c -= p.C; ++tap; }
+            }
+            if (warp == WG_WARPS - 1) {          // ones row: D[K, f] = sum_p dY[p, f] (dY is zero filled past the image)
+                const int r = p.K;
+                *reinterpret_cast<float*>(a + (r >> 7) * (CBM * CBK * 4) + sw128_off(r & 127, lane)) = 1.0f;
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
         }
-        // ===== epilogue: atomically add the partial gW^T tile =====
-        if (nkb > 0) {
+        // ===== epilogue (warps 0-3): atomically add the partial gW^T tile =====
+        if (warp < 4 && nkb > 0) {
             mbar_wait(acc_full, 0);
             tc_fence_after();
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt) {
                 const int r = mt * CBM + warp * 32 + lane;
+                const int tap = r / p.C, c = r % p.C;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t v[32];
@@ -309,14 +315,14 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
                         const int f = n0 + c0 + j;
                         if (c0 + j < BN && f < p.F) {
                             const float g = __uint_as_float(v[j]) * p.inv_m;
-                            if (r < p.K) atomicAdd(p.gw + (size_t)f * p.K + r, g);       // lanes = consecutive k -> coalesced
+                            if (r < p.K) atomicAdd(p.gw + ((size_t)f * p.C + c) * khw + tap, g);
                             else if (r == p.K && p.gb) atomicAdd(p.gb + f, g);
                         }
                     }
                 }
             }
         }
-    } else if (warp == 4 && lane == 0) {
+    } else if (warp == WG_WARPS && lane == 0) {
         for (int i = 0; i < nkb; ++i) {
             const int s = i % ST;
             const long kb = kb0 + i;
@@ -324,7 +330,7 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
             mbar_arrive_expect_tx(&full[s], B_BYTES);
             tma_load_3d(sB + s * B_BYTES, &tmD, (int)(kb % p.pb_per_img) * 32, n0, (int)(kb / p.pb_per_img), &full[s]);
         }
-    } else if (warp == 5 && lane == 0) {
+    } else if (warp == WG_WARPS + 1 && lane == 0) {
         const uint32_t idesc = make_idesc_tf32(CBM, BN, 0, 0);
         for (int i = 0; i < nkb; ++i) {
             const int s = i % ST;
@@ -343,18 +349,18 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == WG_WARPS) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 static int pick_bn(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128)); }
 
 template <int BN, bool STRIDED>
 static int launch_gather(const char* name, const CUtensorMap& tb, const ConvGemmParams& p, cudaStream_t st) {
-    const size_t smem = CSTAGES * (CBM * CBK * 4 + BN * CBK * 4) + 128 + (size_t)p.Kp * 8 + 1024;
+    const size_t smem = CSTAGES * (CBM * CBK * 4 + BN * CBK * 4) + 128 + (size_t)p.Kp + 1024;
     cudaFuncSetAttribute(tc_conv_gather_kernel<BN, STRIDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const long npix = (long)p.B * p.Hd * p.Wd;
     dim3 grid((unsigned)((npix + CBM - 1) / CBM), (p.Cd + BN - 1) / BN);
-    tc_conv_gather_kernel<BN, STRIDED><<<grid, CONV_THREADS, smem, st>>>(tb, p);
+    tc_conv_gather_kernel<BN, STRIDED><<<grid, GATHER_THREADS, smem, st>>>(tb, p);
     DNB_LAUNCH_CHECK(name);
     return DNB_OK;
 }
@@ -381,16 +387,17 @@ static int run_gather(const char* name, const float* wprep, int n_pad, ConvGemmP
 using namespace tc;
 
 // workspace: [fwd filters: pad16(F) x pad32(C*khw)] [dgrad filters: pad16(C) x pad32(F*khw)]
-static size_t ws_fwd_floats(const dnb_win_t* g) { return (size_t)round_up(g->F, 128) * round_up(g->C * g->kh * g->kw, CBK); }
-static size_t ws_dgrad_floats(const dnb_win_t* g) { return (size_t)round_up(g->C, 128) * round_up(g->F * g->kh * g->kw, CBK); }
+static size_t ws_fwd_floats(const dnb_win_t* g) { return (size_t)round_up(g->F, 128) * round_up(round_up(g->C, 4) * g->kh * g->kw, CBK); }
+static size_t ws_dgrad_floats(const dnb_win_t* g) { return (size_t)round_up(g->C, 128) * round_up(round_up(g->F, 4) * g->kh * g->kw, CBK); }
 
 size_t tc_conv_ws_bytes(const dnb_win_t* g) { return (ws_fwd_floats(g) + ws_dgrad_floats(g)) * sizeof(float) + 256; }
 
 bool tc_conv_supported(const dnb_win_t* g, int kind) {
     if (!get_encode_tiled()) return false;
     const int khw = g->kh * g->kw;
-    if (kind == TC_CONV_FWD) return g->C * khw <= MAX_K && g->kh < 256 && g->kw < 256;
-    if (kind == TC_CONV_DGRAD) return g->F * khw <= MAX_K && g->kh < 256 && g->kw < 256;
+    // tiny reductions (C*kh*kw < 32, e.g. a 1-channel 3x3) are FMA/HBM work for the SIMT kernel, not a tensor-core shape
+    if (kind == TC_CONV_FWD) return g->C * khw >= 32 && round_up(g->C, 4) * khw <= MAX_K && g->kh < 128 && g->kw < 256;
+    if (kind == TC_CONV_DGRAD) return round_up(g->F, 4) * khw <= MAX_K && g->kh < 128 && g->kw < 256;
     // wgrad: dY rows are read by a 3-D TMA box -> 16-byte aligned plane pitch; M tiles limited by TMEM (512 columns)
     if ((g->OH * g->OW) % 4) return false;
     const int mt = (g->C * khw + 1 + CBM - 1) / CBM;
@@ -400,22 +407,22 @@ bool tc_conv_supported(const dnb_win_t* g, int kind) {
 
 int tc_conv_fwd(const float* x, const float* w, const float* b, float* y, const dnb_win_t* g, void* ws, cudaStream_t st) {
     if (!ws) return set_err(DNB_ERR_INVALID, "conv2d_fwd(tf32): workspace required");
-    const int K = g->C * g->kh * g->kw, Kp = round_up(K, CBK), n_pad = round_up(g->F, 128);
+    const int cp = round_up(g->C, 4), Kp = round_up(cp * g->kh * g->kw, CBK), n_pad = round_up(g->F, 128);
     float* wp = static_cast<float*>(ws);
-    prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, 0);
+    prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, cp, 0);
     DNB_LAUNCH_CHECK("conv2d_prep_weights");
-    ConvGemmParams p{x, y, b, g->B, g->C, g->H, g->W, g->F, g->OH, g->OW, g->kh, g->kw, K, Kp,
-                     g->sy, g->sx, 1, 1, g->pt, g->pl, (float)K};
+    ConvGemmParams p{x, y, b, g->B, g->C, g->H, g->W, g->F, g->OH, g->OW, g->kh, g->kw, cp, Kp,
+                     g->sy, g->sx, 1, 1, g->pt, g->pl, (float)(g->C * g->kh * g->kw)};
     return run_gather("tc_conv2d_fwd", wp, n_pad, p, st);
 }
 
 int tc_conv_dgrad(const float* dy, const float* w, float* dx, const dnb_win_t* g, void* ws, cudaStream_t st) {
     if (!ws) return set_err(DNB_ERR_INVALID, "conv2d_bwd(tf32): workspace required");
-    const int K = g->F * g->kh * g->kw, Kp = round_up(K, CBK), n_pad = round_up(g->C, 128);
+    const int cp = round_up(g->F, 4), Kp = round_up(cp * g->kh * g->kw, CBK), n_pad = round_up(g->C, 128);
     float* wp = static_cast<float*>(ws) + ws_fwd_floats(g);
-    prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, 1);
+    prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, cp, 1);
     DNB_LAUNCH_CHECK("conv2d_prep_weights_t");
-    ConvGemmParams p{dy, dx, nullptr, g->B, g->F, g->OH, g->OW, g->C, g->H, g->W, g->kh, g->kw, K, Kp,
+    ConvGemmParams p{dy, dx, nullptr, g->B, g->F, g->OH, g->OW, g->C, g->H, g->W, g->kh, g->kw, cp, Kp,
                      1, 1, g->sy, g->sx, g->kh - 1 - g->pt, g->kw - 1 - g->pl, 0.f};
     return run_gather("tc_conv2d_bwd_data", wp, n_pad, p, st);
 }
@@ -423,14 +430,14 @@ int tc_conv_dgrad(const float* dy, const float* w, float* dx, const dnb_win_t* g
 template <int MT, int BN>
 static int launch_wgrad(const CUtensorMap& td, WgradParams p, int fb, cudaStream_t st) {
     constexpr int ST = (MT == 1) ? 4 : 3;
-    const size_t smem = ST * (MT * CBM * CBK * 4 + BN * CBK * 4) + 128 + (size_t)MT * CBM * 8 + 1024;
+    const size_t smem = ST * (MT * CBM * CBK * 4 + BN * CBK * 4) + 128 + 1024;
     cudaFuncSetAttribute(tc_conv_wgrad_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const long total_kb = (long)p.B * p.pb_per_img;
     long ctas = std::min<long>(total_kb, std::max(1, kNumSMs / fb));
     p.kb_per_cta = (total_kb + ctas - 1) / ctas;
     ctas = (total_kb + p.kb_per_cta - 1) / p.kb_per_cta;
     dim3 grid((unsigned)ctas, fb);
-    tc_conv_wgrad_kernel<MT, BN><<<grid, CONV_THREADS, smem, st>>>(td, p);
+    tc_conv_wgrad_kernel<MT, BN><<<grid, WGRAD_THREADS, smem, st>>>(td, p);
     DNB_LAUNCH_CHECK("tc_conv2d_bwd_weight");
     return DNB_OK;
 }

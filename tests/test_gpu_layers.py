@@ -161,6 +161,48 @@ def test_config_shapes_vs_oracle(case, ns):
             assert e <= TOL32, (k, e)
 
 
+TC_KINDS = ("Dense", "Conv2D", "PointwiseConv2D")
+TOL_TF32 = 2e-2
+
+
+@pytest.mark.parametrize("case", [c for c in cases.LAYER_CASES + BIG_CASES if c["kind"] in TC_KINDS], ids=lambda c: c["name"])
+def test_tensor_core_path_vs_oracle(case, ns):
+    """math="tf32": tcgen05 kernels (TF32 operands, fp32 accumulation in TMEM) for Dense / Conv2D /
+    PointwiseConv2D, tolerance rel 2e-2 (BASELINE north_star); shapes the tensor path does not take
+    (tiny reductions, N < 32) transparently run the fp32 kernels."""
+    import dnpy_b200
+    dnpy_b200.set_math("tf32")
+    try:
+        got = drive.run_layer_case(ns, case)
+    finally:
+        dnpy_b200.set_math("fp32")
+    want = drive.run_layer_case_oracle(ns, case)
+    for k, w in want.items():
+        if k in got:
+            e = rel_err(np.asarray(got[k]).reshape(np.shape(w)), w)
+            assert e <= TOL_TF32, (k, e)
+
+
+def test_tc_gemm_all_operand_orientations():
+    """dnb_gemm_tf32: K-major and MN-major (128B swizzle with 32-byte atoms) operands, edge tiles."""
+    import torch
+    from dnpy_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(0)
+    for (M, N, K) in [(128, 128, 32), (256, 32, 96), (1024, 512, 784), (200, 100, 52), (1000, 36, 40)]:
+        A, B = torch.randn(M, K, device="cuda"), torch.randn(K, N, device="cuda")
+        ref = A.double() @ B.double()
+        for a_mn in (0, 1):
+            for b_mn in (0, 1):
+                a_st = A.t().contiguous() if a_mn else A.contiguous()
+                b_st = B.contiguous() if b_mn else B.t().contiguous()
+                C = torch.full((M, N), float("nan"), device="cuda")
+                _lib.check(lib.dnb_gemm_tf32(a_st.data_ptr(), b_st.data_ptr(), C.data_ptr(), M, N, K, a_mn, b_mn, None))
+                torch.cuda.synchronize()
+                err = float((C.double() - ref).abs().max() / ref.abs().max())
+                assert err <= 5e-3, (M, N, K, a_mn, b_mn, err)
+
+
 @pytest.mark.parametrize("case", [c for c in cases.LAYER_CASES + BIG_CASES if c["kind"] in ("MaxPool2D", "GlobalMaxPool2D")],
                          ids=lambda c: c["name"])
 def test_maxpool_per_sample_route(case, ns):

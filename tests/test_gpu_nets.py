@@ -148,6 +148,64 @@ def test_steps_along_the_reference_trajectory(name, kw, batch, steps, ns):
     assert flips <= max(1, steps // 10), f"{flips} of {steps} steps had an fp32 argmax near-tie"
 
 
+TF32_NETS = [
+    ("mnist_mlp", dict(h1=512, h2=256), 128, 6),
+    ("mnist_cnn", dict(f1=32, f2=64), 16, 6),
+    ("res_conv", dict(size=8, c1=32, c2=64), 32, 4),
+]
+
+
+@pytest.mark.parametrize("name,kw,batch,steps", TF32_NETS, ids=[c[0] for c in TF32_NETS])
+def test_tensor_core_steps_along_the_reference_trajectory(name, kw, batch, steps, ns):
+    """Same protocol with math="tf32" (tcgen05 Dense/Conv kernels): the loss within rel 2e-2 of the
+    float64 oracle at every visited parameter state, every gradient within 2e-2 of the largest gradient
+    of its layer chain (errors of ~1e-3 per TF32 contraction accumulate through the backward chain).
+    TF32 resolution (1e-3) makes pooling near-ties common: at most 1% of the argmax entries may differ,
+    and gradients are compared only for the layers ABOVE the lowest pool that flipped (everything below
+    it legitimately sees a different delta, massively so under the LITERAL routing)."""
+    import dnpy_b200
+    dnpy_b200.set_math("tf32")
+    try:
+        np.random.seed(42)
+        net = topologies.BUILDERS[name](ns, **kw)
+        onet = OracleNet.mirror(net)
+        net.set_mode("train")
+        onet.set_mode("train")
+        x, y = topologies.make_data(name, batch * 2, np.random.RandomState(1234), **kw)
+        compared = 0
+        for s in range(steps):
+            lo = (s % 2) * batch
+            xb, yb = [x[lo:lo + batch]], [y[lo:lo + batch]]
+            net.set_params([dict(n.params) for n in onet.fts])
+            loss = _manual_step(net, xb, yb)[0]
+            want = onet.step(xb, yb)[0]
+            assert abs(loss - want) <= 2e-2 * max(1.0, abs(want)), (s, loss, want)
+            first_ok = 0
+            for li, (l, n) in enumerate(zip(net.fts_layers, onet.fts)):
+                if "idx" in n.cache:
+                    diff = float(np.mean(np.asarray(l.output_idxs) != n.cache["idx"]))
+                    assert diff <= 0.01, (s, l.name, diff)
+                    if diff > 0:
+                        first_ok = li + 1
+            gmax = max([float(np.max(np.abs(g))) for n in onet.fts for g in n.grads.values()] + [1e-30])
+            for li, (l, n) in enumerate(zip(net.fts_layers, onet.fts)):
+                if li < first_ok:
+                    continue
+                for k, g in n.grads.items():
+                    # the reference's own gradient-check metric (tests/coverage/test_gradient_checking.py:
+                    # 32-92): ||a-b|| / (||a||+||b||) — norm-wise, because TF32 round-off flips a few relu
+                    # gates / near-zero pre-activations and each flip moves single entries by ~1/batch
+                    a = np.asarray(l.grads[k]).reshape(g.shape)
+                    if float(np.max(np.abs(g))) < 1e-3 * gmax:
+                        continue
+                    e = float(np.linalg.norm(a - g) / (np.linalg.norm(a) + np.linalg.norm(g)))
+                    assert e <= 2e-2, (s, l.name, k, e)
+                    compared += 1
+        assert compared > 0
+    finally:
+        dnpy_b200.set_math("fp32")
+
+
 def test_fit_evaluate_api(ns, capsys):
     """Net.fit / Net.evaluate end to end with the reference's print strings."""
     np.random.seed(42)
