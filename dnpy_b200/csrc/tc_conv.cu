@@ -68,7 +68,9 @@ struct ConvGemmParams {
 constexpr int GATHER_WARPS = 8;                                   // producer warps (also epilogue: warps 0-3)
 constexpr int GATHER_THREADS = (GATHER_WARPS + 2) * 32;            // + TMA warp + MMA warp
 
-template <int BN, bool STRIDED>
+// FAST: the gathered tensor has a multiple of 32 channels, so one 32-wide K block is ONE tap x 32
+// channels: a single bounds test per thread per K block, then 16 strided loads and 4 vector stores.
+template <int BN, bool STRIDED, bool FAST>
 __global__ void __launch_bounds__(GATHER_THREADS, 1)
 tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p) {
     constexpr int A_BYTES = CBM * CBK * 4, B_BYTES = BN * CBK * 4;
@@ -121,10 +123,37 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
         const float* sp = p.src + (long)b * p.Cs * plane_s;
         const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
         const int rx = row & 7;
+        int tap = 0, cb = 0, ti = 0, tj = 0;            // FAST: K block kb = (tap, 32-channel block cb)
+        const int cblks = p.Cs >> 5;
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % CSTAGES;
             if (kb >= CSTAGES) mbar_wait(&empty[s], ((kb / CSTAGES) - 1) & 1);
             uint8_t* a = sA + s * A_BYTES + row_off;
+            if (FAST) {
+                int ty = y0 + ti, tx = x0 + tj;
+                bool ok = valid && ty >= 0 && tx >= 0;
+                if (STRIDED) {
+                    ok = ok && (ty % p.div_y) == 0 && (tx % p.div_x) == 0;
+                    ty /= p.div_y; tx /= p.div_x;
+                }
+                ok = ok && ty < p.Hs && tx < p.Ws;
+                float4 v[4];
+                if (ok) {
+                    const float* g = sp + (long)(cb * 32 + half * 16) * plane_s + (long)ty * p.Ws + tx;
+                    float t[16];
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) t[n] = __ldg(g + n * plane_s);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4*>(a + ((((half * 4 + q) ^ rx) & 7) << 4)) = v[q];
+                if (++cb == cblks) { cb = 0; ++tap; if (++tj == p.kw) { tj = 0; ++ti; } }
+            } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int kc = half * 4 + q;
@@ -148,6 +177,7 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
                     }
                 }
                 *reinterpret_cast<float4*>(a + (((kc ^ rx) & 7) << 4)) = v;
+            }
             }
             fence_proxy_async_smem();           // generic-proxy stores -> visible to tcgen05.mma
             mbar_arrive(&full[s]);
@@ -278,6 +308,25 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
             const float* xb = p.x + (size_t)b * p.C * plane;
             if (i >= ST) mbar_wait(&empty[s], ((i / ST) - 1) & 1);
             uint8_t* a = sA + s * A_BYTES;
+            if ((p.C & 7) == 0) {
+                // C % 8 == 0: warp w owns channels c = w (mod 8) of EVERY tap, so (row & 7) == w is constant:
+                // the bounds test / pixel offset are hoisted per tap and the swizzled address just steps by 1024 B
+                const uint32_t coff = (uint32_t)(warp * 128 + ((((lane >> 2) ^ warp) & 7) << 4) + ((lane & 3) << 2));
+                int ti = 0, tj = 0;
+                for (int tap = 0; tap < khw; ++tap) {
+                    const int iy = y0 + ti, ix = x0 + tj;
+                    const bool ok = pv && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                    const float* g = xb + ((size_t)warp * p.H + iy) * p.W + ix;
+                    uint8_t* ar = a + (uint32_t)(((tap * p.C + warp) >> 3) * 1024) + coff;
+#pragma unroll 4
+                    for (int c = warp; c < p.C; c += WG_WARPS) {
+                        *reinterpret_cast<float*>(ar) = ok ? __ldg(g) : 0.f;
+                        g += 8 * plane;
+                        ar += 1024;
+                    }
+                    if (++tj == p.kw) { tj = 0; ++ti; }
+                }
+            } else {
             // rows r = tap*C + c are dealt round-robin to the producer warps (balanced for any C)
             int tap = warp / p.C, c = warp % p.C;
 #pragma unroll 4
@@ -288,6 +337,7 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
                 *reinterpret_cast<float*>(a + (r >> 7) * (CBM * CBK * 4) + sw128_off(r & 127, lane)) = val;
                 c += WG_WARPS;
                 while (c >= p.C) { c -= p.C; ++tap; }
+            }
             }
             if (warp == WG_WARPS - 1) {          // ones row: D[K, f] = sum_p dY[p, f] (dY is zero filled past the image)
                 const int r = p.K;
@@ -354,13 +404,13 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
 
 static int pick_bn(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128)); }
 
-template <int BN, bool STRIDED>
+template <int BN, bool STRIDED, bool FAST>
 static int launch_gather(const char* name, const CUtensorMap& tb, const ConvGemmParams& p, cudaStream_t st) {
     const size_t smem = CSTAGES * (CBM * CBK * 4 + BN * CBK * 4) + 128 + (size_t)p.Kp + 1024;
-    cudaFuncSetAttribute(tc_conv_gather_kernel<BN, STRIDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(tc_conv_gather_kernel<BN, STRIDED, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const long npix = (long)p.B * p.Hd * p.Wd;
     dim3 grid((unsigned)((npix + CBM - 1) / CBM), (p.Cd + BN - 1) / BN);
-    tc_conv_gather_kernel<BN, STRIDED><<<grid, GATHER_THREADS, smem, st>>>(tb, p);
+    tc_conv_gather_kernel<BN, STRIDED, FAST><<<grid, GATHER_THREADS, smem, st>>>(tb, p);
     DNB_LAUNCH_CHECK(name);
     return DNB_OK;
 }
@@ -372,7 +422,9 @@ static int run_gather(const char* name, const float* wprep, int n_pad, ConvGemmP
     uint32_t box[2] = {CBK, (uint32_t)bn};
     if (!make_tmap_f32(&tb, wprep, 2, dims, str, box)) return set_err(DNB_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", name);
     const bool strided = (p.div_y != 1 || p.div_x != 1);
-#define DNB_GO(BN_) (strided ? launch_gather<BN_, true>(name, tb, p, st) : launch_gather<BN_, false>(name, tb, p, st))
+    const bool fast = (p.Cs % 32) == 0;
+#define DNB_GO(BN_) (strided ? (fast ? launch_gather<BN_, true, true>(name, tb, p, st) : launch_gather<BN_, true, false>(name, tb, p, st)) \
+                             : (fast ? launch_gather<BN_, false, true>(name, tb, p, st) : launch_gather<BN_, false, false>(name, tb, p, st)))
     switch (bn) {
         case 16: return DNB_GO(16);
         case 32: return DNB_GO(32);
