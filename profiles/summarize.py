@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Turn ncu outputs brought back in gpurun_out/ into the small text summaries committed here.
+
+  python profiles/summarize.py launches gpurun_out/launches_X.csv  > profiles/r01_launches_X.txt
+  python profiles/summarize.py full     gpurun_out/prof_X.ncu-rep  > profiles/r01_full_X.txt
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_tensor.sum',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'l1tex__throughput.avg.pct_of_peak_sustained_active', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__inst_executed.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'launch__shared_mem_per_block_dynamic', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers']
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith('==')]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        v = float(row['Metric Value'].replace(',', ''))
+        u = row['Metric Unit']
+        v = v / 1e3 if u == 'ns' else (v * 1e3 if u == 'ms' else v)
+        a = agg.setdefault(row['Kernel Name'], [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(v[1] for v in agg.values())
+    print(f"# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n# {path}; total {tot/1e3:.3f} ms over {sum(v[0] for v in agg.values())} launches")
+    print(f"{'avg us':>10} {'count':>6} {'share':>7}  kernel")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{v[1]/v[0]:10.1f} {v[0]:6d} {100*v[1]/tot:6.1f}%  {k[:110]}")
+
+
+def full(path):
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    print(f"# ncu --set full --clock-control none; {path}")
+    for r in rows[2:]:
+        print(f"\n== {r[idx['Kernel Name']][:120]}")
+        for k in KEYS:
+            if k in idx:
+                print(f"   {k:70s} {r[idx[k]]} {units[idx[k]]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
