@@ -205,6 +205,9 @@ def run_cpu_reference(workload, steps, warmup, sample_batch=None):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything a library prints (NCCL banner ...) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -244,7 +247,8 @@ def main():
                                              f"oracle port, BLAS {r['blas']}"),
                     e2e=dict(value=r["value"], unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                     gpu_launches=0)
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
         return 0
 
     # ---------------------------------------------------------------- native arm (GPU)
@@ -304,18 +308,27 @@ def main():
         torch.cuda.current_stream().synchronize()      # the user reads the loss every step
         last["loss"] = float(loss_host[0])
 
-    for i in range(max(3, args.warmup)):
-        step_resident(i)
     sampler = ClockSampler(dev)
-    sampler.start()
+    sampler.start()                      # nvidia-smi needs ~100 ms to start: begin before the warm-up
+    t_w = time.perf_counter()
+    i_w = 0
+    while i_w < max(3, args.warmup) or (time.perf_counter() - t_w) < 0.5:     # >= 0.5 s under load before timing
+        step_resident(i_w)
+        i_w += 1
+        if i_w % 8 == 0:
+            torch.cuda.synchronize()
     ms, launches = timed(step_resident, args.steps)
-    clocks = sampler.stop()
     loss = float(last["o"][0][0].item())
+    if world > 1:
+        lt = torch.tensor([loss], device="cuda")
+        torch.distributed.all_reduce(lt)
+        loss = float(lt.item()) / world
     if not np.isfinite(loss):
         raise RuntimeError(f"non-finite loss {loss} during the benchmark")
     for i in range(2):
         step_e2e(i)
     ms_e2e, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop()
     value = batch * world * args.steps / (ms * 1e-3)
     e2e_value = batch * world * args.steps / (ms_e2e * 1e-3)
     h2d = int(px[0].numel() * px[0].element_size() + py[0].numel() * py[0].element_size())
@@ -372,7 +385,7 @@ def main():
                 roof = dict(bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"], traffic=None)
             roof.update(kernel=f"{tag}/{kname}", ms_per_launch=per_launch_ms, share_of_step=top["ms"] / total_ms,
                         algorithmic_bytes=byts, algorithmic_flops=flops, peak_source=pk["source"])
-        top5 = [dict(kernel=f"{t}/{k}", ms_per_step=e["ms"] / prof_steps, share=e["ms"] / total_ms) for (t, k), e in rows[:8]]
+        top5 = [dict(kernel=f"{t}/{k}", ms_per_step=e["ms"] / prof_steps, share=e["ms"] / total_ms) for (t, k), e in rows[:24]]
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -388,7 +401,8 @@ def main():
                     e2e=dict(value=e2e_value, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, top_kernels=top5, final_loss=loss)
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         parallel.shutdown()
     return 0

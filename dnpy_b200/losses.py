@@ -47,8 +47,8 @@ class Loss:
             bufs = (DArray.device(dev_empty((b, n))), dev_empty((2,)), dev_empty(((ws_bytes + 3) // 4,)))
             self._bufs = {key: bufs}
         delta, out, ws = bufs
-        # mean over the GLOBAL batch when the minibatch is sharded across ranks
-        scale = config.inv_world / float(b)
+        # mean over the LOCAL rows; under data parallelism Net averages the per-rank means when it reports
+        scale = 1.0 / float(b)
         _lib.call(self._kernel, p.ptr(), t.ptr(), delta.ptr(), out.data_ptr(), b, n, *self._extra(), scale,
                   ws.data_ptr(), stream_ptr())
         delta.written()

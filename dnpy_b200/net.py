@@ -402,6 +402,10 @@ class Net:
                     self.forward()
                     b_losses, b_deltas = self.compute_losses(y_target=y_mb)
                     b_metrics = self.compute_metrics(y_target=y_mb)
+                    if config.world > 1:          # report the global batch: mean of the per-rank means
+                        from . import parallel
+                        b_losses = parallel.mean_over_ranks(b_losses)
+                        b_metrics = [parallel.mean_over_ranks(m) for m in b_metrics]
                     str_eval = self._format_eval(b_losses, b_metrics)
                     if verbose:
                         print(f"\t - Batch {b+1}/{num_batches} - Losses[{', '.join(str_eval[0])}]; Metrics[{'; '.join(str_eval[1])}]")

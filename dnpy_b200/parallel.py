@@ -23,7 +23,8 @@ def init(backend=None):
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if torch.cuda.is_available():
-            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            # one GPU per rank; ranks wrap around when a test box has fewer GPUs than ranks (gloo only)
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count())
         dist.init_process_group(backend=backend)
     config.world = dist.get_world_size()
     config.rank = dist.get_rank()
@@ -57,6 +58,18 @@ def allreduce_flat(tensor):
     if config.world > 1:
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
     return tensor
+
+
+def mean_over_ranks(values):
+    """Average a short list of Python floats over the ranks (equal shards => global mean)."""
+    import torch
+    import torch.distributed as dist
+    if config.world == 1:
+        return values
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64,
+                     device="cuda" if (torch.cuda.is_available() and dist.get_backend() == "nccl") else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) / config.world for v in t.tolist()]
 
 
 def allreduce_grads(net):
