@@ -33,6 +33,52 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restric
     }
 }
 
+// Fast path for unpadded pools with compile-time window/stride and an even input row pitch: a thread
+// produces FOUR adjacent outputs of one row, reading each input row once with 8-byte loads
+// ((3*S + K) columns instead of 4*K scalar loads) and 32-bit index arithmetic.
+template <int K, int S>
+__global__ void __launch_bounds__(256) maxpool_fwd_strip_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                int32_t* __restrict__ idx, int planes, int H, int W, int OH, int OW) {
+    constexpr int NCOL = 3 * S + K;                    // input columns feeding 4 outputs
+    constexpr int NV = (NCOL + 1) / 2;                 // float2 loads per row
+    const int spr = (OW + 3) >> 2;
+    const long total = (long)planes * OH * spr;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const int sx = (int)(t % spr);
+        const long r = t / spr;
+        const int oy = (int)(r % OH);
+        const long pl = r / OH;
+        const int ox0 = sx * 4;
+        const float* xp = x + pl * (long)H * W + (long)(oy * S) * W + ox0 * S;
+        float best[4];
+        int bi[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) { best[p] = 0.f; bi[p] = -1; }
+        const int ncol_ok = W - ox0 * S;               // columns available in this row from ox0*S on
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            float v[2 * NV];
+            const float2* rp = reinterpret_cast<const float2*>(xp + (long)i * W);
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                if (2 * q + 1 < ncol_ok) { float2 f = __ldg(rp + q); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+                else { v[2 * q] = (2 * q < ncol_ok) ? __ldg(xp + (long)i * W + 2 * q) : 0.f; v[2 * q + 1] = 0.f; }
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const float c = v[p * S + j];
+                    if (bi[p] < 0 || c > best[p] || (c != c && best[p] == best[p])) { best[p] = c; bi[p] = i * K + j; }
+                }
+        }
+        const long o = (pl * OH + oy) * (long)OW + ox0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+            if (ox0 + p < OW) { y[o + p] = best[p]; idx[o + p] = bi[p]; }
+    }
+}
+
 // PER_SAMPLE: dx[b,c,iy,ix] = sum over windows covering it whose argmax points here.
 __global__ void __launch_bounds__(256) maxpool_bwd_per_sample_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx,
                                                                      float* __restrict__ dx, dnb_win_t g) {
@@ -152,6 +198,17 @@ int dnb_maxpool2d_fwd(const float* x, float* y, int32_t* idx, const dnb_win_t* g
     long n = (long)g->B * g->C * g->OH * g->OW;
     if (n == 0) return DNB_OK;
     DNB_CHECK_ARG(x && y && idx, "maxpool2d_fwd: null pointer");
+    const bool nopad = !(g->pt | g->pb | g->pl | g->pr);
+    const bool even = (g->W % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+    if (nopad && even && g->kh == g->kw && g->sy == g->sx && g->sy == 2 && (g->kh == 2 || g->kh == 3) &&
+        (g->OH - 1) * g->sy + g->kh <= g->H) {
+        const long strips = (long)g->B * g->C * g->OH * ((g->OW + 3) / 4);
+        const int planes = g->B * g->C;
+        if (g->kh == 3) maxpool_fwd_strip_kernel<3, 2><<<ew_grid(strips, 256), 256, 0, S(stream)>>>(x, y, idx, planes, g->H, g->W, g->OH, g->OW);
+        else maxpool_fwd_strip_kernel<2, 2><<<ew_grid(strips, 256), 256, 0, S(stream)>>>(x, y, idx, planes, g->H, g->W, g->OH, g->OW);
+        DNB_LAUNCH_CHECK("maxpool2d_fwd");
+        return DNB_OK;
+    }
     maxpool_fwd_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(x, y, idx, *g);
     DNB_LAUNCH_CHECK("maxpool2d_fwd");
     return DNB_OK;

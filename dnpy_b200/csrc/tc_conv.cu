@@ -129,6 +129,7 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
             const int s = kb % CSTAGES;
             if (kb >= CSTAGES) mbar_wait(&empty[s], ((kb / CSTAGES) - 1) & 1);
             uint8_t* a = sA + s * A_BYTES + row_off;
+            const uint32_t a_s = smem_u32(a);
             if (FAST) {
                 int ty = y0 + ti, tx = x0 + tj;
                 bool ok = valid && ty >= 0 && tx >= 0;
@@ -150,8 +151,7 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
                     for (int q = 0; q < 4; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<float4*>(a + ((((half * 4 + q) ^ rx) & 7) << 4)) = v[q];
+                for (int q = 0; q < 4; ++q) sts128(a_s + ((((half * 4 + q) ^ rx) & 7) << 4), v[q]);
                 if (++cb == cblks) { cb = 0; ++tap; if (++tj == p.kw) { tj = 0; ++ti; } }
             } else {
 #pragma unroll
@@ -176,24 +176,34 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
                         if (c0 + 3 < p.Cs) v.w = __ldg(g + 3 * plane_s);
                     }
                 }
-                *reinterpret_cast<float4*>(a + (((kc ^ rx) & 7) << 4)) = v;
+                sts128(a_s + (((kc ^ rx) & 7) << 4), v);
             }
             }
             fence_proxy_async_smem();           // generic-proxy stores -> visible to tcgen05.mma
             mbar_arrive(&full[s]);
         }
-        // ===== epilogue (warps 0-3 own the four TMEM lane quadrants) =====
-        if (warp < 4) {
+        // ===== epilogue: warp w reads TMEM lane quadrant (w & 3); warps 0-3 take the lower half of the
+        // columns, warps 4-7 the upper half (pixel rows 0..127 map to lanes, so thread -> pixel (warp&3)*32+lane)
+        {
+            const int erow = (warp & 3) * 32 + lane;
+            const long epix = m0 + erow;
+            const bool ev = epix < npix;
+            int eb = 0, ey = 0, ex = 0;
+            if (ev) { ex = (int)(epix % p.Wd); long t = epix / p.Wd; ey = (int)(t % p.Hd); eb = (int)(t / p.Hd); }
             mbar_wait(acc_full, 0);
             tc_fence_after();
             const size_t plane = (size_t)p.Hd * p.Wd;
-            float* dp = p.dst + ((size_t)b * p.Cd) * plane + (size_t)y * p.Wd + x;
+            float* dp = p.dst + ((size_t)eb * p.Cd) * plane + (size_t)ey * p.Wd + ex;
+            constexpr int NCH = (BN + 31) / 32;               // 32-column chunks
+            constexpr int PER = (NCH + 1) / 2;
+            const int ch_lo = (warp >> 2) * PER, ch_hi = (warp >> 2) ? NCH : PER;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                const int c0 = ch * 32;
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
                 tmem_ld_wait();
-                if (valid) {
+                if (ev) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int d = n0 + c0 + j;
@@ -312,19 +322,44 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
                 // C % 8 == 0: warp w owns channels c = w (mod 8) of EVERY tap, so (row & 7) == w is constant:
                 // the bounds test / pixel offset are hoisted per tap and the swizzled address just steps by 1024 B
                 const uint32_t coff = (uint32_t)(warp * 128 + ((((lane >> 2) ^ warp) & 7) << 4) + ((lane & 3) << 2));
+                const uint32_t a_s = smem_u32(a) + coff;
+                const int nch = p.C >> 3;                 // channels of this warp per tap
+                if (khw == 9 && nch <= 4) {
+                    // 3x3 window, <= 32 channels: issue every load of the stage (9 taps x nch channels) before
+                    // the first store — one memory latency per stage instead of nine
+                    float v[9][4];
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int iy = y0 + tap / 3, ix = x0 + tap % 3;
+                        const bool ok = pv && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                        const float* g = xb + ((size_t)warp * p.H + iy) * p.W + ix;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) v[tap][u] = (ok && u < nch) ? __ldg(g + (size_t)u * 8 * plane) : 0.f;
+                    }
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t ar = a_s + (uint32_t)(((tap * p.C + warp) >> 3) * 1024);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (u < nch) sts32(ar + u * 1024, v[tap][u]);
+                    }
+                } else {
                 int ti = 0, tj = 0;
                 for (int tap = 0; tap < khw; ++tap) {
                     const int iy = y0 + ti, ix = x0 + tj;
                     const bool ok = pv && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
                     const float* g = xb + ((size_t)warp * p.H + iy) * p.W + ix;
-                    uint8_t* ar = a + (uint32_t)(((tap * p.C + warp) >> 3) * 1024) + coff;
-#pragma unroll 4
-                    for (int c = warp; c < p.C; c += WG_WARPS) {
-                        *reinterpret_cast<float*>(ar) = ok ? __ldg(g) : 0.f;
-                        g += 8 * plane;
-                        ar += 1024;
+                    const uint32_t ar = a_s + (uint32_t)(((tap * p.C + warp) >> 3) * 1024);
+                    for (int c0 = 0; c0 < nch; c0 += 4) {     // batches of 4 independent loads
+                        float v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) v[u] = (ok && c0 + u < nch) ? __ldg(g + (size_t)(c0 + u) * 8 * plane) : 0.f;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (c0 + u < nch) sts32(ar + (c0 + u) * 1024, v[u]);
                     }
                     if (++tj == p.kw) { tj = 0; ++ti; }
+                }
                 }
             } else {
             // rows r = tap*C + c are dealt round-robin to the producer warps (balanced for any C)
