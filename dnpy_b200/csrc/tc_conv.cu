@@ -70,7 +70,9 @@ constexpr int GATHER_THREADS = (GATHER_WARPS + 2) * 32;            // + TMA warp
 
 // FAST: the gathered tensor has a multiple of 32 channels, so one 32-wide K block is ONE tap x 32
 // channels: a single bounds test per thread per K block, then 16 strided loads and 4 vector stores.
-template <int BN, bool STRIDED, bool FAST>
+// PLS: compile-time source plane size Hs*Ws (0 = runtime): lets the 16 channel-strided loads of a K block
+// use immediate offsets from ONE base address instead of 64-bit address arithmetic per element.
+template <int BN, bool STRIDED, bool FAST, int PLS>
 __global__ void __launch_bounds__(GATHER_THREADS, 1)
 tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p) {
     constexpr int A_BYTES = CBM * CBK * 4, B_BYTES = BN * CBK * 4;
@@ -119,41 +121,46 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
         int b = 0, y = 0, x = 0;
         if (valid) { x = (int)(pix % p.Wd); long t = pix / p.Wd; y = (int)(t % p.Hd); b = (int)(t / p.Hd); }
         const int y0 = y * p.mul_y - p.off_y, x0 = x * p.mul_x - p.off_x;
-        const long plane_s = (long)p.Hs * p.Ws;
+        const long plane_s = PLS ? (long)PLS : (long)p.Hs * p.Ws;
         const float* sp = p.src + (long)b * p.Cs * plane_s;
         const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
         const int rx = row & 7;
-        int tap = 0, cb = 0, ti = 0, tj = 0;            // FAST: K block kb = (tap, 32-channel block cb)
+        int cb = 0, ti = 0, tj = 0;                     // FAST: K block kb = (tap (ti,tj), 32-channel block cb)
         const int cblks = p.Cs >> 5;
+        float tn[16];                                   // FAST: the NEXT K block's 16 values, loaded one block ahead
+        auto fast_load = [&](float (&t)[16]) {
+            int ty = y0 + ti, tx = x0 + tj;
+            bool ok = valid && ty >= 0 && tx >= 0;
+            if (STRIDED) {
+                ok = ok && (ty % p.div_y) == 0 && (tx % p.div_x) == 0;
+                ty /= p.div_y; tx /= p.div_x;
+            }
+            ok = ok && ty < p.Hs && tx < p.Ws;
+            if (ok) {
+                const float* g = sp + (long)(cb * 32 + half * 16) * plane_s + (long)ty * p.Ws + tx;
+#pragma unroll
+                for (int n = 0; n < 16; ++n) t[n] = PLS ? __ldg(g + n * PLS) : __ldg(g + n * plane_s);
+            } else {
+#pragma unroll
+                for (int n = 0; n < 16; ++n) t[n] = 0.f;
+            }
+            if (++cb == cblks) { cb = 0; if (++tj == p.kw) { tj = 0; ++ti; } }
+        };
+        if (FAST && nkb > 0) fast_load(tn);
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % CSTAGES;
-            if (kb >= CSTAGES) mbar_wait(&empty[s], ((kb / CSTAGES) - 1) & 1);
             uint8_t* a = sA + s * A_BYTES + row_off;
             const uint32_t a_s = smem_u32(a);
             if (FAST) {
-                int ty = y0 + ti, tx = x0 + tj;
-                bool ok = valid && ty >= 0 && tx >= 0;
-                if (STRIDED) {
-                    ok = ok && (ty % p.div_y) == 0 && (tx % p.div_x) == 0;
-                    ty /= p.div_y; tx /= p.div_x;
-                }
-                ok = ok && ty < p.Hs && tx < p.Ws;
                 float4 v[4];
-                if (ok) {
-                    const float* g = sp + (long)(cb * 32 + half * 16) * plane_s + (long)ty * p.Ws + tx;
-                    float t[16];
 #pragma unroll
-                    for (int n = 0; n < 16; ++n) t[n] = __ldg(g + n * plane_s);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int q = 0; q < 4; ++q) v[q] = make_float4(tn[4 * q], tn[4 * q + 1], tn[4 * q + 2], tn[4 * q + 3]);
+                if (kb + 1 < nkb) fast_load(tn);          // next block's loads fly while this one is stored
+                if (kb >= CSTAGES) mbar_wait(&empty[s], ((kb / CSTAGES) - 1) & 1);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) sts128(a_s + ((((half * 4 + q) ^ rx) & 7) << 4), v[q]);
-                if (++cb == cblks) { cb = 0; ++tap; if (++tj == p.kw) { tj = 0; ++ti; } }
             } else {
+            if (kb >= CSTAGES) mbar_wait(&empty[s], ((kb / CSTAGES) - 1) & 1);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int kc = half * 4 + q;
@@ -204,14 +211,17 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
                 tmem_ld_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
                 tmem_ld_wait();
                 if (ev) {
+                    float* o = dp + (size_t)(n0 + c0) * plane;
+                    const int nvalid = min(32, min(BN - c0, p.Cd - (n0 + c0)));
+                    if (p.bias) {
+                        const float* bp = p.bias + n0 + c0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int d = n0 + c0 + j;
-                        if (c0 + j < BN && d < p.Cd) {
-                            float r = __uint_as_float(v[j]);
-                            if (p.bias) r += p.bias_k * p.bias[d];
-                            dp[(size_t)d * plane] = r;      // lanes = consecutive pixels -> coalesced per channel plane
-                        }
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) { *o = fmaf(p.bias_k, __ldg(bp + j), __uint_as_float(v[j])); o += plane; }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) { *o = __uint_as_float(v[j]); o += plane; }   // lanes = consecutive pixels -> coalesced
                     }
                 }
             }
@@ -439,13 +449,13 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
 
 static int pick_bn(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128)); }
 
-template <int BN, bool STRIDED, bool FAST>
+template <int BN, bool STRIDED, bool FAST, int PLS>
 static int launch_gather(const char* name, const CUtensorMap& tb, const ConvGemmParams& p, cudaStream_t st) {
     const size_t smem = CSTAGES * (CBM * CBK * 4 + BN * CBK * 4) + 128 + (size_t)p.Kp + 1024;
-    cudaFuncSetAttribute(tc_conv_gather_kernel<BN, STRIDED, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(tc_conv_gather_kernel<BN, STRIDED, FAST, PLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const long npix = (long)p.B * p.Hd * p.Wd;
     dim3 grid((unsigned)((npix + CBM - 1) / CBM), (p.Cd + BN - 1) / BN);
-    tc_conv_gather_kernel<BN, STRIDED, FAST><<<grid, GATHER_THREADS, smem, st>>>(tb, p);
+    tc_conv_gather_kernel<BN, STRIDED, FAST, PLS><<<grid, GATHER_THREADS, smem, st>>>(tb, p);
     DNB_LAUNCH_CHECK(name);
     return DNB_OK;
 }
@@ -458,14 +468,22 @@ static int run_gather(const char* name, const float* wprep, int n_pad, ConvGemmP
     if (!make_tmap_f32(&tb, wprep, 2, dims, str, box)) return set_err(DNB_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", name);
     const bool strided = (p.div_y != 1 || p.div_x != 1);
     const bool fast = (p.Cs % 32) == 0;
-#define DNB_GO(BN_) (strided ? (fast ? launch_gather<BN_, true, true>(name, tb, p, st) : launch_gather<BN_, true, false>(name, tb, p, st)) \
-                             : (fast ? launch_gather<BN_, false, true>(name, tb, p, st) : launch_gather<BN_, false, false>(name, tb, p, st)))
+    const int pls = p.Hs * p.Ws;
+    // fast path instantiated for the plane sizes of the BASELINE configs (12x12, 16x16, 32x32, 64x64); others run PLS=0
+#define DNB_FAST(BN_, ST_) (pls == 144 ? launch_gather<BN_, ST_, true, 144>(name, tb, p, st) \
+                          : pls == 256 ? launch_gather<BN_, ST_, true, 256>(name, tb, p, st) \
+                          : pls == 1024 ? launch_gather<BN_, ST_, true, 1024>(name, tb, p, st) \
+                          : pls == 4096 ? launch_gather<BN_, ST_, true, 4096>(name, tb, p, st) \
+                          : launch_gather<BN_, ST_, true, 0>(name, tb, p, st))
+#define DNB_GO(BN_) (strided ? (fast ? DNB_FAST(BN_, true) : launch_gather<BN_, true, false, 0>(name, tb, p, st)) \
+                             : (fast ? DNB_FAST(BN_, false) : launch_gather<BN_, false, false, 0>(name, tb, p, st)))
     switch (bn) {
         case 16: return DNB_GO(16);
         case 32: return DNB_GO(32);
         case 64: return DNB_GO(64);
         default: return DNB_GO(128);
     }
+#undef DNB_FAST
 #undef DNB_GO
 }
 
