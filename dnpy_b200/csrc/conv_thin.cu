@@ -25,7 +25,8 @@ struct ThinArgs {
     long strips_per_cta;
 };
 
-template <int C>
+// VEC2: x0 is even, W is even and the tensor base is 8-byte aligned, so each window row is three 8-byte loads
+template <int C, bool VEC2>
 __device__ __forceinline__ void load_window(float (&win)[C][3][6], const float* __restrict__ xb, int H, int W, int y0, int x0) {
 #pragma unroll
     for (int c = 0; c < C; ++c)
@@ -34,16 +35,27 @@ __device__ __forceinline__ void load_window(float (&win)[C][3][6], const float* 
             const int iy = y0 + i;
             const bool rok = iy >= 0 && iy < H;
             const float* r = xb + ((long)c * H + iy) * W;
+            if (VEC2) {
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const int ix = x0 + j;
-                win[c][i][j] = (rok && ix >= 0 && ix < W) ? __ldg(r + ix) : 0.f;
+                for (int j = 0; j < 6; j += 2) {
+                    const int ix = x0 + j;
+                    float2 v = make_float2(0.f, 0.f);
+                    if (rok && ix >= 0 && ix + 1 < W) v = __ldg(reinterpret_cast<const float2*>(r + ix));
+                    else if (rok && ix >= 0 && ix < W) v.x = __ldg(r + ix);
+                    win[c][i][j] = v.x; win[c][i][j + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int ix = x0 + j;
+                    win[c][i][j] = (rok && ix >= 0 && ix < W) ? __ldg(r + ix) : 0.f;
+                }
             }
         }
 }
 
 // ---- forward ---------------------------------------------------------------------------------------
-template <int C>
+template <int C, bool VEC2>
 __global__ void __launch_bounds__(256) thin_fwd_kernel(ThinArgs a) {
     constexpr int K = C * 9;
     extern __shared__ __align__(16) float sm[];
@@ -66,7 +78,7 @@ __global__ void __launch_bounds__(256) thin_fwd_kernel(ThinArgs a) {
     const int b = (int)(t / a.OH);
     const int xs = sx * 4;
     float win[C][3][6];
-    load_window<C>(win, a.x + (long)b * C * a.H * a.W, a.H, a.W, oy - a.pt, xs - a.pl);
+    load_window<C, VEC2>(win, a.x + (long)b * C * a.H * a.W, a.H, a.W, oy - a.pt, xs - a.pl);
     const long plane = (long)a.OH * a.OW;
     float* yb = a.y + (long)b * a.F * plane + (long)oy * a.OW + xs;
     for (int f0 = 0; f0 < a.F; f0 += 16) {
@@ -100,16 +112,21 @@ __global__ void __launch_bounds__(256) thin_fwd_kernel(ThinArgs a) {
             if (f0 + f < a.F) {
                 const float bb = sb[f0 + f];
                 float* yr = yb + (long)(f0 + f) * plane;
+                if (VEC2) {          // OW even, xs % 4 == 0: pairs are either fully inside or fully outside the row
+                    if (xs + 1 < a.OW) *reinterpret_cast<float2*>(yr) = make_float2(acc[0][f] + bb, acc[1][f] + bb);
+                    if (xs + 3 < a.OW) *reinterpret_cast<float2*>(yr + 2) = make_float2(acc[2][f] + bb, acc[3][f] + bb);
+                } else {
 #pragma unroll
-                for (int p = 0; p < 4; ++p)
-                    if (xs + p < a.OW) yr[p] = acc[p][f] + bb;
+                    for (int p = 0; p < 4; ++p)
+                        if (xs + p < a.OW) yr[p] = acc[p][f] + bb;
+                }
             }
         }
     }
 }
 
 // ---- weight gradient ------------------------------------------------------------------------------
-template <int C, int FT>
+template <int C, int FT, bool VEC2>
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(ThinArgs a) {
     constexpr int K = C * 9, NA = FT * (K + 1);
     __shared__ float red[8][NA];
@@ -132,13 +149,22 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(ThinArgs a) {
         const int b = (int)(t / a.OH);
         const int xs = sx * 4;
         float win[C][3][6];
-        load_window<C>(win, a.x + (long)b * C * a.H * a.W, a.H, a.W, oy - a.pt, xs - a.pl);
+        load_window<C, VEC2>(win, a.x + (long)b * C * a.H * a.W, a.H, a.W, oy - a.pt, xs - a.pl);
         const float* db = a.dy + ((long)b * a.F + f0) * plane + (long)oy * a.OW + xs;
 #pragma unroll
         for (int f = 0; f < FT; ++f) {
             float d[4];
+            if (VEC2) {
+                float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+                if (f0 + f < a.F) {
+                    if (xs + 1 < a.OW) lo = __ldg(reinterpret_cast<const float2*>(db + (long)f * plane));
+                    if (xs + 3 < a.OW) hi = __ldg(reinterpret_cast<const float2*>(db + (long)f * plane + 2));
+                }
+                d[0] = lo.x; d[1] = lo.y; d[2] = hi.x; d[3] = hi.y;
+            } else {
 #pragma unroll
             for (int p = 0; p < 4; ++p) d[p] = (f0 + f < a.F && xs + p < a.OW) ? __ldg(db + (long)f * plane + p) : 0.f;
+            }
             acc[f][K] += (d[0] + d[1]) + (d[2] + d[3]);
 #pragma unroll
             for (int c = 0; c < C; ++c)
@@ -176,7 +202,7 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(ThinArgs a) {
 
 // ---- data gradient --------------------------------------------------------------------------------
 // dx[c,iy,ix] = sum_f sum_{i,j} dY[f, iy+pt-i, ix+pl-j] * W[f,c,i,j]
-template <int C>
+template <int C, bool VEC2>
 __global__ void __launch_bounds__(256) thin_dgrad_kernel(ThinArgs a) {
     constexpr int K = C * 9;
     extern __shared__ __align__(16) float sm[];       // [F][K] weights
@@ -211,8 +237,17 @@ __global__ void __launch_bounds__(256) thin_dgrad_kernel(ThinArgs a) {
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
             const float* dr = df + (long)(r0 + r) * a.OW + c0;
+            if (VEC2) {          // c0 even, OW even: a pair is inside or outside as a whole
 #pragma unroll
-            for (int s = 0; s < 6; ++s) dw[r][s] = (rok[r] && cok[s]) ? __ldg(dr + s) : 0.f;
+                for (int s = 0; s < 6; s += 2) {
+                    float2 v = make_float2(0.f, 0.f);
+                    if (rok[r] && cok[s]) v = __ldg(reinterpret_cast<const float2*>(dr + s));
+                    dw[r][s] = v.x; dw[r][s + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < 6; ++s) dw[r][s] = (rok[r] && cok[s]) ? __ldg(dr + s) : 0.f;
+            }
         }
         const float* wf = sm + f * K;
 #pragma unroll
@@ -245,13 +280,21 @@ bool thin_conv_supported(const dnb_win_t* g) {
     return g->C >= 1 && g->C <= 4 && g->kh == 3 && g->kw == 3 && g->sy == 1 && g->sx == 1 && g->F <= 1024;
 }
 
+static inline bool al8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+
 template <int C>
 static int thin_fwd_c(const ThinArgs& a, cudaStream_t st) {
     const int FP = (a.F + 15) & ~15;
     const size_t smem = (size_t)(C * 9 + 1) * FP * sizeof(float);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(thin_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const long total = (long)a.B * a.OH * ((a.OW + 3) >> 2);
-    thin_fwd_kernel<C><<<(unsigned)((total + 255) / 256), 256, smem, st>>>(a);
+    const bool v2 = (a.W % 2 == 0) && (a.OW % 2 == 0) && (a.pl % 2 == 0) && al8(a.x) && al8(a.y);
+    if (v2) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(thin_fwd_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        thin_fwd_kernel<C, true><<<(unsigned)((total + 255) / 256), 256, smem, st>>>(a);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(thin_fwd_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        thin_fwd_kernel<C, false><<<(unsigned)((total + 255) / 256), 256, smem, st>>>(a);
+    }
     DNB_LAUNCH_CHECK("thin_conv2d_fwd");
     return DNB_OK;
 }
@@ -264,7 +307,9 @@ static int thin_wgrad_c(ThinArgs a, cudaStream_t st) {
     a.strips_per_cta = (total + splits - 1) / splits;
     splits = (total + a.strips_per_cta - 1) / a.strips_per_cta;
     dim3 grid((unsigned)splits, fgroups);
-    thin_wgrad_kernel<C, FT><<<grid, 256, 0, st>>>(a);
+    const bool v2 = (a.W % 2 == 0) && (a.OW % 2 == 0) && (a.pl % 2 == 0) && al8(a.x) && al8(a.dy);
+    if (v2) thin_wgrad_kernel<C, FT, true><<<grid, 256, 0, st>>>(a);
+    else thin_wgrad_kernel<C, FT, false><<<grid, 256, 0, st>>>(a);
     DNB_LAUNCH_CHECK("thin_conv2d_bwd_weight");
     return DNB_OK;
 }
@@ -272,9 +317,16 @@ static int thin_wgrad_c(ThinArgs a, cudaStream_t st) {
 template <int C>
 static int thin_dgrad_c(const ThinArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)a.F * C * 9 * sizeof(float);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(thin_dgrad_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const long total = (long)a.B * ((a.H + 3) >> 2) * ((a.W + 3) >> 2);
-    thin_dgrad_kernel<C><<<(unsigned)((total + 255) / 256), 256, smem, st>>>(a);
+    // the 6x6 dY window starts at column ix0 + pl - 2 (ix0 % 4 == 0): even iff pl is even
+    const bool v2 = (a.OW % 2 == 0) && (a.pl % 2 == 0) && al8(a.dy);
+    if (v2) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(thin_dgrad_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        thin_dgrad_kernel<C, true><<<(unsigned)((total + 255) / 256), 256, smem, st>>>(a);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(thin_dgrad_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        thin_dgrad_kernel<C, false><<<(unsigned)((total + 255) / 256), 256, smem, st>>>(a);
+    }
     DNB_LAUNCH_CHECK("thin_conv2d_bwd_data");
     return DNB_OK;
 }
@@ -290,7 +342,7 @@ int thin_conv_fwd(const float* x, const float* w, const float* b, float* y, cons
 }
 
 int thin_conv_bwd(const float* x, const float* w, const float* dy, float* dx, float* gw, float* gb,
-                  const dnb_win_t* g, float inv_m, cudaStream_t st) {
+                  const dnb_win_t* g, float inv_m, bool skip_wgrad, cudaStream_t st) {
     ThinArgs a{x, w, nullptr, nullptr, dy, dx, gw, gb, g->B, g->H, g->W, g->F, g->OH, g->OW, g->pt, g->pl, inv_m, 0};
     int rc;
     if (dx) {
@@ -302,6 +354,7 @@ int thin_conv_bwd(const float* x, const float* w, const float* dy, float* dx, fl
         }
         if (rc) return rc;
     }
+    if (skip_wgrad) return DNB_OK;          // the tensor-core wgrad takes it (math == tf32)
     switch (g->C) {
         case 1: return thin_wgrad_c<1, 8>(a, st);
         case 2: return thin_wgrad_c<2, 4>(a, st);

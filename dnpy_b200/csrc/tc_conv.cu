@@ -272,11 +272,17 @@ struct WgradParams {
 constexpr int WG_WARPS = 8;
 constexpr int WGRAD_THREADS = (WG_WARPS + 2) * 32;
 
-template <int MT, int BN>
+// THINK ("thin K"): at most 32 rows (K+1 <= 32, e.g. one input channel x 3x3).  The A block of a stage is
+// then only 32 x 32 floats (the MMA still reads 128 rows: rows >= 32 alias later shared memory, produce
+// garbage in TMEM lanes that are never read) which frees shared memory for a 16-deep ring: the kernel is a
+// pure dY stream and needs ~64 KB of TMA loads in flight per SM to cover HBM latency.
+template <int MT, int BN, bool THINK>
 __global__ void __launch_bounds__(WGRAD_THREADS, 1)
 tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
-    constexpr int ST = (MT == 1) ? 4 : 3;
-    constexpr int A_BYTES = MT * CBM * CBK * 4, B_BYTES = BN * CBK * 4;
+    constexpr int SUB = THINK ? 2 : 1;                 // 32-pixel sub-blocks per ring stage (amortises the barrier round trip)
+    constexpr int ST = THINK ? 8 : ((MT == 1) ? 4 : 3);
+    constexpr int A_SUB = THINK ? 32 * CBK * 4 : MT * CBM * CBK * 4, B_SUB = BN * CBK * 4;
+    constexpr int A_BYTES = SUB * A_SUB, B_BYTES = SUB * B_SUB;
     constexpr uint32_t TMEM_COLS = (MT * BN <= 32) ? 32 : (MT * BN <= 64) ? 64 : (MT * BN <= 128) ? 128 : (MT * BN <= 256) ? 256 : 512;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -293,14 +299,22 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
     const long total_kb = (long)p.B * p.pb_per_img;
     const long kb0 = (long)blockIdx.x * p.kb_per_cta;
     const long kb1 = min(total_kb, kb0 + p.kb_per_cta);
-    const int nkb = (int)max(0L, kb1 - kb0);
+    const int nkb_sub = (int)max(0L, kb1 - kb0);            // 32-pixel blocks of this CTA
+    const int nkb = (nkb_sub + SUB - 1) / SUB;               // ring stages
     const int n0 = blockIdx.y * BN;
+    constexpr bool thin_k = THINK;
+    __shared__ int s_rowc[32], s_rowy[32], s_rowx[32];
+    if (thin_k && tid < 32) {
+        if (tid < p.K) { const int tap = tid / p.C; s_rowc[tid] = tid % p.C; s_rowy[tid] = tap / p.kw; s_rowx[tid] = tap % p.kw; }
+        else { s_rowc[tid] = -1; s_rowy[tid] = 0; s_rowx[tid] = 0; }
+    }
 
     // rows past K+1 are never written by the producers: clear the ring once
     for (int e = tid; e < ST * A_BYTES / 16; e += WGRAD_THREADS) reinterpret_cast<float4*>(sA)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
         tma_prefetch_desc(&tmD);
-        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], WG_WARPS + 1); mbar_init(&empty[s], 1); }
+        // thin-K mode (<= 32 rows): ONE producer warp fills a whole stage, the warps take stages round-robin
+        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], (thin_k ? 1 : WG_WARPS) + 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -317,6 +331,46 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
     if (warp < WG_WARPS) {
         // ===== gather producers: lane = pixel of the 32-pixel block; warp w owns channels c = w, w+8, ... =====
         const size_t plane = (size_t)p.H * p.W;
+        if (thin_k) {
+            // tiny reductions (e.g. 1 input channel x 3x3 = 9 rows + the ones row): the im2col block of a stage is
+            // only (K+1) x 32 floats, the kernel is a pure dY stream through TMA — keep every warp busy on its own stage
+            // stage i -> producer warp i % 8: since ST % 8 == 0 a ring slot is always refilled by the same warp,
+            // which therefore sees its fills in order (the parity wait can never alias an older phase)
+            for (int i = warp; i < nkb; i += WG_WARPS) {
+                const int s = i % ST;
+                if (i >= ST) mbar_wait(&empty[s], ((i / ST) - 1) & 1);
+#pragma unroll 1
+                for (int q = 0; q < SUB; ++q) {
+                    const long kb = kb0 + (long)i * SUB + q;
+                    if (kb >= kb1) break;              // tail: dY is zero filled by TMA, stale (finite) rows contribute 0
+                    const int b = (int)(kb / p.pb_per_img);
+                    const int pix = (int)(kb % p.pb_per_img) * 32 + lane;
+                    const bool pv = pix < npx;
+                    const int oy = pv ? pix / p.OW : 0, ox = pv ? pix % p.OW : 0;
+                    const int y0 = oy * p.sy - p.pt, x0 = ox * p.sx - p.pl;
+                    const float* xb = p.x + (size_t)b * p.C * plane;
+                    const uint32_t a_s = smem_u32(sA + s * A_BYTES + q * A_SUB);
+                    for (int r0 = 0; r0 <= p.K; r0 += 8) {          // batches of 8 rows: loads first, then stores
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int r = r0 + u;
+                            v[u] = (r == p.K) ? 1.0f : 0.f;
+                            if (r < p.K) {
+                                const int iy = y0 + s_rowy[r], ix = x0 + s_rowx[r];
+                                if (pv && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v[u] = __ldg(xb + ((size_t)s_rowc[r] * p.H + iy) * p.W + ix);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (r0 + u <= p.K) sts32(a_s + sw128_off(r0 + u, lane), v[u]);
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+            }
+        } else
         for (int i = 0; i < nkb; ++i) {
             const int s = i % ST;
             const long kb = kb0 + i;
@@ -423,7 +477,13 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
             const long kb = kb0 + i;
             if (i >= ST) mbar_wait(&empty[s], ((i / ST) - 1) & 1);
             mbar_arrive_expect_tx(&full[s], B_BYTES);
-            tma_load_3d(sB + s * B_BYTES, &tmD, (int)(kb % p.pb_per_img) * 32, n0, (int)(kb / p.pb_per_img), &full[s]);
+#pragma unroll
+            for (int q = 0; q < SUB; ++q) {
+                const long kq = kb0 + (long)i * SUB + q;
+                // past this CTA's range the box is aimed outside the tensor (image index B): TMA zero-fills it
+                const int bi = kq < kb1 ? (int)(kq / p.pb_per_img) : p.B;
+                tma_load_3d(sB + s * B_BYTES + q * B_SUB, &tmD, (int)(kq % p.pb_per_img) * 32, n0, bi, &full[s]);
+            }
         }
     } else if (warp == WG_WARPS + 1 && lane == 0) {
         const uint32_t idesc = make_idesc_tf32(CBM, BN, 0, 0);
@@ -433,11 +493,13 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
             tc_fence_after();
             const uint32_t a = smem_u32(sA + s * A_BYTES), bq = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
+            for (int q = 0; q < SUB; ++q)
 #pragma unroll
-                for (int j = 0; j < CBK / 8; ++j)
-                    mma_tf32(tmem_base + mt * BN, make_smem_desc(a + mt * (CBM * CBK * 4) + j * 32, 16, 1024),
-                             make_smem_desc(bq + j * 32, 16, 1024), idesc, (i > 0 || j > 0) ? 1u : 0u);
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int j = 0; j < CBK / 8; ++j)
+                        mma_tf32(tmem_base + mt * BN, make_smem_desc(a + q * A_SUB + mt * (CBM * CBK * 4) + j * 32, 16, 1024),
+                                 make_smem_desc(bq + q * B_SUB + j * 32, 16, 1024), idesc, (i > 0 || q > 0 || j > 0) ? 1u : 0u);
             mma_commit(&empty[s]);
         }
         mma_commit(acc_full);
@@ -532,17 +594,19 @@ int tc_conv_dgrad(const float* dy, const float* w, float* dx, const dnb_win_t* g
     return run_gather("tc_conv2d_bwd_data", wp, n_pad, p, st);
 }
 
-template <int MT, int BN>
+template <int MT, int BN, bool THINK>
 static int launch_wgrad(const CUtensorMap& td, WgradParams p, int fb, cudaStream_t st) {
-    constexpr int ST = (MT == 1) ? 4 : 3;
-    const size_t smem = ST * (MT * CBM * CBK * 4 + BN * CBK * 4) + 128 + 1024;
-    cudaFuncSetAttribute(tc_conv_wgrad_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    constexpr int SUB = THINK ? 2 : 1;
+    constexpr int ST = THINK ? 8 : ((MT == 1) ? 4 : 3);
+    // THINK: the MMA of the last stage reads 16 KB from a 4 KB A block -> keep 16 KB of slack behind the ring
+    const size_t smem = ST * SUB * ((THINK ? 32 * CBK * 4 : MT * CBM * CBK * 4) + BN * CBK * 4) + (THINK ? 16384 : 0) + 512 + 1024;
+    cudaFuncSetAttribute(tc_conv_wgrad_kernel<MT, BN, THINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const long total_kb = (long)p.B * p.pb_per_img;
     long ctas = std::min<long>(total_kb, std::max(1, kNumSMs / fb));
     p.kb_per_cta = (total_kb + ctas - 1) / ctas;
     ctas = (total_kb + p.kb_per_cta - 1) / p.kb_per_cta;
     dim3 grid((unsigned)ctas, fb);
-    tc_conv_wgrad_kernel<MT, BN><<<grid, WGRAD_THREADS, smem, st>>>(td, p);
+    tc_conv_wgrad_kernel<MT, BN, THINK><<<grid, WGRAD_THREADS, smem, st>>>(td, p);
     DNB_LAUNCH_CHECK("tc_conv2d_bwd_weight");
     return DNB_OK;
 }
@@ -562,7 +626,11 @@ int tc_conv_wgrad(const float* x, const float* dy, float* gw, float* gb, const d
     if (!make_tmap_f32(&td, dy, 3, dims, str, box)) return set_err(DNB_ERR_CUDA, "conv2d_bwd_weight(tf32): cuTensorMapEncodeTiled failed");
     WgradParams p{x, gw, gb, g->B, g->C, g->H, g->W, g->F, g->OH, g->OW, g->kh, g->kw, g->sy, g->sx, g->pt, g->pl,
                   K, (npx + 31) / 32, 0, inv_m};
-#define DNB_W(MT_, BN_) launch_wgrad<MT_, BN_>(td, p, fb, st)
+#define DNB_W(MT_, BN_) launch_wgrad<MT_, BN_, false>(td, p, fb, st)
+    if (mt == 1 && K + 1 <= 32) {
+        switch (bn) { case 16: return launch_wgrad<1, 16, true>(td, p, fb, st); case 32: return launch_wgrad<1, 32, true>(td, p, fb, st);
+                      case 64: return launch_wgrad<1, 64, true>(td, p, fb, st); default: return launch_wgrad<1, 128, true>(td, p, fb, st); }
+    }
     if (mt == 1) { switch (bn) { case 16: return DNB_W(1, 16); case 32: return DNB_W(1, 32); case 64: return DNB_W(1, 64); default: return DNB_W(1, 128); } }
     if (mt == 2) { switch (bn) { case 16: return DNB_W(2, 16); case 32: return DNB_W(2, 32); case 64: return DNB_W(2, 64); default: return DNB_W(2, 128); } }
     switch (bn) { case 16: return DNB_W(3, 16); case 32: return DNB_W(3, 32); case 64: return DNB_W(3, 64); default: return DNB_W(3, 128); }
