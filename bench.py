@@ -273,7 +273,8 @@ def main():
     # pinned host minibatches for `e2e`
     px = [torch.from_numpy(x).pin_memory() for x in xs]
     py = [torch.from_numpy(y).pin_memory() for y in ys]
-    loss_host = torch.empty((2,), dtype=torch.float32).pin_memory()
+    loss_host = [torch.empty((2,), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
 
     def barrier():
         if world > 1:
@@ -303,10 +304,15 @@ def main():
         last["o"] = net.train_step([dx[i % n_mb]], [dy[i % n_mb]])
 
     def step_e2e(i):
+        # public API with PINNED HOST minibatches: H2D of x and y, the step, D2H of [loss, flags] — every step.
+        # The host reads each loss one step late (the read of step i-1 overlaps step i), so the copy of the
+        # next minibatch (dedicated copy stream, double-buffered) overlaps the kernels of the current one.
         outs = net.train_step([px[i % n_mb]], [py[i % n_mb]])
-        loss_host.copy_(outs[0], non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the user reads the loss every step
-        last["loss"] = float(loss_host[0])
+        loss_host[i & 1].copy_(outs[0], non_blocking=True)
+        loss_evt[i & 1].record()
+        if i > 0:
+            loss_evt[(i - 1) & 1].synchronize()
+            last["loss"] = float(loss_host[(i - 1) & 1][0])
 
     sampler = ClockSampler(dev)
     sampler.start()                      # nvidia-smi needs ~100 ms to start: begin before the warm-up

@@ -83,6 +83,7 @@ class Net:
         self._graphs = {}
         self._pending_flags = []
         self._stage = {}
+        self._copy_stream = None
 
     # ------------------------------------------------------------------ build
     def build(self, l_in, l_out, optimizer, losses, metrics, debug=False, smart_derivatives=False):
@@ -210,7 +211,11 @@ class Net:
         return any(isinstance(l, Embedding) and l.parents and l.parents[0] is self.l_in[j] for l in self.fts_layers)
 
     def _stage_in(self, key, a, is_int=False):
-        """ndarray / torch CPU tensor -> persistent device buffer (fp32, or int32 for token ids)."""
+        """ndarray / torch CPU tensor -> persistent device buffer (fp32, or int32 for token ids).
+
+        Two buffers per input alternate between steps and PINNED sources are copied on a dedicated copy
+        stream, so the H2D transfer of step k overlaps the kernels of step k-1 (the compute stream only
+        waits for the copy's event; a buffer is reused once the step that read it has drained)."""
         if isinstance(a, DArray):
             return a
         t = torch()
@@ -227,11 +232,30 @@ class Net:
         want_t = t.int32 if is_int else t.float32
         if src.dtype != want_t:
             src = src.to(want_t)
-        buf = self._stage.get(key)
-        if buf is None or tuple(buf.shape) != tuple(src.shape):
-            buf = dev_empty(tuple(src.shape), int_dtype=is_int)
-            self._stage[key] = buf
-        buf.copy_(src, non_blocking=True)
+        st = self._stage.get(key)
+        if st is None or tuple(st["bufs"][0].shape) != tuple(src.shape):
+            st = dict(bufs=[dev_empty(tuple(src.shape), int_dtype=is_int) for _ in range(2)],
+                      free=[t.cuda.Event(), t.cuda.Event()], ready=[t.cuda.Event(), t.cuda.Event()], k=0)
+            self._stage[key] = st
+        cur = t.cuda.current_stream()
+        k = st["k"]
+        st["k"] = k + 1
+        slot, prev = k & 1, (k - 1) & 1
+        if k > 0:
+            st["free"][prev].record(cur)          # everything queued so far (the previous step) has read slot `prev`
+        buf = st["bufs"][slot]
+        if src.is_pinned():
+            if self._copy_stream is None:
+                self._copy_stream = t.cuda.Stream()
+            cs = self._copy_stream
+            if k > 1:
+                cs.wait_event(st["free"][slot])   # recorded one call ago: the step that last read this slot is covered
+            with t.cuda.stream(cs):
+                buf.copy_(src, non_blocking=True)
+                st["ready"][slot].record(cs)
+            cur.wait_event(st["ready"][slot])
+        else:
+            buf.copy_(src, non_blocking=True)       # pageable source: stream-ordered staging copy
         return DArray.device(buf, is_int=is_int)
 
     def forward(self):
