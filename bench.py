@@ -284,14 +284,14 @@ def main():
     def timed(step_fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = lib.dnb_launch_count()
+        n0 = lib.dnb_launch_count() + net.graph_launches
         e0.record()
         for i in range(steps):
             step_fn(i)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        launches = lib.dnb_launch_count() - n0
+        launches = lib.dnb_launch_count() + net.graph_launches - n0
         if world > 1:
             t = torch.tensor([ms], device="cuda")
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -318,7 +318,10 @@ def main():
     sampler.start()                      # nvidia-smi needs ~100 ms to start: begin before the warm-up
     t_w = time.perf_counter()
     i_w = 0
-    while i_w < max(3, args.warmup) or (time.perf_counter() - t_w) < 0.5:     # >= 0.5 s under load before timing
+    # warm-up: at least W steps, at least 0.5 s under load, and enough calls for every (minibatch buffer) step
+    # graph to be captured (2 eager calls + 1 capture per buffer) so no capture lands in the timed region
+    min_warm = max(3, args.warmup, 3 * n_mb + 4)
+    while i_w < min_warm or (time.perf_counter() - t_w) < 0.5:
         step_resident(i_w)
         i_w += 1
         if i_w % 8 == 0:
@@ -331,7 +334,7 @@ def main():
         loss = float(lt.item()) / world
     if not np.isfinite(loss):
         raise RuntimeError(f"non-finite loss {loss} during the benchmark")
-    for i in range(2):
+    for i in range(10):                  # both staging slots: 2 eager calls + capture each
         step_e2e(i)
     ms_e2e, _ = timed(step_e2e, args.steps)
     clocks = sampler.stop()
@@ -403,7 +406,8 @@ def main():
     if rank == 0:
         line = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype=args.math, data="synthetic", config=config, clocks=clocks,
+                    dtype=args.math, data="synthetic", config=dict(config, warmup_steps_run=i_w, cuda_graph=bool(net.use_graph and world == 1)),
+                    clocks=clocks,
                     e2e=dict(value=e2e_value, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, top_kernels=top5, final_loss=loss)

@@ -18,6 +18,9 @@ from ..runtime import config
 
 
 class Layer:
+    # bumped whenever any layer (re)allocates a device buffer: captured CUDA graphs hold raw addresses and are
+    # only replayed while this generation is unchanged
+    buffer_generation = 0
 
     def __init__(self, name):
         self.name = name
@@ -115,6 +118,7 @@ class Layer:
         if cur is None or cur.shape != shape:
             cur = DArray.device(dev_empty(shape, int_dtype=is_int), is_int=is_int)
             self._bufs[key] = cur
+            Layer.buffer_generation += 1
         return cur.written()
 
     def _raw(self, key, nbytes):
@@ -126,6 +130,7 @@ class Layer:
         if cur is None or cur.size < n:
             cur = DArray.device(dev_empty((n,)))
             self._bufs[key] = cur
+            Layer.buffer_generation += 1
         return cur.ptr()
 
     @staticmethod

@@ -18,19 +18,31 @@ class Dropout(Layer):
         self.rate = rate
         self.gate = None
 
-    def draw_gate(self, shape):
-        return (np.random.random(shape) > self.rate).astype(float)
+    def prepare(self, shape):
+        """Draw this step's mask from the global NumPy stream (the reference's one call per training forward,
+        regularization.py:19) and upload it into the layer's STATIC gate buffer.  Net calls this before it
+        replays a captured step graph; an eager forward calls it itself."""
+        gate = self._bufs.get('gate')
+        if gate is None or gate.shape != tuple(shape):
+            from ..darray import dev_empty
+            gate = DArray.device(dev_empty(tuple(shape)))
+            self._bufs['gate'] = gate
+            Layer.buffer_generation += 1
+        import torch
+        host = (np.random.random(shape) > self.rate).astype(np.float32)
+        gate.dev().copy_(torch.from_numpy(host))
+        gate.written()
+        self.gate = gate
+        self._prepared = True
 
     def forward(self):
         x = self._in()
         out = self._buf('out', x.shape)
         if self.training:
-            gate = self._bufs.get('gate_in')            # a pre-drawn gate (data-parallel shard / graph replay)
-            if gate is None:
-                gate = DArray(host=self.draw_gate(x.shape))
-            self._bufs.pop('gate_in', None)
-            self.gate = gate
-            self._call("dnb_mul", x.ptr(), gate.ptr(), out.ptr(), x.size)
+            if not getattr(self, "_prepared", False):
+                self.prepare(x.shape)
+            self._prepared = False
+            self._call("dnb_mul", x.ptr(), self.gate.ptr(), out.ptr(), x.size)
         else:
             self._call("dnb_scale", x.ptr(), out.ptr(), x.size, float(1 - self.rate))
         self.output = out

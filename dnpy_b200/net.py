@@ -84,6 +84,7 @@ class Net:
         self._pending_flags = []
         self._stage = {}
         self._copy_stream = None
+        self.graph_launches = 0          # kernels executed through graph replays (the library counts eager ones)
 
     # ------------------------------------------------------------------ build
     def build(self, l_in, l_out, optimizer, losses, metrics, debug=False, smart_derivatives=False):
@@ -354,20 +355,81 @@ class Net:
         return t.cuda.is_available()
 
     def train_step(self, x_mb, y_mb):
-        """One iteration of net.py:176-195 without host synchronisation.  Returns the per-loss
-        device tensors ``[loss, flags]``; nothing is read back here."""
-        self.feed_input(x_mb)
+        """One iteration of net.py:176-195 without host synchronisation.  Returns the per-loss device
+        tensors ``[loss, flags]``; nothing is read back here.
+
+        After two eager calls with the same shapes the whole step (forward -> loss -> reset -> backward ->
+        optimizer, ~30-60 kernels) is captured in a CUDA graph per input staging slot and replayed; host-side
+        work per step is then the input copies, the Dropout draws and one graph launch."""
+        xs = [self._stage_in(("x", j), x_mb[j], self._input_is_int(j)) for j in range(len(self.l_in))]
+        ys = [self._stage_in(("y", i), y_mb[i]) for i in range(len(self.losses))]
+        if not (self.use_graph and config.world == 1 and not self.debug):
+            return self._step_body(xs, ys)
+        key = (tuple(x.ptr() for x in xs), tuple(y.ptr() for y in ys), tuple(x.shape for x in xs), self.mode,
+               config.math, config.maxpool_route, self._layer_generation())
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = dict(calls=0, graph=None, outs=None)
+        if ent["graph"] is None:
+            ent["calls"] += 1
+            if ent["calls"] <= 2 or any(l.frozen for l in self.fts_layers):
+                return self._step_body(xs, ys)              # warm-up: every buffer gets allocated here
+            self._prepare_host_draws(xs)
+            t = torch()
+            t.cuda.synchronize()
+            g = t.cuda.CUDAGraph()
+            n0 = _lib.load().dnb_launch_count()
+            with t.cuda.graph(g):
+                outs = self._step_body(xs, ys)
+            if self._layer_generation() != key[-1]:         # something allocated during capture: do not trust it
+                del self._graphs[key]
+                return self._step_body(xs, ys)
+            ent["graph"], ent["outs"] = g, outs
+            ent["launches"] = int(_lib.load().dnb_launch_count() - n0)
+            # capturing records the step without running it: fall through to the replay
+        else:
+            self._prepare_host_draws(xs)
+        ent["graph"].replay()
+        self.graph_launches += ent["launches"]
+        self._mark_written()
+        return ent["outs"]
+
+    def _step_body(self, xs, ys):
+        for j in range(len(self.l_in)):
+            self.l_in[j].output = xs[j]
         self.forward()
         outs, deltas = [], []
         for i, lo in enumerate(self.losses):
-            y_i = self._stage_in(("y", i), y_mb[i])
-            outs.append(lo.result_tensor(self.l_out[i].output, y_i))
-            deltas.append(lo.compute_delta(self.l_out[i].output, y_i))
+            outs.append(lo.result_tensor(self.l_out[i].output, ys[i]))
+            deltas.append(lo.compute_delta(self.l_out[i].output, ys[i]))
         self.reset_grads()
         self.do_delta(deltas)
         self.backward()
         self.apply_grads()
         return outs
+
+    @staticmethod
+    def _layer_generation():
+        from .layers.base import Layer
+        return Layer.buffer_generation
+
+    def _prepare_host_draws(self, xs):
+        """Host-RNG layers (Dropout) draw before a graph capture/replay, in forward order, so the global
+        NumPy stream is consumed exactly like an eager step."""
+        for l in self.fts_layers:
+            if hasattr(l, "prepare") and l.training:
+                shape = l.parents[0].output.shape if l.parents[0].output is not None else None
+                if shape is not None:
+                    l.prepare(shape)
+
+    def _mark_written(self):
+        """After a replay the host copies of everything the step wrote are stale."""
+        for l in self.fts_layers:
+            for d in (l.output, l.delta):
+                if isinstance(d, DArray):
+                    d.written()
+            for d in list(l.params.values()) + list(l.grads.values()):
+                d.written()
 
     # ------------------------------------------------------------------ fit / evaluate
     def _format_eval(self, losses=None, metrics=None):
