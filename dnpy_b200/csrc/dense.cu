@@ -6,6 +6,7 @@
 // in tc_gemm.cu (tcgen05 + TMEM + TMA) and is selected with math == DNB_MATH_TF32.
 #include "common.cuh"
 #include "tc_gemm.cuh"
+#include <algorithm>
 
 namespace dnb {
 
@@ -123,6 +124,113 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Skinny heads (out <= 16, e.g. the 10-class classifier on 1600 or 16384 features): bandwidth-bound
+// GEMV-like shapes where a 64x64 tile wastes 84% of its columns.  Each kernel streams X exactly once.
+// ------------------------------------------------------------------------------------------
+constexpr int SKN = 16;      // padded output width
+
+// Y[b, o] = sum_i X[b,i] W[i,o] + bias[o]: a warp owns RPW rows, lanes stride over i; the (small, L1-resident)
+// W rows are read once per iteration and reused for all RPW rows of the warp.
+constexpr int RPW = 4;
+__global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ y,
+                                                         int B, int in, int out) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int row0 = (blockIdx.x * 8 + wid) * RPW;
+    if (row0 >= B) return;
+    float acc[RPW][SKN];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+        for (int o = 0; o < SKN; ++o) acc[r][o] = 0.f;
+    for (int i = lane; i < in; i += 32) {
+        float wv[SKN];
+#pragma unroll
+        for (int o = 0; o < SKN; ++o) wv[o] = o < out ? __ldg(w + (size_t)i * out + o) : 0.f;
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const float xv = (row0 + r < B) ? __ldg(x + (size_t)(row0 + r) * in + i) : 0.f;
+#pragma unroll
+            for (int o = 0; o < SKN; ++o) acc[r][o] = fmaf(xv, wv[o], acc[r][o]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+#pragma unroll
+        for (int o = 0; o < SKN; ++o) acc[r][o] = warp_sum(acc[r][o]);
+        if (lane < out && row0 + r < B) {
+            float v = 0.f;
+#pragma unroll
+            for (int o = 0; o < SKN; ++o) if (o == lane) v = acc[r][o];
+            y[(size_t)(row0 + r) * out + lane] = v + (bias ? bias[lane] : 0.f);
+        }
+    }
+}
+
+// gW[i, o] += inv_m * (sum_b X[b,i] dY[b,o] + reg'(W[i,o])): a CTA owns a slice of the batch and 256*IPT features;
+// lanes run along i (coalesced X rows), dY rows are broadcast; partial tiles are added atomically.
+template <int IPT>
+__global__ void __launch_bounds__(256) skinny_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                        const float* __restrict__ w, float* __restrict__ gw,
+                                                        const float* __restrict__ bvec, float* __restrict__ gb,
+                                                        int B, int in, int out, int rows_per_cta, float inv_m, float l1, float l2,
+                                                        float bl1, float bl2) {
+    __shared__ float sd[64][SKN];
+    float accb = 0.f;                 // blockIdx.x == 0, thread o < out: column sum of dY -> gb
+    const int i0 = blockIdx.x * 256 * IPT;
+    const int b0 = blockIdx.y * rows_per_cta, b1 = min(B, b0 + rows_per_cta);
+    float acc[IPT][SKN];
+#pragma unroll
+    for (int t = 0; t < IPT; ++t)
+#pragma unroll
+        for (int o = 0; o < SKN; ++o) acc[t][o] = 0.f;
+    for (int bb = b0; bb < b1; bb += 64) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 64 * SKN; e += 256) {
+            int r = e / SKN, o = e % SKN;
+            sd[r][o] = (bb + r < b1 && o < out) ? __ldg(dy + (size_t)(bb + r) * out + o) : 0.f;
+        }
+        __syncthreads();
+        const int nr = min(64, b1 - bb);
+        if (blockIdx.x == 0 && threadIdx.x < SKN)
+            for (int r = 0; r < nr; ++r) accb += sd[r][threadIdx.x];
+        for (int r = 0; r < nr; ++r) {
+            const float* xr = x + (size_t)(bb + r) * in + i0 + threadIdx.x;
+            float xv[IPT];
+#pragma unroll
+            for (int t = 0; t < IPT; ++t) xv[t] = (i0 + threadIdx.x + t * 256 < in) ? __ldg(xr + t * 256) : 0.f;
+#pragma unroll
+            for (int q = 0; q < SKN / 4; ++q) {
+                const float4 d4 = *reinterpret_cast<const float4*>(&sd[r][4 * q]);
+#pragma unroll
+                for (int t = 0; t < IPT; ++t) {
+                    acc[t][4 * q] = fmaf(xv[t], d4.x, acc[t][4 * q]); acc[t][4 * q + 1] = fmaf(xv[t], d4.y, acc[t][4 * q + 1]);
+                    acc[t][4 * q + 2] = fmaf(xv[t], d4.z, acc[t][4 * q + 2]); acc[t][4 * q + 3] = fmaf(xv[t], d4.w, acc[t][4 * q + 3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < IPT; ++t) {
+        const int i = i0 + threadIdx.x + t * 256;
+        if (i < in) {
+#pragma unroll
+            for (int o = 0; o < SKN; ++o)
+                if (o < out) {
+                    float g = acc[t][o] * inv_m;
+                    if (blockIdx.y == 0) g += reg_term(w[(size_t)i * out + o], l1, l2) * inv_m;
+                    atomicAdd(gw + (size_t)i * out + o, g);
+                }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < out) {
+        float g = accb * inv_m;
+        if (blockIdx.y == 0) g += reg_term(bvec[threadIdx.x], bl1, bl2) * inv_m;
+        atomicAdd(gb + threadIdx.x, g);
+    }
+}
+
 }  // namespace dnb
 
 using namespace dnb;
@@ -134,6 +242,11 @@ int dnb_dense_fwd(const float* x, const float* w, const float* b, float* y,
     DNB_CHECK_ARG(B >= 0 && in > 0 && out > 0, "dense_fwd: bad shape B=%d in=%d out=%d", B, in, out);
     if (B == 0) return DNB_OK;
     DNB_CHECK_ARG(x && w && y, "dense_fwd: null pointer");
+    if (out <= SKN && B >= 64) {
+        skinny_fwd_kernel<<<(B + 8 * RPW - 1) / (8 * RPW), 256, 0, S(stream)>>>(x, w, b, y, B, in, out);
+        DNB_LAUNCH_CHECK("dense_fwd");
+        return DNB_OK;
+    }
     if (math == DNB_MATH_TF32 && tc_gemm_supported(B, out, in, /*a_kmajor*/ true, /*b_kmajor*/ false)) {
         // Y[B,out] = X[B,in] . W[in,out]: A is K-major, B is N-major (row-major [K,N])
         return tc_gemm(x, w, y, B, out, in, TC_A_KMAJOR | TC_B_NMAJOR, b, nullptr, 0.f, 0.f, 0.f, S(stream));
@@ -150,6 +263,21 @@ int dnb_dense_bwd(const float* x, const float* w, const float* b, const float* d
     DNB_CHECK_ARG(x && w && b && dy && gw && gb, "dense_bwd: null pointer");
     cudaStream_t st = S(stream);
     int rc;
+    if (out <= SKN && B >= 64) {
+        if (dx) {
+            GemmArgs a{dy, out, 1, w, 1, out, dx, B, in, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0};
+            rc = launch_sgemm<EPI_STORE>("dense_bwd_dx", a, st);
+            if (rc) return rc;
+        }
+        const int itiles = (in + 511) / 512;
+        int bsplit = std::max(1, std::min((B + 255) / 256, (2 * kNumSMs + itiles - 1) / itiles));
+        int rows = ((B + bsplit - 1) / bsplit + 63) / 64 * 64;
+        dim3 grid(itiles, (B + rows - 1) / rows);
+        skinny_dw_kernel<2><<<grid, 256, 0, st>>>(x, dy, w, gw, b, gb, B, in, out, rows, inv_m, reg_w.l1 * reg_scale,
+                                                   reg_w.l2 * reg_scale, reg_b.l1 * reg_scale, reg_b.l2 * reg_scale);
+        DNB_LAUNCH_CHECK("dense_bwd_dw");
+        return DNB_OK;
+    }
     if (dx) {
         // dX[B,in] = dY[B,out] . W^T : B(k=o, n=i) = W[i*out + o]  -> K-major B
         if (math == DNB_MATH_TF32 && tc_gemm_supported(B, in, out, true, true)) {
