@@ -101,6 +101,43 @@ __global__ void __launch_bounds__(256) maxpool_bwd_per_sample_kernel(const float
     }
 }
 
+// PER_SAMPLE fast path (no padding, stride 2, K in {2,3}): a thread owns 4 adjacent input pixels of one row and
+// visits the <= 2 x 3 windows that can reach them, in the reference's (oy, ox) accumulation order.
+template <int K>
+__global__ void __launch_bounds__(256) maxpool_bwd_ps_strip_kernel(const float* __restrict__ dy, const int32_t* __restrict__ idx,
+                                                                   float* __restrict__ dx, int planes, int H, int W, int OH, int OW) {
+    const int spr = (W + 3) >> 2;
+    const long total = (long)planes * H * spr;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const int sx = (int)(t % spr);
+        const long r = t / spr;
+        const int iy = (int)(r % H);
+        const long pl = r / H;
+        const int ix0 = sx * 4;
+        const int oy_lo = iy >= K - 1 ? (iy - K + 2) >> 1 : 0, oy_hi = min(OH - 1, iy >> 1);
+        const int ox_lo = ix0 >= K - 1 ? (ix0 - K + 2) >> 1 : 0, ox_hi = min(OW - 1, (ix0 + 3) >> 1);
+        const float* dp = dy + pl * (long)OH * OW;
+        const int32_t* ip = idx + pl * (long)OH * OW;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+            const int wi = iy - 2 * oy;                    // window row that lands on iy
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                const int off = __ldg(ip + oy * OW + ox);
+                const int oi = off / K, oj = off - oi * K;
+                const int col = 2 * ox + oj - ix0;
+                if (oi == wi && col >= 0 && col < 4) {
+                    const float d = __ldg(dp + oy * OW + ox);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (q == col) acc[q] += d;
+                }
+            }
+        }
+        float* xp = dx + (pl * H + iy) * (long)W + ix0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (ix0 + q < W) xp[q] = acc[q];
+    }
+}
+
 // LITERAL step 1: last[c,oy,ox,p] = max b with idx[b,c,oy,ox] == p  (int32, pre-filled with -1)
 __global__ void __launch_bounds__(256) maxpool_last_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ last,
                                                            dnb_win_t g, int bchunk) {
@@ -228,6 +265,14 @@ int dnb_maxpool2d_bwd(const float* dy, const int32_t* idx, float* dx, const dnb_
     DNB_CHECK_ARG(dy && idx && dx, "maxpool2d_bwd: null pointer");
     cudaStream_t st = S(stream);
     if (route == DNB_ROUTE_PER_SAMPLE || g->B == 1) {
+        const bool nopad = !(g->pt | g->pb | g->pl | g->pr);
+        if (nopad && g->kh == g->kw && g->sy == 2 && g->sx == 2 && (g->kh == 2 || g->kh == 3)) {
+            const long strips = (long)g->B * g->C * g->H * ((g->W + 3) / 4);
+            if (g->kh == 3) maxpool_bwd_ps_strip_kernel<3><<<ew_grid(strips, 256), 256, 0, st>>>(dy, idx, dx, g->B * g->C, g->H, g->W, g->OH, g->OW);
+            else maxpool_bwd_ps_strip_kernel<2><<<ew_grid(strips, 256), 256, 0, st>>>(dy, idx, dx, g->B * g->C, g->H, g->W, g->OH, g->OW);
+            DNB_LAUNCH_CHECK("maxpool2d_bwd");
+            return DNB_OK;
+        }
         maxpool_bwd_per_sample_kernel<<<ew_grid(n, 256), 256, 0, st>>>(dy, idx, dx, *g);
         DNB_LAUNCH_CHECK("maxpool2d_bwd");
         return DNB_OK;
