@@ -17,6 +17,7 @@
 #include "tc_common.cuh"
 #include "tc_conv.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace dnb {
 namespace tc {
@@ -100,7 +101,7 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
     }
     if (tid == 0) {
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < CSTAGES; ++s) { mbar_init(&full[s], GATHER_WARPS * 32 + 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < CSTAGES; ++s) { mbar_init(&full[s], GATHER_WARPS + 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -187,7 +188,8 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
             }
             }
             fence_proxy_async_smem();           // generic-proxy stores -> visible to tcgen05.mma
-            mbar_arrive(&full[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);   // one arrival per producer warp
         }
         // ===== epilogue: warp w reads TMEM lane quadrant (w & 3); warps 0-3 take the lower half of the
         // columns, warps 4-7 the upper half (pixel rows 0..127 map to lanes, so thread -> pixel (warp&3)*32+lane)
@@ -578,6 +580,8 @@ int tc_conv_fwd(const float* x, const float* w, const float* b, float* y, const 
     float* wp = static_cast<float*>(ws);
     prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, cp, 0);
     DNB_LAUNCH_CHECK("conv2d_prep_weights");
+    if (!getenv("DNB_NO_SV") && tc_conv_sv_supported(g, false))
+        return tc_conv_sv_run("tc_conv2d_fwd_sv", x, wp, n_pad, Kp, b, (float)(g->C * g->kh * g->kw), y, g, false, st);
     ConvGemmParams p{x, y, b, g->B, g->C, g->H, g->W, g->F, g->OH, g->OW, g->kh, g->kw, cp, Kp,
                      g->sy, g->sx, 1, 1, g->pt, g->pl, (float)(g->C * g->kh * g->kw)};
     return run_gather("tc_conv2d_fwd", wp, n_pad, p, st);
@@ -589,6 +593,8 @@ int tc_conv_dgrad(const float* dy, const float* w, float* dx, const dnb_win_t* g
     float* wp = static_cast<float*>(ws) + ws_fwd_floats(g);
     prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, cp, 1);
     DNB_LAUNCH_CHECK("conv2d_prep_weights_t");
+    if (!getenv("DNB_NO_SV") && tc_conv_sv_supported(g, true))
+        return tc_conv_sv_run("tc_conv2d_bwd_data_sv", dy, wp, n_pad, Kp, nullptr, 0.f, dx, g, true, st);
     ConvGemmParams p{dy, dx, nullptr, g->B, g->F, g->OH, g->OW, g->C, g->H, g->W, g->kh, g->kw, cp, Kp,
                      1, 1, g->sy, g->sx, g->kh - 1 - g->pt, g->kw - 1 - g->pl, 0.f};
     return run_gather("tc_conv2d_bwd_data", wp, n_pad, p, st);

@@ -14,4 +14,9 @@ int tc_conv_dgrad(const float* dy, const float* w, float* dx, const dnb_win_t* g
 int tc_conv_wgrad(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, void* ws,
                   cudaStream_t st);
 
+// tc_conv_sv.cu: shifted-view kernel (stride 1, 32-channel multiples) used by tc_conv_fwd / tc_conv_dgrad
+bool tc_conv_sv_supported(const dnb_win_t* g, bool dgrad);
+int tc_conv_sv_run(const char* name, const float* src, const float* wprep, int n_pad, int Kp, const float* bias, float bias_k,
+                   float* dst, const dnb_win_t* g, bool dgrad, cudaStream_t st);
+
 }  // namespace dnb
