@@ -236,21 +236,25 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmB, ConvGemmParams p)
             mbar_arrive_expect_tx(&full[s], B_BYTES);
             tma_load_2d(sB + s * B_BYTES, &tmB, kb * CBK, n0, &full[s]);
         }
-    } else if (warp == GATHER_WARPS + 1 && lane == 0) {
-        // ===== MMA issuer =====
+    } else if (warp == GATHER_WARPS + 1) {
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues (43-49 cycles per MMA vs 75 single-threaded) =====
         const uint32_t idesc = make_idesc_tf32(CBM, BN, 0, 0);
+        const uint64_t a0 = make_smem_desc(smem_u32(sA), 16, 1024), b0 = make_smem_desc(smem_u32(sB), 16, 1024);
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % CSTAGES;
             mbar_wait(&full[s], (kb / CSTAGES) & 1);
             tc_fence_after();
-            const uint32_t a = smem_u32(sA + s * A_BYTES), bq = smem_u32(sB + s * B_BYTES);
-#pragma unroll
-            for (int j = 0; j < CBK / 8; ++j)
-                mma_tf32(tmem_base, make_smem_desc(a + j * 32, 16, 1024), make_smem_desc(bq + j * 32, 16, 1024), idesc,
-                         (kb > 0 || j > 0) ? 1u : 0u);
-            mma_commit(&empty[s]);
+            const uint64_t a = a0 + (uint64_t)(s * (A_BYTES >> 4)), bq = b0 + (uint64_t)(s * (B_BYTES >> 4));
+            if (elect_one()) {
+                if (kb == 0) mma_tf32_init(tmem_base, a, bq, idesc); else mma_tf32_acc(tmem_base, a, bq, idesc);
+                mma_tf32_acc(tmem_base, a + 2, bq + 2, idesc);
+                mma_tf32_acc(tmem_base, a + 4, bq + 4, idesc);
+                mma_tf32_acc(tmem_base, a + 6, bq + 6, idesc);
+                mma_commit(&empty[s]);
+            }
+            __syncwarp();
         }
-        mma_commit(acc_full);
+        if (elect_one()) mma_commit(acc_full);
     }
     tc_fence_before();
     __syncthreads();
@@ -487,24 +491,32 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, WgradParams p) {
                 tma_load_3d(sB + s * B_BYTES + q * B_SUB, &tmD, (int)(kq % p.pb_per_img) * 32, n0, bi, &full[s]);
             }
         }
-    } else if (warp == WG_WARPS + 1 && lane == 0) {
+    } else if (warp == WG_WARPS + 1) {
+        // MMA issuer: warp-uniform loop, one elected lane issues
         const uint32_t idesc = make_idesc_tf32(CBM, BN, 0, 0);
+        const uint64_t a0 = make_smem_desc(smem_u32(sA), 16, 1024), b0 = make_smem_desc(smem_u32(sB), 16, 1024);
         for (int i = 0; i < nkb; ++i) {
             const int s = i % ST;
             mbar_wait(&full[s], (i / ST) & 1);
             tc_fence_after();
-            const uint32_t a = smem_u32(sA + s * A_BYTES), bq = smem_u32(sB + s * B_BYTES);
+            const uint64_t a = a0 + (uint64_t)(s * (A_BYTES >> 4)), bq = b0 + (uint64_t)(s * (B_BYTES >> 4));
+            if (elect_one()) {
 #pragma unroll
-            for (int q = 0; q < SUB; ++q)
+                for (int q = 0; q < SUB; ++q)
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
+                    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int j = 0; j < CBK / 8; ++j)
-                        mma_tf32(tmem_base + mt * BN, make_smem_desc(a + q * A_SUB + mt * (CBM * CBK * 4) + j * 32, 16, 1024),
-                                 make_smem_desc(bq + q * B_SUB + j * 32, 16, 1024), idesc, (i > 0 || q > 0 || j > 0) ? 1u : 0u);
-            mma_commit(&empty[s]);
+                        for (int j = 0; j < CBK / 8; ++j) {
+                            const uint64_t ad = a + (uint64_t)((q * A_SUB + mt * (CBM * CBK * 4)) >> 4) + 2 * j;
+                            const uint64_t bd = bq + (uint64_t)((q * B_SUB) >> 4) + 2 * j;
+                            if (i == 0 && q == 0 && j == 0) mma_tf32_init(tmem_base + mt * BN, ad, bd, idesc);
+                            else mma_tf32_acc(tmem_base + mt * BN, ad, bd, idesc);
+                        }
+                mma_commit(&empty[s]);
+            }
+            __syncwarp();
         }
-        mma_commit(acc_full);
+        if (elect_one()) mma_commit(acc_full);
     }
     tc_fence_before();
     __syncthreads();

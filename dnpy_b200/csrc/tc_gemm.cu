@@ -111,26 +111,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (!p.b_mn) tma_load_2d(b, &tmB, k, n0, &full[s]);                       // box {32 k, BN n}
             else for (int j = 0; j < BN / 32; ++j) tma_load_2d(b + j * 4096, &tmB, n0 + j * 32, k, &full[s]);
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
+    } else if (warp == 1) {
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
         const uint32_t idesc = make_idesc_tf32(BM, BN, p.a_mn, p.b_mn);
+        // K-major: step 32 bytes inside the swizzled 128-byte row; MN-major (32B-atom layout): next 8-row K group (1024 B)
+        const uint64_t a0 = p.a_mn ? make_smem_desc(smem_u32(sA), 4096, 512, LAYOUT_SW128_BASE32B) : make_smem_desc(smem_u32(sA), 16, 1024);
+        const uint64_t b0 = p.b_mn ? make_smem_desc(smem_u32(sB), 4096, 512, LAYOUT_SW128_BASE32B) : make_smem_desc(smem_u32(sB), 16, 1024);
+        const uint32_t a_step = p.a_mn ? (1024 >> 4) : (32 >> 4), b_step = p.b_mn ? (1024 >> 4) : (32 >> 4);
         for (int i = 0; i < nkb; ++i) {
             const int s = i % STAGES;
             mbar_wait(&full[s], (i / STAGES) & 1);
             tc_fence_after();
-            const uint32_t a = smem_u32(sA + s * A_BYTES), b = smem_u32(sB + s * B_BYTES);
-#pragma unroll
-            for (int j = 0; j < BK / 8; ++j) {
-                // K-major: step 32 bytes inside the swizzled 128-byte row; MN-major: next 8-row K group (1024 B)
-                const uint64_t ad = p.a_mn ? make_smem_desc(a + j * 1024, 4096, 512, LAYOUT_SW128_BASE32B)
-                                           : make_smem_desc(a + j * 32, 16, 1024);
-                const uint64_t bd = p.b_mn ? make_smem_desc(b + j * 1024, 4096, 512, LAYOUT_SW128_BASE32B)
-                                           : make_smem_desc(b + j * 32, 16, 1024);
-                mma_tf32(tmem_base, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+            const uint64_t a = a0 + (uint64_t)(s * (A_BYTES >> 4)), b = b0 + (uint64_t)(s * (B_BYTES >> 4));
+            if (elect_one()) {
+                if (i == 0) mma_tf32_init(tmem_base, a, b, idesc); else mma_tf32_acc(tmem_base, a, b, idesc);
+                mma_tf32_acc(tmem_base, a + a_step, b + b_step, idesc);
+                mma_tf32_acc(tmem_base, a + 2 * a_step, b + 2 * b_step, idesc);
+                mma_tf32_acc(tmem_base, a + 3 * a_step, b + 3 * b_step, idesc);
+                mma_commit(&empty[s]);          // slot reusable once these MMAs have read it
             }
-            mma_commit(&empty[s]);          // slot reusable once these MMAs have read it
+            __syncwarp();
         }
-        mma_commit(acc_full);               // accumulator tile complete
+        if (elect_one()) mma_commit(acc_full);  // accumulator tile complete
     } else if (warp >= 2) {
         // ===== epilogue: TMEM -> registers -> global =====
         const int q = warp & 3;             // TMEM lane quadrant this warp may access
