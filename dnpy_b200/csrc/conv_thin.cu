@@ -13,7 +13,9 @@
 //
 // Literal semantics as in conv.cu: bias enters as K*b (Q1), gW/gb are (1/B) * full sums.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace dnb {
 
@@ -276,6 +278,316 @@ __global__ void __launch_bounds__(256) thin_dgrad_kernel(ThinArgs a) {
             }
 }
 
+
+// =====================================================================================================
+// "Flat" variants for C <= 2 when every F-channel plane is a multiple of 4 floats (e.g. 26x26 = 676): the
+// F-channel tensor is then a dense array of 16-byte quads and is streamed with 128-bit accesses that never
+// care about the (8-byte aligned, 104-byte) image rows.  A thread owns one quad q of one image = 4 flat
+// output positions (which may straddle an image row) and keeps their C*9 taps in registers.
+//
+//   forward : taps from L1 (36 scalar loads per thread, reused for all F filters), one STG.128 per filter.
+//   dgrad   : T[tap][q] = sum_f W[f][tap] * dY[f][q] per pixel (dY read ONCE with LDG.128, 9*F FMAs per pixel),
+//             staged in shared memory, then dx[p] = sum_taps T[tap][p - tap]: 9 shared loads per dx pixel.
+//   wgrad   : dY planes arrive through a cp.async.bulk (TMA) ring, (image, 8-filter chunk) per stage, a
+//             producer thread keeps the ring full; consumers read dY with LDS.128 and accumulate
+//             privately; one block reduction + atomics per CTA at the end.
+// =====================================================================================================
+template <int C>
+__device__ __forceinline__ void flat_taps(float (&xin)[4][C * 9], const float* __restrict__ xb, int H, int W, int OW,
+                                          int pt, int pl, int p0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int p = p0 + e;
+        const int oy = p / OW, ox = p - oy * OW;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int iy = oy - pt + i;
+                const bool rok = iy >= 0 && iy < H;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int ix = ox - pl + j;
+                    xin[e][(c * 3 + i) * 3 + j] = (rok && ix >= 0 && ix < W) ? __ldg(xb + ((long)c * H + iy) * W + ix) : 0.f;
+                }
+            }
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) thin_fwd_flat_kernel(ThinArgs a) {
+    constexpr int K = C * 9, K4 = (K + 3) & ~3;
+    extern __shared__ __align__(16) float sm[];
+    float* sw = sm;                   // [F][K4]
+    float* sb = sm + a.F * K4;        // [F]  K*b
+    for (int e = threadIdx.x; e < a.F * K4; e += 256) {
+        const int f = e / K4, k = e - f * K4;
+        sw[e] = k < K ? a.w[(long)f * K + k] : 0.f;
+    }
+    for (int f = threadIdx.x; f < a.F; f += 256) sb[f] = (float)K * a.b[f];
+    __syncthreads();
+    const int plane = a.OH * a.OW, qpi = plane >> 2;
+    const long item = (long)blockIdx.x * 256 + threadIdx.x;
+    if (item >= (long)a.B * qpi) return;
+    const int b = (int)(item / qpi), q = (int)(item - (long)b * qpi);
+    float xin[4][K];
+    flat_taps<C>(xin, a.x + (long)b * C * a.H * a.W, a.H, a.W, a.OW, a.pt, a.pl, 4 * q);
+    float4* yq = reinterpret_cast<float4*>(a.y + (long)b * a.F * plane) + q;
+#pragma unroll 4
+    for (int f = 0; f < a.F; ++f) {
+        const float bb = sb[f];
+        float acc[4] = {bb, bb, bb, bb};
+        const float4* wr = reinterpret_cast<const float4*>(sw + f * K4);
+#pragma unroll
+        for (int k4 = 0; k4 < K4 / 4; ++k4) {
+            const float4 w4 = wr[k4];
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (4 * k4 + u < K) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[e] = fmaf(xin[e][4 * k4 + u], wv[u], acc[e]);
+                }
+        }
+        yq[(long)f * qpi] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+}
+
+constexpr int FLAT_DG_THREADS = 192;
+template <int C>
+__global__ void __launch_bounds__(FLAT_DG_THREADS) thin_dgrad_flat_kernel(ThinArgs a) {
+    constexpr int K = C * 9, K4 = (K + 3) & ~3;
+    extern __shared__ __align__(16) float sm[];
+    const int plane = a.OH * a.OW, qpi = plane >> 2;
+    float* sT = sm;                   // [K][plane]
+    float* sw = sm + K * plane;       // [F][K4]
+    for (int e = threadIdx.x; e < a.F * K4; e += FLAT_DG_THREADS) {
+        const int f = e / K4, k = e - f * K4;
+        sw[e] = k < K ? a.w[(long)f * K + k] : 0.f;
+    }
+    __syncthreads();
+    const int hw4 = (a.H * a.W) >> 2, w4n = a.W >> 2;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        // ---- phase 1: per-pixel contraction over the filters
+        const float4* dq = reinterpret_cast<const float4*>(a.dy + (long)b * a.F * plane);
+        for (int q = threadIdx.x; q < qpi; q += FLAT_DG_THREADS) {
+            float T[K][4];
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) T[k][e] = 0.f;
+            for (int f0 = 0; f0 < a.F; f0 += 8) {
+                float4 d[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) d[u] = (f0 + u < a.F) ? __ldg(dq + (long)(f0 + u) * qpi + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (f0 + u < a.F) {
+                        const float4* wr = reinterpret_cast<const float4*>(sw + (f0 + u) * K4);
+#pragma unroll
+                        for (int k4 = 0; k4 < K4 / 4; ++k4) {
+                            const float4 w4 = wr[k4];
+                            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                            for (int v = 0; v < 4; ++v)
+                                if (4 * k4 + v < K) {
+                                    T[4 * k4 + v][0] = fmaf(wv[v], d[u].x, T[4 * k4 + v][0]);
+                                    T[4 * k4 + v][1] = fmaf(wv[v], d[u].y, T[4 * k4 + v][1]);
+                                    T[4 * k4 + v][2] = fmaf(wv[v], d[u].z, T[4 * k4 + v][2]);
+                                    T[4 * k4 + v][3] = fmaf(wv[v], d[u].w, T[4 * k4 + v][3]);
+                                }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                *reinterpret_cast<float4*>(sT + k * plane + 4 * q) = make_float4(T[k][0], T[k][1], T[k][2], T[k][3]);
+        }
+        __syncthreads();
+        // ---- phase 2: dx[c, iy, ix] = sum_{i,j} T[c,i,j][iy + pt - i, ix + pl - j]
+        float4* xq = reinterpret_cast<float4*>(a.dx + (long)b * C * a.H * a.W);
+        for (int t = threadIdx.x; t < C * hw4; t += FLAT_DG_THREADS) {
+            const int c = t / hw4, r = t - c * hw4;
+            const int iy = r / w4n, ix0 = (r - iy * w4n) * 4;
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int oy = iy + a.pt - i;
+                if (oy < 0 || oy >= a.OH) continue;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float* tr = sT + ((c * 3 + i) * 3 + j) * plane + oy * a.OW;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int ox = ix0 + e + a.pl - j;
+                        if (ox >= 0 && ox < a.OW) o[e] += tr[ox];
+                    }
+                }
+            }
+            xq[t] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- wgrad: bulk-copy (TMA) ring ---------------------------------------------------------------------
+constexpr int FLAT_WG_CONSUMERS = 192, FLAT_WG_THREADS = FLAT_WG_CONSUMERS + 32, FLAT_WG_STAGES = 4;
+__host__ __device__ constexpr int flat_wg_ft(int C) { return C == 1 ? 8 : 4; }      // filters per CTA: FT*(9C+1) private accumulators per thread
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(ThinArgs a) {
+    constexpr int K = C * 9, FT = flat_wg_ft(C), ST = FLAT_WG_STAGES;
+    extern __shared__ __align__(128) uint8_t smraw[];
+    const int plane = a.OH * a.OW, qpi = plane >> 2, xsz = C * a.H * a.W;
+    const int f0 = blockIdx.y * FT, nf = min(FT, a.F - f0);
+    const uint32_t x_bytes = (uint32_t)xsz * 4, d_bytes = (uint32_t)nf * plane * 4;
+    const uint32_t stage_bytes = ((x_bytes + (uint32_t)FT * plane * 4) + 127u) & ~127u;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw);
+    uint64_t* empty = full + ST;
+    uint8_t* stages = smraw + 128;
+    __shared__ float red[FLAT_WG_CONSUMERS / 32][FT * (K + 1)];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < ST; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], FLAT_WG_CONSUMERS / 32); }
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+    const int nimg = (a.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // images b = blockIdx.x + n*gridDim.x
+
+    if (wid == FLAT_WG_CONSUMERS / 32) {
+        // ===== producer: one elected lane keeps ST stages of (x image, dY chunk) in flight =====
+        if (lane == 0) {
+            for (int n = 0; n < nimg; ++n) {
+                const int s = n % ST;
+                if (n >= ST) tc::mbar_wait(&empty[s], ((n / ST) - 1) & 1);
+                const long b = (long)blockIdx.x + (long)n * gridDim.x;
+                uint8_t* st = stages + (size_t)s * stage_bytes;
+                tc::mbar_arrive_expect_tx(&full[s], x_bytes + d_bytes);
+                bulk_g2s(st, a.x + b * xsz, x_bytes, &full[s]);
+                bulk_g2s(st + x_bytes, a.dy + (b * a.F + f0) * plane, d_bytes, &full[s]);
+            }
+        }
+        return;
+    }
+    // ===== consumers =====
+    float acc[FT][K + 1];
+#pragma unroll
+    for (int f = 0; f < FT; ++f)
+#pragma unroll
+        for (int k = 0; k <= K; ++k) acc[f][k] = 0.f;
+    for (int n = 0; n < nimg; ++n) {
+        const int s = n % ST;
+        tc::mbar_wait(&full[s], (n / ST) & 1);
+        const float* sx = reinterpret_cast<const float*>(stages + (size_t)s * stage_bytes);
+        const float* sd = sx + xsz;
+        for (int q = tid; q < qpi; q += FLAT_WG_CONSUMERS) {
+            float xin[4][K];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int p = 4 * q + e;
+                const int oy = p / a.OW, ox = p - oy * a.OW;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const int iy = oy - a.pt + i;
+                        const bool rok = iy >= 0 && iy < a.H;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const int ix = ox - a.pl + j;
+                            xin[e][(c * 3 + i) * 3 + j] = (rok && ix >= 0 && ix < a.W) ? sx[(c * a.H + iy) * a.W + ix] : 0.f;
+                        }
+                    }
+            }
+#pragma unroll
+            for (int f = 0; f < FT; ++f) {
+                if (f < nf) {
+                    const float4 d = *reinterpret_cast<const float4*>(sd + f * plane + 4 * q);
+                    acc[f][K] += (d.x + d.y) + (d.z + d.w);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        float t = acc[f][k];
+                        t = fmaf(d.x, xin[0][k], t); t = fmaf(d.y, xin[1][k], t);
+                        t = fmaf(d.z, xin[2][k], t); t = fmaf(d.w, xin[3][k], t);
+                        acc[f][k] = t;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&empty[s]);
+    }
+    // ===== block reduction + atomics =====
+#pragma unroll
+    for (int f = 0; f < FT; ++f)
+#pragma unroll
+        for (int k = 0; k <= K; ++k) {
+            const float v = warp_sum(acc[f][k]);
+            if (lane == 0) red[wid][f * (K + 1) + k] = v;
+        }
+    // consumers only: named barrier 1 (the producer warp has returned)
+    asm volatile("bar.sync 1, %0;" ::"n"(FLAT_WG_CONSUMERS) : "memory");
+    for (int e = tid; e < FT * (K + 1); e += FLAT_WG_CONSUMERS) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < FLAT_WG_CONSUMERS / 32; ++w) sum += red[w][e];
+        const int f = f0 + e / (K + 1), k = e % (K + 1);
+        if (f < a.F) {
+            if (k < K) atomicAdd(a.gw + (long)f * K + k, sum * a.inv_m);
+            else if (a.gb) atomicAdd(a.gb + f, sum * a.inv_m);
+        }
+    }
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool flat_ok(const ThinArgs& a, int C) {
+    return C <= 2 && ((a.OH * a.OW) & 3) == 0 && !getenv("DNB_NO_THIN_FLAT");
+}
+
+template <int C>
+static int thin_fwd_flat(const ThinArgs& a, cudaStream_t st) {
+    constexpr int K4 = (C * 9 + 3) & ~3;
+    const size_t smem = (size_t)a.F * (K4 + 1) * sizeof(float);
+    const long total = (long)a.B * ((a.OH * a.OW) >> 2);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(thin_fwd_flat_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    thin_fwd_flat_kernel<C><<<(unsigned)((total + 255) / 256), 256, smem, st>>>(a);
+    DNB_LAUNCH_CHECK("thin_conv2d_fwd");
+    return DNB_OK;
+}
+
+template <int C>
+static int thin_dgrad_flat(const ThinArgs& a, cudaStream_t st) {
+    constexpr int K = C * 9, K4 = (K + 3) & ~3;
+    const size_t smem = ((size_t)K * a.OH * a.OW + (size_t)a.F * K4) * sizeof(float);
+    cudaFuncSetAttribute(thin_dgrad_flat_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, thin_dgrad_flat_kernel<C>, FLAT_DG_THREADS, smem);
+    const int grid = std::min<long>(a.B, (long)kNumSMs * std::max(1, per_sm));
+    thin_dgrad_flat_kernel<C><<<grid, FLAT_DG_THREADS, smem, st>>>(a);
+    DNB_LAUNCH_CHECK("thin_conv2d_bwd_data");
+    return DNB_OK;
+}
+
+template <int C>
+static int thin_wgrad_flat(const ThinArgs& a, cudaStream_t st) {
+    constexpr int FT = flat_wg_ft(C);
+    const size_t stage = (((size_t)C * a.H * a.W + (size_t)FT * a.OH * a.OW) * 4 + 127) & ~(size_t)127;
+    const size_t smem = 128 + FLAT_WG_STAGES * stage;
+    cudaFuncSetAttribute(thin_wgrad_flat_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int fgroups = (a.F + FT - 1) / FT;
+    const int splits = (int)std::max<long>(1, std::min<long>(a.B, (2L * kNumSMs + fgroups - 1) / fgroups));
+    dim3 grid(splits, fgroups);
+    thin_wgrad_flat_kernel<C><<<grid, FLAT_WG_THREADS, smem, st>>>(a);
+    DNB_LAUNCH_CHECK("thin_conv2d_bwd_weight");
+    return DNB_OK;
+}
+
 bool thin_conv_supported(const dnb_win_t* g) {
     return g->C >= 1 && g->C <= 4 && g->kh == 3 && g->kw == 3 && g->sy == 1 && g->sx == 1 && g->F <= 1024;
 }
@@ -333,6 +645,7 @@ static int thin_dgrad_c(const ThinArgs& a, cudaStream_t st) {
 
 int thin_conv_fwd(const float* x, const float* w, const float* b, float* y, const dnb_win_t* g, cudaStream_t st) {
     ThinArgs a{x, w, b, y, nullptr, nullptr, nullptr, nullptr, g->B, g->H, g->W, g->F, g->OH, g->OW, g->pt, g->pl, 0.f, 0};
+    if (flat_ok(a, g->C) && al16(a.y)) return g->C == 1 ? thin_fwd_flat<1>(a, st) : thin_fwd_flat<2>(a, st);
     switch (g->C) {
         case 1: return thin_fwd_c<1>(a, st);
         case 2: return thin_fwd_c<2>(a, st);
@@ -345,7 +658,12 @@ int thin_conv_bwd(const float* x, const float* w, const float* dy, float* dx, fl
                   const dnb_win_t* g, float inv_m, bool skip_wgrad, cudaStream_t st) {
     ThinArgs a{x, w, nullptr, nullptr, dy, dx, gw, gb, g->B, g->H, g->W, g->F, g->OH, g->OW, g->pt, g->pl, inv_m, 0};
     int rc;
-    if (dx) {
+    const bool flat = flat_ok(a, g->C) && al16(a.dy);
+    const size_t dg_smem = ((size_t)g->C * 9 * g->OH * g->OW + (size_t)g->F * 12 * g->C) * 4;
+    if (dx && flat && (g->W & 3) == 0 && al16(dx) && dg_smem <= 200 * 1024) {
+        rc = g->C == 1 ? thin_dgrad_flat<1>(a, st) : thin_dgrad_flat<2>(a, st);
+        if (rc) return rc;
+    } else if (dx) {
         switch (g->C) {
             case 1: rc = thin_dgrad_c<1>(a, st); break;
             case 2: rc = thin_dgrad_c<2>(a, st); break;
@@ -355,6 +673,9 @@ int thin_conv_bwd(const float* x, const float* w, const float* dy, float* dx, fl
         if (rc) return rc;
     }
     if (skip_wgrad) return DNB_OK;          // the tensor-core wgrad takes it (math == tf32)
+    const size_t wg_stage = ((size_t)g->C * g->H * g->W + (size_t)flat_wg_ft(g->C) * g->OH * g->OW) * 4 + 128;
+    if (flat && al16(a.x) && ((g->C * g->H * g->W) & 3) == 0 && 128 + FLAT_WG_STAGES * wg_stage <= 110 * 1024)
+        return g->C == 1 ? thin_wgrad_flat<1>(a, st) : thin_wgrad_flat<2>(a, st);
     switch (g->C) {
         case 1: return thin_wgrad_c<1, 8>(a, st);
         case 2: return thin_wgrad_c<2, 4>(a, st);

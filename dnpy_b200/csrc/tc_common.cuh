@@ -56,6 +56,14 @@ __device__ __forceinline__ void sts32(uint32_t saddr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
 }
 
+// read-only shared loads the compiler may hoist and batch (no memory clobber: only for data that is not
+// rewritten after the initial __syncthreads, e.g. the staged bias)
+__device__ __forceinline__ float4 lds128_ro(uint32_t saddr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
 // ---- TMA -----------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -107,6 +115,17 @@ __device__ __forceinline__ void mma_tf32_acc(uint32_t d_tmem, uint64_t adesc, ui
 __device__ __forceinline__ void mma_tf32_init(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+// descriptors passed as (lo, hi) words, accumulate flag and issuing-lane predicate as values: in a fully
+// unrolled issue loop the operands reduce to (uniform base + immediate) and `acc` folds to a constant
+__device__ __forceinline__ void mma_tf32_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, bool acc, bool leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"((uint32_t)acc), "r"((uint32_t)leader) : "memory");
 }
 // all previously issued MMAs of this thread arrive on `bar` when they complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

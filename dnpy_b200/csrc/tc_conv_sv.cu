@@ -44,7 +44,9 @@ struct SvParams {
 constexpr int SV_LOADERS = 8, SV_EPI = 4;
 constexpr int SV_THREADS = (SV_LOADERS + SV_EPI + 1) * 32;
 
-template <int BN>
+// K33: 3x3 window known at compile time -> the MMA issue loop is fully unrolled, every descriptor is
+// (uniform base + immediate); CB = 32-channel blocks of the gathered tensor (0 = run-time).
+template <int BN, bool K33, int CB>
 __global__ void __launch_bounds__(SV_THREADS, 1)
 tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, SvParams p) {
     constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -63,6 +65,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, SvParams p) {
     uint64_t* acc_full = bars + 5;     // [2]
     uint64_t* acc_empty = bars + 7;    // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* s_bias = reinterpret_cast<float*>(bars + 10);   // [BN]  K*bias (0 without a bias): no global load in the store loop
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const long ngroups = (p.units + p.NI - 1) / p.NI;
@@ -70,6 +73,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, SvParams p) {
 
     // zero both image buffers once (slack rows and never-written garbage must stay finite)
     for (uint32_t e = tid; e < 2 * buf_bytes / 16; e += SV_THREADS) reinterpret_cast<float4*>(sX)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int f = tid; f < (BN < 32 ? 32 : BN); f += SV_THREADS) s_bias[f] = (p.bias && f < p.Cd) ? p.bias_k * __ldg(p.bias + f) : 0.f;
     if (tid == 0) {
         tma_prefetch_desc(&tmW);
         mbar_init(w_full, 1);
@@ -170,6 +174,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, SvParams p) {
         // ===================== epilogue: TMEM -> NCHW global =====================
         const int q = warp & 3;                             // TMEM lane quadrant of this warp
         const size_t plane_d = (size_t)p.Hd * p.Wd;
+        const uint32_t s_bias_u32 = smem_u32(s_bias);
         int tcount = 0;
         for (long g = blockIdx.x; g < ngroups; g += gridDim.x) {
             for (int t = 0; t < p.tiles; ++t, ++tcount) {
@@ -189,19 +194,19 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, SvParams p) {
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
+                    float bv[32];                           // K*bias of these 32 channels: 8 broadcast LDS.128 under the TMEM load
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 b4 = lds128_ro(s_bias_u32 + (uint32_t)(c0 + 4 * j4) * 4);
+                        bv[4 * j4] = b4.x; bv[4 * j4 + 1] = b4.y; bv[4 * j4 + 2] = b4.z; bv[4 * j4 + 3] = b4.w;
+                    }
                     tmem_ld_wait();
                     if (valid && !(p.debug & 1)) {
                         float* o = dp + (size_t)c0 * plane_d;
                         const int nvalid = min(32, min(BN - c0, p.Cd - c0));
-                        if (p.bias) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nvalid) { *o = fmaf(p.bias_k, __ldg(p.bias + c0 + j), __uint_as_float(v[j])); o += plane_d; }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nvalid) { *o = __uint_as_float(v[j]); o += plane_d; }
-                        }
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) { *o = __uint_as_float(v[j]) + bv[j]; o += plane_d; }
                     }
                 }
                 tc_fence_before();
@@ -221,6 +226,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, SvParams p) {
         mbar_wait(w_full, 0);
         const uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
         const uint64_t w_d0 = make_smem_desc(smem_u32(sW), 16, 1024);
+        const uint32_t pw8 = (uint32_t)p.PW * 8, region16 = region_bytes >> 4;
         int it = 0, tcount = 0;
         for (long g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
             const int s = it & 1;
@@ -231,25 +237,51 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, SvParams p) {
                 const int as = tcount & 1;
                 if (tcount >= 2) { mbar_wait(&acc_empty[as], ((tcount >> 1) - 1) & 1); tc_fence_after(); }
                 const uint32_t d_t = tmem_base + as * BN;
-                int kb = 0;
-                for (int i = 0; i < p.kh; ++i)
-                    for (int j = 0; j < p.kw; ++j) {
-                        const uint32_t shift16 = (uint32_t)(t * 128 + i * p.PW + j) * 8;       // (rows*128 B) >> 4
-                        for (int cb = 0; cb < cblks; ++cb, ++kb) {
-                            const uint64_t a = x_d0 + (uint64_t)(cb * (region_bytes >> 4) + shift16);
-                            const uint64_t bw = w_d0 + (uint64_t)(kb * (W_KB >> 4));
-                            if (!(p.debug & 2) && elect_one()) {
-                                if (kb == 0) mma_tf32_init(d_t, a, bw, idesc); else mma_tf32_acc(d_t, a, bw, idesc);
-                                mma_tf32_acc(d_t, a + 2, bw + 2, idesc);
-                                mma_tf32_acc(d_t, a + 4, bw + 4, idesc);
-                                mma_tf32_acc(d_t, a + 6, bw + 6, idesc);
+                // descriptor address fields only ever grow by < 256 KB >> 4: a plain 64-bit add never carries out
+                const uint64_t a_t = x_d0 + (uint64_t)((uint32_t)t * (128 * 8));
+                // ONE elected-thread region per tile (ptxas keeps the operands in uniform registers only when the
+                // branch is on the elect itself); inside it the 3x3 case is a straight line of MMAs whose
+                // descriptors are (tile base + immediate)
+                if (elect_one()) {
+                    if (!(p.debug & 2)) {
+                        if (K33 && CB > 0) {
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                const uint64_t a_i = a_t + (uint64_t)((uint32_t)i * pw8);
+#pragma unroll
+                                for (int j = 0; j < 3; ++j)
+#pragma unroll
+                                    for (int cb = 0; cb < CB; ++cb) {
+                                        const int kb = (i * 3 + j) * CB + cb;
+                                        const uint64_t a = a_i + (uint64_t)(j * 8) + (uint64_t)((uint32_t)cb * region16);
+                                        const uint64_t bw = w_d0 + (uint64_t)(kb * (W_KB >> 4));
+                                        if (kb == 0) mma_tf32_init(d_t, a, bw, idesc); else mma_tf32_acc(d_t, a, bw, idesc);
+                                        mma_tf32_acc(d_t, a + 2, bw + 2, idesc);
+                                        mma_tf32_acc(d_t, a + 4, bw + 4, idesc);
+                                        mma_tf32_acc(d_t, a + 6, bw + 6, idesc);
+                                    }
                             }
+                        } else {
+                            int kb = 0;
+                            for (int i = 0; i < p.kh; ++i)
+                                for (int j = 0; j < p.kw; ++j) {
+                                    const uint64_t a_ij = a_t + (uint64_t)((uint32_t)i * pw8 + (uint32_t)(j * 8));
+                                    for (int cb = 0; cb < cblks; ++cb, ++kb) {
+                                        const uint64_t a = a_ij + (uint64_t)((uint32_t)cb * region16);
+                                        const uint64_t bw = w_d0 + (uint64_t)(kb * (W_KB >> 4));
+                                        if (kb == 0) mma_tf32_init(d_t, a, bw, idesc); else mma_tf32_acc(d_t, a, bw, idesc);
+                                        mma_tf32_acc(d_t, a + 2, bw + 2, idesc);
+                                        mma_tf32_acc(d_t, a + 4, bw + 4, idesc);
+                                        mma_tf32_acc(d_t, a + 6, bw + 6, idesc);
+                                    }
+                                }
                         }
                     }
-                if (elect_one()) mma_commit(&acc_full[as]);
+                    mma_commit(&acc_full[as]);
+                    if (t == p.tiles - 1) mma_commit(&x_empty[s]);   // fires when every MMA that read this buffer is done
+                }
+                __syncwarp();
             }
-            if (elect_one()) mma_commit(&x_empty[s]);          // fires when every MMA that read this buffer is done
-            __syncwarp();
         }
     }
     tc_fence_before();
@@ -260,7 +292,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, SvParams p) {
 static size_t sv_smem_bytes(const SvParams& p, int bn) {
     const size_t region = (size_t)p.region_rows * 128;
     const size_t buf = ((region * (p.Cs / 32) + 1023) / 1024) * 1024;
-    return (size_t)p.nkb * bn * 128 + 2 * buf + 128 + 1024;
+    return (size_t)p.nkb * bn * 128 + 2 * buf + 128 + (size_t)(bn < 32 ? 32 : bn) * 4 + 1024;
 }
 
 // choose band height and units per group so that two image buffers + the resident filters fit in 227 KB
@@ -295,15 +327,22 @@ static bool sv_plan(SvParams& p, int bn) {
 
 static int pick_bn_sv(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128)); }
 
-template <int BN>
-static int sv_launch(const char* name, const CUtensorMap& tw, const SvParams& p, cudaStream_t st) {
+template <int BN, bool K33, int CB>
+static int sv_launch_k(const char* name, const CUtensorMap& tw, const SvParams& p, cudaStream_t st) {
     const size_t smem = sv_smem_bytes(p, BN);
-    cudaFuncSetAttribute(tc_conv_sv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(tc_conv_sv_kernel<BN, K33, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const long ngroups = (p.units + p.NI - 1) / p.NI;
     const int grid = (int)std::min<long>(ngroups, kNumSMs);
-    tc_conv_sv_kernel<BN><<<grid, SV_THREADS, smem, st>>>(tw, p);
+    tc_conv_sv_kernel<BN, K33, CB><<<grid, SV_THREADS, smem, st>>>(tw, p);
     DNB_LAUNCH_CHECK(name);
     return DNB_OK;
+}
+
+template <int BN>
+static int sv_launch(const char* name, const CUtensorMap& tw, const SvParams& p, cudaStream_t st) {
+    if (p.kh == 3 && p.kw == 3 && p.Cs == 32) return sv_launch_k<BN, true, 1>(name, tw, p, st);
+    if (p.kh == 3 && p.kw == 3 && p.Cs == 64) return sv_launch_k<BN, true, 2>(name, tw, p, st);
+    return sv_launch_k<BN, false, 0>(name, tw, p, st);
 }
 
 }  // namespace tc

@@ -118,6 +118,13 @@ BIG_CASES = [
     dict(name="big_dense_head", kind="Dense", in_shape=(1600,), batch=128, kw=dict(units=10, kernel_regularizer=["L2", 0.01])),
     dict(name="big_conv1", kind="Conv2D", in_shape=(1, 28, 28), batch=64,
          kw=dict(filters=32, kernel_size=(3, 3), strides=(1, 1), padding="none")),
+    # flat thin-conv kernels (C <= 2, plane % 4 == 0): filter-count tails, padding, many images per CTA, W % 4 != 0
+    dict(name="flat_conv_c2_same", kind="Conv2D", in_shape=(2, 12, 12), batch=37,
+         kw=dict(filters=7, kernel_size=(3, 3), strides=(1, 1), padding="same")),
+    dict(name="flat_conv_c1_same_many", kind="Conv2D", in_shape=(1, 8, 8), batch=700,
+         kw=dict(filters=5, kernel_size=(3, 3), strides=(1, 1), padding="same")),
+    dict(name="flat_conv_c1_w30", kind="Conv2D", in_shape=(1, 30, 30), batch=9,
+         kw=dict(filters=12, kernel_size=(3, 3), strides=(1, 1), padding="none")),
     dict(name="big_conv2", kind="Conv2D", in_shape=(32, 12, 12), batch=48,
          kw=dict(filters=64, kernel_size=(3, 3), strides=(1, 1), padding="same")),
     dict(name="big_conv_s2", kind="Conv2D", in_shape=(32, 16, 16), batch=16,
