@@ -545,6 +545,134 @@ __global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(Thi
     }
 }
 
+// ---- dgrad with the same bulk-copy ring (plane/4 <= 192: one quad per thread) ----------------------------
+// stage = (image, 8-filter chunk of dY); T accumulates over the chunks of an image in registers.
+constexpr int FLAT_DG_STAGES = 3, FLAT_DG_FT = 8;
+template <int C>
+__global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_dgrad_ring_kernel(ThinArgs a) {
+    constexpr int K = C * 9, K4 = (K + 3) & ~3, FT = FLAT_DG_FT, ST = FLAT_DG_STAGES, NC = FLAT_WG_CONSUMERS;
+    extern __shared__ __align__(128) uint8_t smraw[];
+    const int plane = a.OH * a.OW, qpi = plane >> 2;
+    const int G = (a.F + FT - 1) / FT;
+    const uint32_t stage_bytes = (uint32_t)FT * plane * 4;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw);
+    uint64_t* empty = full + ST;
+    uint8_t* stages = smraw + 128;
+    float* sT = reinterpret_cast<float*>(stages + (size_t)ST * stage_bytes);     // [K][plane]
+    float* sw = sT + K * plane;                                                  // [F][K4]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int e = tid; e < a.F * K4; e += FLAT_WG_THREADS) {
+        const int f = e / K4, k = e - f * K4;
+        sw[e] = k < K ? a.w[(long)f * K + k] : 0.f;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < ST; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], NC / 32); }
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+    const int nimg = (a.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (wid == NC / 32) {
+        if (lane == 0) {
+            int it = 0;
+            for (int n = 0; n < nimg; ++n) {
+                const long b = (long)blockIdx.x + (long)n * gridDim.x;
+                for (int g = 0; g < G; ++g, ++it) {
+                    const int s = it % ST;
+                    if (it >= ST) tc::mbar_wait(&empty[s], ((it / ST) - 1) & 1);
+                    const uint32_t bytes = (uint32_t)min(FT, a.F - g * FT) * plane * 4;
+                    tc::mbar_arrive_expect_tx(&full[s], bytes);
+                    bulk_g2s(stages + (size_t)s * stage_bytes, a.dy + (b * a.F + (long)g * FT) * plane, bytes, &full[s]);
+                }
+            }
+        }
+        return;
+    }
+    // phase-2 geometry of this thread's dx quads (image independent): up to 2 quads (C*H*W/4 <= 2*NC)
+    const int hw4 = (a.H * a.W) >> 2, w4n = a.W >> 2, nxq = C * hw4;
+    int x_base[2]; uint32_t x_rm[2], x_cm[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int t = min(tid + r * NC, nxq - 1);
+        const int c = t / hw4, rr = t - c * hw4;
+        const int iy = rr / w4n, ix0 = (rr - iy * w4n) * 4;
+        x_base[r] = (c * 9) * plane + (iy + a.pt) * a.OW + ix0 + a.pl;       // tap (i,j), element e: + (i*3+j)*plane - i*OW - j + e
+        uint32_t rm = 0, cm = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const int oy = iy + a.pt - i; if (oy >= 0 && oy < a.OH) rm |= 1u << i; }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const int ox = ix0 + e + a.pl - j; if (ox >= 0 && ox < a.OW) cm |= 1u << (j * 4 + e); }
+        x_rm[r] = rm; x_cm[r] = cm;
+    }
+    const bool active = tid < qpi;
+    int it = 0;
+    for (int n = 0; n < nimg; ++n) {
+        const long b = (long)blockIdx.x + (long)n * gridDim.x;
+        float T[K][4];
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) T[k][e] = 0.f;
+        for (int g = 0; g < G; ++g, ++it) {
+            const int s = it % ST;
+            tc::mbar_wait(&full[s], (it / ST) & 1);
+            if (active) {
+                const float4* sd = reinterpret_cast<const float4*>(stages + (size_t)s * stage_bytes) + tid;
+                const int nf = min(FT, a.F - g * FT);
+#pragma unroll
+                for (int u = 0; u < FT; ++u) {
+                    if (u < nf) {
+                        const float4 d = sd[u * qpi];
+                        const float4* wr = reinterpret_cast<const float4*>(sw + (g * FT + u) * K4);
+#pragma unroll
+                        for (int k4 = 0; k4 < K4 / 4; ++k4) {
+                            const float4 w4 = wr[k4];
+                            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                            for (int v = 0; v < 4; ++v)
+                                if (4 * k4 + v < K) {
+                                    T[4 * k4 + v][0] = fmaf(wv[v], d.x, T[4 * k4 + v][0]);
+                                    T[4 * k4 + v][1] = fmaf(wv[v], d.y, T[4 * k4 + v][1]);
+                                    T[4 * k4 + v][2] = fmaf(wv[v], d.z, T[4 * k4 + v][2]);
+                                    T[4 * k4 + v][3] = fmaf(wv[v], d.w, T[4 * k4 + v][3]);
+                                }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&empty[s]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");        // phase 2 of the previous image has finished reading sT
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                *reinterpret_cast<float4*>(sT + k * plane + 4 * tid) = make_float4(T[k][0], T[k][1], T[k][2], T[k][3]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+        float4* xq = reinterpret_cast<float4*>(a.dx + b * C * a.H * a.W);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int t = tid + r * NC;
+            if (t < nxq) {
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const float* tr = sT + x_base[r] + (i * 3 + j) * plane - i * a.OW - j;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (((x_rm[r] >> i) & 1u) && ((x_cm[r] >> (j * 4 + e)) & 1u)) o[e] += tr[e];
+                    }
+                xq[t] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static bool flat_ok(const ThinArgs& a, int C) {
     return C <= 2 && ((a.OH * a.OW) & 3) == 0 && !getenv("DNB_NO_THIN_FLAT");
@@ -575,11 +703,31 @@ static int thin_dgrad_flat(const ThinArgs& a, cudaStream_t st) {
 }
 
 template <int C>
+static int thin_dgrad_ring(const ThinArgs& a, cudaStream_t st) {
+    constexpr int K = C * 9, K4 = (K + 3) & ~3;
+    const int plane = a.OH * a.OW;
+    const size_t smem = 128 + (size_t)FLAT_DG_STAGES * FLAT_DG_FT * plane * 4 + ((size_t)K * plane + (size_t)a.F * K4) * 4;
+    cudaFuncSetAttribute(thin_dgrad_ring_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(thin_dgrad_ring_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    const int grid = (int)std::min<long>(a.B, 2L * kNumSMs);
+    thin_dgrad_ring_kernel<C><<<grid, FLAT_WG_THREADS, smem, st>>>(a);
+    DNB_LAUNCH_CHECK("thin_conv2d_bwd_data");
+    return DNB_OK;
+}
+static bool dgrad_ring_ok(const dnb_win_t* g) {
+    const int plane = g->OH * g->OW, K = g->C * 9;
+    const size_t smem = 128 + (size_t)FLAT_DG_STAGES * FLAT_DG_FT * plane * 4 + ((size_t)K * plane + (size_t)g->F * ((K + 3) & ~3)) * 4;
+    return (plane >> 2) <= FLAT_WG_CONSUMERS && g->C * ((g->H * g->W) >> 2) <= 2 * FLAT_WG_CONSUMERS && smem <= 110 * 1024 &&
+           !getenv("DNB_NO_THIN_RING");
+}
+
+template <int C>
 static int thin_wgrad_flat(const ThinArgs& a, cudaStream_t st) {
     constexpr int FT = flat_wg_ft(C);
     const size_t stage = (((size_t)C * a.H * a.W + (size_t)FT * a.OH * a.OW) * 4 + 127) & ~(size_t)127;
     const size_t smem = 128 + FLAT_WG_STAGES * stage;
     cudaFuncSetAttribute(thin_wgrad_flat_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!getenv("DNB_NO_CARVEOUT")) cudaFuncSetAttribute(thin_wgrad_flat_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     const int fgroups = (a.F + FT - 1) / FT;
     const int splits = (int)std::max<long>(1, std::min<long>(a.B, (2L * kNumSMs + fgroups - 1) / fgroups));
     dim3 grid(splits, fgroups);
@@ -661,7 +809,8 @@ int thin_conv_bwd(const float* x, const float* w, const float* dy, float* dx, fl
     const bool flat = flat_ok(a, g->C) && al16(a.dy);
     const size_t dg_smem = ((size_t)g->C * 9 * g->OH * g->OW + (size_t)g->F * 12 * g->C) * 4;
     if (dx && flat && (g->W & 3) == 0 && al16(dx) && dg_smem <= 200 * 1024) {
-        rc = g->C == 1 ? thin_dgrad_flat<1>(a, st) : thin_dgrad_flat<2>(a, st);
+        if (dgrad_ring_ok(g)) rc = g->C == 1 ? thin_dgrad_ring<1>(a, st) : thin_dgrad_ring<2>(a, st);
+        else rc = g->C == 1 ? thin_dgrad_flat<1>(a, st) : thin_dgrad_flat<2>(a, st);
         if (rc) return rc;
     } else if (dx) {
         switch (g->C) {

@@ -130,29 +130,58 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------
 constexpr int SKN = 16;      // padded output width
 
-// Y[b, o] = sum_i X[b,i] W[i,o] + bias[o]: a warp owns RPW rows, lanes stride over i; the (small, L1-resident)
-// W rows are read once per iteration and reused for all RPW rows of the warp.
-constexpr int RPW = 4;
+// Y[b, o] = sum_i X[b,i] W[i,o] + bias[o]: a warp owns RPW rows, lanes stride over i.  W is staged through
+// shared memory in chunks of SKC features (coalesced global reads; 80-byte pitch -> conflict-free LDS.128), and each
+// lane issues RPW x 8 independent X loads before the first FMA of a chunk step.
+constexpr int RPW = 2, SKC = 512, SKP = SKN + 4;
 __global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ y,
                                                          int B, int in, int out) {
+    __shared__ __align__(16) float sw[SKC * SKP];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int row0 = (blockIdx.x * 8 + wid) * RPW;
-    if (row0 >= B) return;
     float acc[RPW][SKN];
 #pragma unroll
     for (int r = 0; r < RPW; ++r)
 #pragma unroll
         for (int o = 0; o < SKN; ++o) acc[r][o] = 0.f;
-    for (int i = lane; i < in; i += 32) {
-        float wv[SKN];
+    const float* xr[RPW];
 #pragma unroll
-        for (int o = 0; o < SKN; ++o) wv[o] = o < out ? __ldg(w + (size_t)i * out + o) : 0.f;
+    for (int r = 0; r < RPW; ++r) xr[r] = x + (size_t)min(row0 + r, B - 1) * in;
+    for (int c0 = 0; c0 < in; c0 += SKC) {
+        const int cn = min(SKC, in - c0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cn * out; e += 256) {          // W[c0 .. c0+cn) is contiguous: coalesced
+            const int i = e / out, o = e - i * out;
+            sw[i * SKP + o] = __ldg(w + (size_t)c0 * out + e);
+        }
+        if (out < SKN)
+            for (int e = threadIdx.x; e < cn * (SKN - out); e += 256) {
+                const int i = e / (SKN - out), o = out + e - i * (SKN - out);
+                sw[i * SKP + o] = 0.f;
+            }
+        __syncthreads();
+        for (int i0 = lane; i0 < cn; i0 += 256) {
+            float xv[8][RPW];
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-            const float xv = (row0 + r < B) ? __ldg(x + (size_t)(row0 + r) * in + i) : 0.f;
+            for (int t = 0; t < 8; ++t)
 #pragma unroll
-            for (int o = 0; o < SKN; ++o) acc[r][o] = fmaf(xv, wv[o], acc[r][o]);
+                for (int r = 0; r < RPW; ++r) xv[t][r] = (i0 + 32 * t < cn) ? __ldg(xr[r] + c0 + i0 + 32 * t) : 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (i0 + 32 * t < cn) {
+                    const float4* wr = reinterpret_cast<const float4*>(sw + (i0 + 32 * t) * SKP);
+#pragma unroll
+                    for (int q = 0; q < SKN / 4; ++q) {
+                        const float4 w4 = wr[q];
+#pragma unroll
+                        for (int r = 0; r < RPW; ++r) {
+                            acc[r][4 * q] = fmaf(xv[t][r], w4.x, acc[r][4 * q]); acc[r][4 * q + 1] = fmaf(xv[t][r], w4.y, acc[r][4 * q + 1]);
+                            acc[r][4 * q + 2] = fmaf(xv[t][r], w4.z, acc[r][4 * q + 2]); acc[r][4 * q + 3] = fmaf(xv[t][r], w4.w, acc[r][4 * q + 3]);
+                        }
+                    }
+                }
+            }
         }
     }
 #pragma unroll
@@ -168,15 +197,50 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict
     }
 }
 
+// dX[b, i] = sum_o dY[b,o] W[i,o]: W^T staged in shared memory ([o][in], conflict-free LDS.128 along i), a thread owns
+// 4 consecutive features of TWO rows (each W quad is reused for both), stores are 128-bit and coalesced.
+__global__ void __launch_bounds__(256) skinny_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                        float* __restrict__ dx, int B, int in, int out, int rows_per_cta) {
+    extern __shared__ __align__(16) float sdx[];
+    float* swt = sdx;                         // [out][in]
+    float* sdy = sdx + (size_t)out * in;      // [rows_per_cta][SKN]
+    const int b0 = blockIdx.x * rows_per_cta, nr = min(rows_per_cta, B - b0);
+    for (int e = threadIdx.x; e < in * out; e += 256) {
+        const int i = e / out, o = e - i * out;
+        swt[o * in + i] = __ldg(w + e);
+    }
+    for (int e = threadIdx.x; e < rows_per_cta * SKN; e += 256) {
+        const int r = e / SKN, o = e % SKN;
+        sdy[e] = (r < nr && o < out) ? __ldg(dy + (size_t)(b0 + r) * out + o) : 0.f;
+    }
+    __syncthreads();
+    const int in4 = in >> 2;
+    for (int item = threadIdx.x; item < (rows_per_cta >> 1) * in4; item += 256) {
+        const int rp = item / in4, c4 = item - rp * in4;
+        const int r0 = 2 * rp;
+        if (r0 >= nr) break;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        for (int o = 0; o < out; ++o) {
+            const float4 w4 = *reinterpret_cast<const float4*>(swt + o * in + 4 * c4);
+            const float d0 = sdy[r0 * SKN + o], d1 = sdy[(r0 + 1) * SKN + o];
+            a0.x = fmaf(d0, w4.x, a0.x); a0.y = fmaf(d0, w4.y, a0.y); a0.z = fmaf(d0, w4.z, a0.z); a0.w = fmaf(d0, w4.w, a0.w);
+            a1.x = fmaf(d1, w4.x, a1.x); a1.y = fmaf(d1, w4.y, a1.y); a1.z = fmaf(d1, w4.z, a1.z); a1.w = fmaf(d1, w4.w, a1.w);
+        }
+        reinterpret_cast<float4*>(dx + (size_t)(b0 + r0) * in)[c4] = a0;
+        if (r0 + 1 < nr) reinterpret_cast<float4*>(dx + (size_t)(b0 + r0 + 1) * in)[c4] = a1;
+    }
+}
+
 // gW[i, o] += inv_m * (sum_b X[b,i] dY[b,o] + reg'(W[i,o])): a CTA owns a slice of the batch and 256*IPT features;
-// lanes run along i (coalesced X rows), dY rows are broadcast; partial tiles are added atomically.
+// lanes run along i (coalesced X rows), dY rows are broadcast from shared memory; 8 rows of X loads are in flight per
+// thread before the first FMA; partial tiles are added atomically.
 template <int IPT>
 __global__ void __launch_bounds__(256) skinny_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                         const float* __restrict__ w, float* __restrict__ gw,
                                                         const float* __restrict__ bvec, float* __restrict__ gb,
                                                         int B, int in, int out, int rows_per_cta, float inv_m, float l1, float l2,
                                                         float bl1, float bl2) {
-    __shared__ float sd[64][SKN];
+    __shared__ __align__(16) float sd[64][SKN];
     float accb = 0.f;                 // blockIdx.x == 0, thread o < out: column sum of dY -> gb
     const int i0 = blockIdx.x * 256 * IPT;
     const int b0 = blockIdx.y * rows_per_cta, b1 = min(B, b0 + rows_per_cta);
@@ -185,6 +249,9 @@ __global__ void __launch_bounds__(256) skinny_dw_kernel(const float* __restrict_
     for (int t = 0; t < IPT; ++t)
 #pragma unroll
         for (int o = 0; o < SKN; ++o) acc[t][o] = 0.f;
+    bool iv[IPT];
+#pragma unroll
+    for (int t = 0; t < IPT; ++t) iv[t] = i0 + (int)threadIdx.x + t * 256 < in;
     for (int bb = b0; bb < b1; bb += 64) {
         __syncthreads();
         for (int e = threadIdx.x; e < 64 * SKN; e += 256) {
@@ -195,18 +262,24 @@ __global__ void __launch_bounds__(256) skinny_dw_kernel(const float* __restrict_
         const int nr = min(64, b1 - bb);
         if (blockIdx.x == 0 && threadIdx.x < SKN)
             for (int r = 0; r < nr; ++r) accb += sd[r][threadIdx.x];
-        for (int r = 0; r < nr; ++r) {
-            const float* xr = x + (size_t)(bb + r) * in + i0 + threadIdx.x;
-            float xv[IPT];
+        for (int r0 = 0; r0 < nr; r0 += 8) {
+            float xv[8][IPT];
 #pragma unroll
-            for (int t = 0; t < IPT; ++t) xv[t] = (i0 + threadIdx.x + t * 256 < in) ? __ldg(xr + t * 256) : 0.f;
+            for (int u = 0; u < 8; ++u) {
+                const float* xr = x + (size_t)(bb + r0 + u) * in + i0 + threadIdx.x;
 #pragma unroll
-            for (int q = 0; q < SKN / 4; ++q) {
-                const float4 d4 = *reinterpret_cast<const float4*>(&sd[r][4 * q]);
+                for (int t = 0; t < IPT; ++t) xv[u][t] = (r0 + u < nr && iv[t]) ? __ldg(xr + t * 256) : 0.f;
+            }
 #pragma unroll
-                for (int t = 0; t < IPT; ++t) {
-                    acc[t][4 * q] = fmaf(xv[t], d4.x, acc[t][4 * q]); acc[t][4 * q + 1] = fmaf(xv[t], d4.y, acc[t][4 * q + 1]);
-                    acc[t][4 * q + 2] = fmaf(xv[t], d4.z, acc[t][4 * q + 2]); acc[t][4 * q + 3] = fmaf(xv[t], d4.w, acc[t][4 * q + 3]);
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int q = 0; q < SKN / 4; ++q) {
+                    const float4 d4 = *reinterpret_cast<const float4*>(&sd[min(r0 + u, 63)][4 * q]);
+#pragma unroll
+                    for (int t = 0; t < IPT; ++t) {
+                        acc[t][4 * q] = fmaf(xv[u][t], d4.x, acc[t][4 * q]); acc[t][4 * q + 1] = fmaf(xv[u][t], d4.y, acc[t][4 * q + 1]);
+                        acc[t][4 * q + 2] = fmaf(xv[u][t], d4.z, acc[t][4 * q + 2]); acc[t][4 * q + 3] = fmaf(xv[u][t], d4.w, acc[t][4 * q + 3]);
+                    }
                 }
             }
         }
@@ -264,13 +337,18 @@ int dnb_dense_bwd(const float* x, const float* w, const float* b, const float* d
     cudaStream_t st = S(stream);
     int rc;
     if (out <= SKN && B >= 64) {
-        if (dx) {
+        const size_t dx_smem = ((size_t)out * in + 32 * SKN) * sizeof(float);
+        if (dx && (in & 3) == 0 && dx_smem <= 160 * 1024 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+            cudaFuncSetAttribute(skinny_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dx_smem);
+            skinny_dx_kernel<<<(B + 31) / 32, 256, dx_smem, st>>>(dy, w, dx, B, in, out, 32);
+            DNB_LAUNCH_CHECK("dense_bwd_dx");
+        } else if (dx) {
             GemmArgs a{dy, out, 1, w, 1, out, dx, B, in, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0};
             rc = launch_sgemm<EPI_STORE>("dense_bwd_dx", a, st);
             if (rc) return rc;
         }
         const int itiles = (in + 511) / 512;
-        int bsplit = std::max(1, std::min((B + 255) / 256, (2 * kNumSMs + itiles - 1) / itiles));
+        int bsplit = std::max(1, std::min((B + 127) / 128, (4 * kNumSMs + itiles - 1) / itiles));
         int rows = ((B + bsplit - 1) / bsplit + 63) / 64 * 64;
         dim3 grid(itiles, (B + rows - 1) / rows);
         skinny_dw_kernel<2><<<grid, 256, 0, st>>>(x, dy, w, gw, b, gb, B, in, out, rows, inv_m, reg_w.l1 * reg_scale,
