@@ -139,13 +139,14 @@ __global__ void __launch_bounds__(256) maxpool_bwd_ps_strip_kernel(const float* 
 }
 
 // LITERAL step 1: last[c,oy,ox,p] = max b with idx[b,c,oy,ox] == p  (int32, pre-filled with -1)
+// step 1b: samples [0, b_end) in chunks, only for positions step 1a could not finish (constant windows ...)
 __global__ void __launch_bounds__(256) maxpool_last_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ last,
-                                                           dnb_win_t g, int bchunk) {
+                                                           const int32_t* __restrict__ done, dnb_win_t g, int bchunk, int b_end) {
     const long npos = (long)g.C * g.OH * g.OW;
     const long pos = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= npos) return;
+    if (pos >= npos || done[pos]) return;
     const int P = g.kh * g.kw;
-    const int b_hi = min(g.B, (int)(blockIdx.y + 1) * bchunk) - 1, b_lo = blockIdx.y * bchunk;
+    const int b_hi = min(b_end, (int)(blockIdx.y + 1) * bchunk) - 1, b_lo = blockIdx.y * bchunk;
     // walk this chunk from its last sample down; the first hit per offset is the chunk's last
     unsigned long long seen_lo = 0ull;      // offsets 0..63 tracked in a bitmask, the rest go straight to atomicMax
     for (int b = b_hi; b >= b_lo; --b) {
@@ -156,6 +157,30 @@ __global__ void __launch_bounds__(256) maxpool_last_kernel(const int32_t* __rest
         }
         atomicMax(last + pos * P + p, b);
     }
+}
+// LITERAL step 1a: the newest TOP samples decide almost every (window, offset) pair — a thread walks its window
+// position from the last sample down and stops as soon as all kh*kw offsets have been seen (plain stores: no
+// other thread owns this position).  done[pos] tells step 1b (maxpool_last_kernel over the older samples) to skip it.
+__global__ void __launch_bounds__(128) maxpool_last_top_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ last,
+                                                               int32_t* __restrict__ done, dnb_win_t g, int top) {
+    const long npos = (long)g.C * g.OH * g.OW;
+    const long pos = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= npos) return;
+    const int P = g.kh * g.kw;
+    const unsigned long long all = P >= 64 ? ~0ull : ((1ull << P) - 1ull);
+    unsigned long long seen = 0ull;
+    const int b_lo = max(0, g.B - top);
+    for (int b0 = g.B - 1; b0 >= b_lo && seen != all; b0 -= 8) {
+        int pv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) pv[u] = (b0 - u >= b_lo) ? __ldg(idx + (long)(b0 - u) * npos + pos) : -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int p = pv[u];
+            if (p >= 0 && p < 64 && !(seen >> p & 1ull)) { seen |= 1ull << p; last[pos * P + p] = b0 - u; }
+        }
+    }
+    done[pos] = (P <= 64 && seen == all) || b_lo == 0;
 }
 // LITERAL step 2: dx[0,c,iy,ix] = sum over covering windows of dy[last, c, oy, ox]; dx[b>0] = 0
 __global__ void __launch_bounds__(256) maxpool_bwd_literal_kernel(const float* __restrict__ dy, const int32_t* __restrict__ last,
@@ -253,7 +278,7 @@ int dnb_maxpool2d_fwd(const float* x, float* y, int32_t* idx, const dnb_win_t* g
 
 size_t dnb_maxpool2d_bwd_ws_bytes(const dnb_win_t* g, int route) {
     if (!g || route != DNB_ROUTE_LITERAL) return 0;
-    return (size_t)g->C * g->OH * g->OW * g->kh * g->kw * sizeof(int32_t);
+    return (size_t)g->C * g->OH * g->OW * (g->kh * g->kw + 1) * sizeof(int32_t);      // last[npos][P] + done[npos]
 }
 
 int dnb_maxpool2d_bwd(const float* dy, const int32_t* idx, float* dx, const dnb_win_t* g,
@@ -284,10 +309,15 @@ int dnb_maxpool2d_bwd(const float* dy, const int32_t* idx, float* dx, const dnb_
     int32_t* last = static_cast<int32_t*>(ws);
     cudaError_t e = cudaMemsetAsync(last, 0xff, (size_t)npos * P * sizeof(int32_t), st);     // -1
     if (e != cudaSuccess) return set_err(DNB_ERR_CUDA, "maxpool2d_bwd: %s", cudaGetErrorString(e));
-    const int bchunk = 64;
-    dim3 grid((unsigned)((npos + 255) / 256), (g->B + bchunk - 1) / bchunk);
-    maxpool_last_kernel<<<grid, 256, 0, st>>>(idx, last, *g, bchunk);
-    DNB_LAUNCH_CHECK("maxpool2d_bwd_last");
+    int32_t* done = last + npos * P;
+    const int top = 128, bchunk = 64;
+    maxpool_last_top_kernel<<<(unsigned)((npos + 127) / 128), 128, 0, st>>>(idx, last, done, *g, top);
+    DNB_LAUNCH_CHECK("maxpool2d_bwd_last_top");
+    if (g->B > top) {
+        dim3 grid((unsigned)((npos + 255) / 256), (g->B - top + bchunk - 1) / bchunk);
+        maxpool_last_kernel<<<grid, 256, 0, st>>>(idx, last, done, *g, bchunk, g->B - top);
+        DNB_LAUNCH_CHECK("maxpool2d_bwd_last");
+    }
     const long n0 = (long)g->C * g->H * g->W;
     if (g->B > 1) {
         e = cudaMemsetAsync(dx + n0, 0, (size_t)(n - n0) * sizeof(float), st);               // samples 1..B-1 get no delta

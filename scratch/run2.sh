@@ -1,6 +1,5 @@
-python -m pytest tests/test_gpu_layers.py -m gpu -x -q -k "conv or Conv or dense or Dense" 2>&1 | tail -3
-for v in 0 1; do
-if [ $v = 1 ]; then export DNB_NO_CARVEOUT=1; fi
+python -m pytest tests/test_gpu_layers.py -m gpu -x -q -k "pool or Pool" 2>&1 | tail -3
+python -m pytest tests/test_gpu_nets.py -m gpu -x -q 2>&1 | tail -3
 python bench.py --no-cpu --steps 10 > gpurun_out/b2.json 2> gpurun_out/b2.err; tail -3 gpurun_out/b2.err
 python - <<'PY'
 import json
@@ -8,4 +7,3 @@ d=json.load(open('gpurun_out/b2.json'))
 print(round(d['value']), d['ms_per_step'], d['e2e']['value'], d['roofline']['kernel'], d['roofline']['frac'])
 print([(k['kernel'].split('/')[-1], round(k['ms_per_step'],3)) for k in d['top_kernels']])
 PY
-done
