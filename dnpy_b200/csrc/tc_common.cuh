@@ -174,9 +174,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_tiled();
-// fp32 tensor with `rank` dims (innermost first), byte strides for dims 1.., box per dim; 128B swizzle, zero OOB fill
+// fp32 tensor with `rank` dims (innermost first), byte strides for dims 1.., box per dim; zero OOB fill;
+// swz: 0 = 128B swizzle, 1 = 128B swizzle with 32B atoms (MN-major 32-bit operands), 2 = no swizzle (raw staging)
 bool make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, bool atom32 = false);
+                   const uint32_t* box, int swz = 0);
 
 }  // namespace tc
 }  // namespace dnb

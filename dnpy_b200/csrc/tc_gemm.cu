@@ -34,7 +34,7 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 bool make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, bool atom32) {
+                   const uint32_t* box, int swz) {
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return false;
     cuuint64_t gdim[5], gstr[5];
@@ -42,7 +42,7 @@ bool make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t*
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz == 1 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (swz == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B),
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
