@@ -632,6 +632,7 @@ static int launch_wgrad(const CUtensorMap& td, WgradParams p, int fb, cudaStream
 int tc_conv_wgrad(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, void* ws,
                   cudaStream_t st) {
     (void)ws;
+    if (tc_conv_wgrad_sv_supported(g)) return tc_conv_wgrad_sv(x, dy, gw, gb, g, inv_m, st);
     const int K = g->C * g->kh * g->kw;
     const int npx = g->OH * g->OW;
     const int mt = (K + 1 + CBM - 1) / CBM;

@@ -19,4 +19,8 @@ bool tc_conv_sv_supported(const dnb_win_t* g, bool dgrad);
 int tc_conv_sv_run(const char* name, const float* src, const float* wprep, int n_pad, int Kp, const float* bias, float bias_k,
                    float* dst, const dnb_win_t* g, bool dgrad, cudaStream_t st);
 
+// tc_conv_wg.cu: shifted-view weight gradient (3x3 stride 1, 32 input channels, small images)
+bool tc_conv_wgrad_sv_supported(const dnb_win_t* g);
+int tc_conv_wgrad_sv(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, cudaStream_t st);
+
 }  // namespace dnb

@@ -1,0 +1,318 @@
+// "Shifted-view" weight gradient for 3x3 stride-1 convolutions with 32 input channels and small images (conv2 of
+// the MNIST CNN: 32 x 12 x 12 -> 64 x 12 x 12): gW[f][c][i][j] = (1/m) sum_{b,oy,ox} dY[b,f,oy,ox] * Xp[b,c,oy+i,ox+j].
+//
+// The reduction runs over pixels, so both operands are staged PIXEL-major (one 128-byte row per pixel of the
+// zero-padded PW-wide grid, 32 channels / filters per row) and fed to the tensor core as MN-major TF32 operands
+// (128B swizzle with 32-byte atoms):
+//     A = dY  rows m = oy*PW + ox (zero in the pad columns)      M = filters (32-element chunks, LBO = region pitch)
+//     B = Xp  rows m + i*PW + j                                   N = (j, c): the three column taps of a kernel row are
+//                                                                  three 32-channel chunks ONE ROW APART (LBO = 128 B)
+//     D_i[f][(j,c)] += A[k][f] * B[k][(j,c)]                      K = 8 pixel rows per MMA, 3 MMAs (i = 0,1,2) per K step
+// Like the forward kernel nothing is ever im2col'ed: a tap is a start-address shift of the one staged image (the
+// swizzle is a function of the absolute address), and here even the j taps are folded into the N extent of one MMA.
+// The three accumulators D_i (128 x 96 fp32, TMEM) persist over ALL images of the CTA; one epilogue at the end.
+//
+//   warp 0      TMA producer: raw NCHW x image + dY image (4-D tiled maps, no swizzle) per unit
+//   warp 1      MMA issue (tcgen05.mma.kind::tf32, M=128 N=96, both operands MN-major)
+//   warps 2-9   transposers raw -> swizzled pixel-major (conflict-free LDS, STS.128) + running sum of dY for gb;
+//               afterwards the same warps read TMEM and add the CTA's partial gW / gb atomically.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_conv.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+namespace dnb {
+namespace tc {
+
+struct WgSvParams {
+    float* gw; float* gb;
+    int B, H, W, F, OH, OW, pt, pl;
+    int PW;                  // padded row pitch in pixels: OW + 2
+    int KR;                  // reduction rows per image: round_up(OH*PW, 8)
+    int xs_rows;             // rows of one staged X buffer (padded image + tap/chunk overhang), multiple of 8
+    int fr;                  // 32-filter regions of dY: F / 32
+    float inv_m;
+};
+
+constexpr int WG_TR = 8;                                   // transposer warps
+constexpr int WGSV_THREADS = (2 + WG_TR) * 32;
+constexpr int WG_TBX = 6, WG_TBD = 10;                     // task slots per transposer thread (x / dY)
+
+__device__ __forceinline__ void wg_tma_load_4d(void* dst, const CUtensorMap* m, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ float wg_lds32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tmem_ld_16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+// byte offset of 4 consecutive MN elements (16 bytes, quad q8 of 8) of K row `row` in the 32B-atom 128B swizzle
+__device__ __forceinline__ uint32_t sw32_off(int row, int q8) {
+    return (uint32_t)row * 128 + ((((q8 >> 1) ^ (row & 3)) & 3) << 5) + ((q8 & 1) << 4);
+}
+
+__global__ void __launch_bounds__(WGSV_THREADS, 1)
+tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, WgSvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t dreg_bytes = (uint32_t)p.KR * 128;                    // one 32-filter region of a dY buffer
+    const uint32_t dbuf_bytes = dreg_bytes * p.fr;
+    const uint32_t xbuf_bytes = (uint32_t)p.xs_rows * 128;
+    const uint32_t rawx_bytes = (uint32_t)p.H * p.W * 32 * 4, rawd_box = (uint32_t)p.OH * p.OW * 32 * 4;
+    uint8_t* sD = smem;                                    // 2 x fr regions (A operand; chunks >= fr of the M=128 MMA alias what follows)
+    uint8_t* sX = sD + 2 * (size_t)dbuf_bytes;             // 2 buffers (B operand)
+    uint8_t* sRx = sX + 2 * (size_t)xbuf_bytes;            // raw x image   [32][H][W]
+    uint8_t* sRd = sRx + rawx_bytes;                       // raw dY image  [F][OH][OW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRd + (size_t)rawd_box * p.fr);
+    uint64_t* raw_full = bars;         // tx
+    uint64_t* raw_empty = bars + 1;    // WG_TR
+    uint64_t* xd_full = bars + 2;      // [2] WG_TR
+    uint64_t* xd_empty = bars + 4;     // [2] commit
+    uint64_t* acc_full = bars + 6;     // commit
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    float* s_gb = reinterpret_cast<float*>(bars + 8);      // [128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int nimg = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    // zero the staged buffers once: pad ring / pad columns / overhang rows are never written afterwards
+    for (uint32_t e = tid; e < (2 * dbuf_bytes + 2 * xbuf_bytes) / 16; e += WGSV_THREADS)
+        reinterpret_cast<float4*>(sD)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < 128) s_gb[tid] = 0.f;
+    if (tid == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmD);
+        mbar_init(raw_full, 1); mbar_init(raw_empty, WG_TR);
+        for (int s = 0; s < 2; ++s) { mbar_init(&xd_full[s], WG_TR); mbar_init(&xd_empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            for (int n = 0; n < nimg; ++n) {
+                if (n >= 1) mbar_wait(raw_empty, (n - 1) & 1);
+                const int b = (int)blockIdx.x + n * (int)gridDim.x;
+                mbar_arrive_expect_tx(raw_full, rawx_bytes + rawd_box * p.fr);
+                wg_tma_load_4d(sRx, &tmX, 0, 0, 0, b, raw_full);
+                for (int r = 0; r < p.fr; ++r) wg_tma_load_4d(sRd + (size_t)r * rawd_box, &tmD, 0, 0, r * 32, b, raw_full);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issue =====================
+        const uint32_t idesc = make_idesc_tf32(128, 96, 1, 1);
+        const int ksteps = p.KR >> 3;
+        const uint32_t pw8 = (uint32_t)p.PW * 8;
+        for (int n = 0; n < nimg; ++n) {
+            const int s = n & 1;
+            mbar_wait(&xd_full[s], (n >> 1) & 1);
+            tc_fence_after();
+            // A: M chunks of 32 filters dreg_bytes apart, 4-row atoms 512 B apart; B: N chunks = the same rows + j
+            const uint64_t a0 = make_smem_desc(smem_u32(sD + (size_t)s * dbuf_bytes), dreg_bytes, 512, LAYOUT_SW128_BASE32B);
+            const uint64_t b0 = make_smem_desc(smem_u32(sX + (size_t)s * xbuf_bytes), 128, 512, LAYOUT_SW128_BASE32B);
+            if (elect_one()) {
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint64_t a = a0 + (uint64_t)((uint32_t)ks * 64);                 // 8 rows = 1024 B
+                    const uint64_t bq = b0 + (uint64_t)((uint32_t)ks * 64);
+                    const uint32_t acc = (n > 0 || ks > 0) ? 1u : 0u;
+                    mma_tf32(tmem_base, a, bq, idesc, acc);
+                    mma_tf32(tmem_base + 96, a, bq + (uint64_t)pw8, idesc, acc);
+                    mma_tf32(tmem_base + 192, a, bq + (uint64_t)(2 * pw8), idesc, acc);
+                }
+                mma_commit(&xd_empty[s]);
+                if (n == nimg - 1) mma_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== transposers =====================
+        const int ttid = tid - 64;
+        constexpr int LT = WG_TR * 32;
+        const int npx_x = p.H * p.W, npx_d = p.OH * p.OW;
+        const int tasks_x = npx_x * 8, tasks_d = npx_d * 8 * p.fr;
+        const uint32_t chx = (uint32_t)npx_x * 4, chd = (uint32_t)npx_d * 4;        // bytes between channels of the raw images
+        uint32_t xs_src[WG_TBX], xs_dst[WG_TBX], ds_src[WG_TBD], ds_dst[WG_TBD];
+#pragma unroll
+        for (int r = 0; r < WG_TBX; ++r) {
+            const int t = ttid + r * LT;
+            xs_src[r] = 0; xs_dst[r] = 0xffffffffu;
+            if (t < tasks_x) {
+                const int pp = t % npx_x, quad = t / npx_x;
+                const int y = pp / p.W, x = pp - y * p.W;
+                const int row = (y + p.pt) * p.PW + x + p.pl;
+                xs_src[r] = (uint32_t)(quad * 4) * chx + (uint32_t)pp * 4;
+                xs_dst[r] = sw32_off(row, quad);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < WG_TBD; ++r) {
+            const int t = ttid + r * LT;
+            ds_src[r] = 0; ds_dst[r] = 0xffffffffu;
+            if (t < tasks_d) {
+                const int pp = t % npx_d, qf = t / npx_d;               // qf: filter quad 0 .. 8*fr-1
+                const int oy = pp / p.OW, ox = pp - oy * p.OW;
+                const int row = oy * p.PW + ox;
+                ds_src[r] = (uint32_t)(qf * 4) * chd + (uint32_t)pp * 4;
+                ds_dst[r] = (uint32_t)(qf >> 3) * dreg_bytes + sw32_off(row, qf & 7);
+            }
+        }
+        float gbs[WG_TBD][4];
+#pragma unroll
+        for (int r = 0; r < WG_TBD; ++r) { gbs[r][0] = 0.f; gbs[r][1] = 0.f; gbs[r][2] = 0.f; gbs[r][3] = 0.f; }
+        const uint32_t rx = smem_u32(sRx), rd = smem_u32(sRd);
+        for (int n = 0; n < nimg; ++n) {
+            const int s = n & 1;
+            mbar_wait(raw_full, n & 1);
+            if (n >= 2) mbar_wait(&xd_empty[s], ((n >> 1) - 1) & 1);
+            const uint32_t xb = smem_u32(sX + (size_t)s * xbuf_bytes), db = smem_u32(sD + (size_t)s * dbuf_bytes);
+#pragma unroll
+            for (int r0 = 0; r0 < WG_TBX; r0 += 3) {
+                float4 v[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    if (xs_dst[r0 + r] != 0xffffffffu) {
+                        const uint32_t a = rx + xs_src[r0 + r];
+                        v[r].x = wg_lds32(a); v[r].y = wg_lds32(a + chx); v[r].z = wg_lds32(a + 2 * chx); v[r].w = wg_lds32(a + 3 * chx);
+                    }
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    if (xs_dst[r0 + r] != 0xffffffffu) sts128(xb + xs_dst[r0 + r], v[r]);
+            }
+#pragma unroll
+            for (int r0 = 0; r0 < WG_TBD; r0 += 5) {
+                float4 v[5];
+#pragma unroll
+                for (int r = 0; r < 5; ++r)
+                    if (ds_dst[r0 + r] != 0xffffffffu) {
+                        const uint32_t a = rd + ds_src[r0 + r];
+                        v[r].x = wg_lds32(a); v[r].y = wg_lds32(a + chd); v[r].z = wg_lds32(a + 2 * chd); v[r].w = wg_lds32(a + 3 * chd);
+                    }
+#pragma unroll
+                for (int r = 0; r < 5; ++r)
+                    if (ds_dst[r0 + r] != 0xffffffffu) {
+                        sts128(db + ds_dst[r0 + r], v[r]);
+                        gbs[r0 + r][0] += v[r].x; gbs[r0 + r][1] += v[r].y; gbs[r0 + r][2] += v[r].z; gbs[r0 + r][3] += v[r].w;
+                    }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&xd_full[s]); mbar_arrive(raw_empty); }
+        }
+        // ---- bias gradient: per-slot sums -> shared -> global
+        if (p.gb) {
+#pragma unroll
+            for (int r = 0; r < WG_TBD; ++r) {
+                const int t = ttid + r * LT;
+                if (t < tasks_d) {
+                    const int f0 = (t / npx_d) * 4;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) atomicAdd(&s_gb[f0 + u], gbs[r][u]);
+                }
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(WG_TR * 32) : "memory");
+        if (p.gb && ttid < p.F && nimg > 0) atomicAdd(p.gb + ttid, s_gb[ttid] * p.inv_m);
+        // ---- epilogue: D_i[f][(j,c)] -> gW[f][c][i][j]
+        if (nimg > 0) {
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            const int q = warp & 3, half = (warp - 2) >> 2;           // lane quadrant, column half (144 columns each)
+            const int f = q * 32 + lane;
+            if (q * 32 < p.F) {
+#pragma unroll 1
+                for (int c0 = half * 144; c0 < half * 144 + 144; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld_16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                    tmem_ld_wait();
+                    if (f < p.F) {
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            const int col = c0 + u;
+                            const int i = col / 96, jc = col - i * 96, j = jc >> 5, c = jc & 31;
+                            atomicAdd(p.gw + (((size_t)f * 32 + c) * 3 + i) * 3 + j, __uint_as_float(v[u]) * p.inv_m);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static size_t wgsv_smem(const WgSvParams& p) {
+    return 2 * (size_t)p.KR * 128 * p.fr + 2 * (size_t)p.xs_rows * 128 + (size_t)p.H * p.W * 32 * 4 +
+           (size_t)p.OH * p.OW * 32 * 4 * p.fr + 64 + 128 * 4 + 1024;
+}
+
+static bool wgsv_plan(const dnb_win_t* g, WgSvParams& p) {
+    if (g->kh != 3 || g->kw != 3 || g->sy != 1 || g->sx != 1 || g->C != 32) return false;
+    if (g->F % 32 || g->F > 128 || g->W % 4 || g->OW % 4) return false;
+    if (g->OH != g->H + g->pt + g->pb - 2 || g->OW != g->W + g->pl + g->pr - 2) return false;
+    p.B = g->B; p.H = g->H; p.W = g->W; p.F = g->F; p.OH = g->OH; p.OW = g->OW; p.pt = g->pt; p.pl = g->pl;
+    p.PW = g->OW + 2;
+    p.KR = (g->OH * p.PW + 7) & ~7;
+    p.xs_rows = (p.KR + 2 * p.PW + 2 + 8 + 7) & ~7;
+    p.fr = g->F / 32;
+    if ((g->H + g->pt) * p.PW + g->pl > p.xs_rows) return false;
+    if (g->H * g->W * 8 > WG_TBX * WG_TR * 32 || g->OH * g->OW * 8 * p.fr > WG_TBD * WG_TR * 32) return false;
+    if (g->H > 256 || g->W > 256 || g->OH > 256 || g->OW > 256) return false;
+    // chunks fr..3 of the M=128 A operand alias the memory behind the dY buffers: it must exist
+    const size_t behind = 2 * (size_t)p.xs_rows * 128 + (size_t)g->H * g->W * 128 + (size_t)g->OH * g->OW * 128 * p.fr;
+    if ((size_t)(4 - p.fr) * p.KR * 128 > behind) return false;
+    return wgsv_smem(p) <= 225 * 1024;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+bool tc_conv_wgrad_sv_supported(const dnb_win_t* g) {
+    WgSvParams p{};
+    return get_encode_tiled() && !getenv("DNB_NO_WGSV") && wgsv_plan(g, p);
+}
+
+int tc_conv_wgrad_sv(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, cudaStream_t st) {
+    WgSvParams p{};
+    if (!wgsv_plan(g, p)) return set_err(DNB_ERR_UNSUPPORTED, "conv2d_bwd_weight(sv): unsupported shape");
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15))
+        return set_err(DNB_ERR_UNSUPPORTED, "conv2d_bwd_weight(sv): tensors must be 16-byte aligned");
+    p.gw = gw; p.gb = gb; p.inv_m = inv_m;
+    CUtensorMap tx, td;
+    uint64_t xd[4] = {(uint64_t)g->W, (uint64_t)g->H, 32, (uint64_t)g->B};
+    uint64_t xs[3] = {(uint64_t)g->W * 4, (uint64_t)g->W * g->H * 4, (uint64_t)g->W * g->H * 32 * 4};
+    uint32_t xb[4] = {(uint32_t)g->W, (uint32_t)g->H, 32, 1};
+    if (!make_tmap_f32(&tx, x, 4, xd, xs, xb, 2)) return set_err(DNB_ERR_CUDA, "conv2d_bwd_weight(sv): cuTensorMapEncodeTiled(x) failed");
+    uint64_t dd[4] = {(uint64_t)g->OW, (uint64_t)g->OH, (uint64_t)g->F, (uint64_t)g->B};
+    uint64_t ds[3] = {(uint64_t)g->OW * 4, (uint64_t)g->OW * g->OH * 4, (uint64_t)g->OW * g->OH * g->F * 4};
+    uint32_t dbx[4] = {(uint32_t)g->OW, (uint32_t)g->OH, 32, 1};
+    if (!make_tmap_f32(&td, dy, 4, dd, ds, dbx, 2)) return set_err(DNB_ERR_CUDA, "conv2d_bwd_weight(sv): cuTensorMapEncodeTiled(dy) failed");
+    const size_t smem = wgsv_smem(p);
+    cudaFuncSetAttribute(tc_conv_wgrad_sv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = std::min(g->B, kNumSMs);
+    tc_conv_wgrad_sv_kernel<<<grid, WGSV_THREADS, smem, st>>>(tx, td, p);
+    DNB_LAUNCH_CHECK("tc_conv2d_bwd_weight_sv");
+    return DNB_OK;
+}
+
+}  // namespace dnb
