@@ -41,6 +41,7 @@ struct SvParams {
     int region_rows;             // rows per 32-channel region of an image buffer: tiles*128 + (kh-1)*PW + kw (multiple of 8)
     int nkb;                     // kh*kw*(Cs/32)
     long units;                  // B * nbands
+    int flat;                    // source map is (H*W, C, B): a band of a channel is ONE contiguous row of the box
     float bias_k;
 };
 
@@ -141,8 +142,11 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 const int b = (int)(u / p.nbands), band = (int)(u % p.nbands);
                 const int y0 = band * p.TH - p.off_y;                     // may be negative / run past Hs: zero filled
                 mbar_arrive_expect_tx(&raw_full[s], box_bytes * cblks);
-                for (int cb = 0; cb < cblks; ++cb)
-                    tma_load_4d(sR + (size_t)s * raw_bytes + (size_t)cb * box_bytes, &tmX, 0, y0, cb * 32, b, &raw_full[s]);
+                for (int cb = 0; cb < cblks; ++cb) {
+                    void* dstp = sR + (size_t)s * raw_bytes + (size_t)cb * box_bytes;
+                    if (p.flat) tma_load_3d(dstp, &tmX, y0 * p.Ws, cb * 32, b, &raw_full[s]);
+                    else tma_load_4d(dstp, &tmX, 0, y0, cb * 32, b, &raw_full[s]);
+                }
             }
         }
     } else if (warp == SV_W_MMA) {
@@ -399,11 +403,23 @@ int tc_conv_sv_run(const char* name, const float* src, const float* wprep, int n
     uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)n_pad}, str[1] = {(uint64_t)Kp * 4};
     uint32_t box[2] = {32, (uint32_t)bn};
     if (!make_tmap_f32(&tw, wprep, 2, dims, str, box)) return set_err(DNB_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", name);
-    // source as (W, H, C, B); one box = a PH-row band of 32 channels, unswizzled, zero filled outside the image
-    uint64_t xd[4] = {(uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.Cs, (uint64_t)p.B};
-    uint64_t xs[3] = {(uint64_t)p.Ws * 4, (uint64_t)p.Ws * p.Hs * 4, (uint64_t)p.Ws * p.Hs * p.Cs * 4};
-    uint32_t xb[4] = {(uint32_t)p.Ws, (uint32_t)p.PH, 32, 1};
-    if (!make_tmap_f32(&tx, src, 4, xd, xs, xb, 2)) return set_err(DNB_ERR_CUDA, "%s: cuTensorMapEncodeTiled (source) failed", name);
+    // one box = a PH-row band of 32 channels, unswizzled, zero filled outside the image.  The rows of a band are
+    // contiguous in NCHW: when they fit a box row (<= 256 elements) the map is (H*W, C, B) and a channel's band is ONE
+    // contiguous box row (TMA moves 48-byte image rows an order of magnitude slower); otherwise (W, H, C, B).
+    p.flat = (p.PH * p.Ws <= 256) && !getenv("DNB_SV_NOFLAT");
+    bool ok;
+    if (p.flat) {
+        uint64_t xd[3] = {(uint64_t)p.Ws * p.Hs, (uint64_t)p.Cs, (uint64_t)p.B};
+        uint64_t xs[2] = {(uint64_t)p.Ws * p.Hs * 4, (uint64_t)p.Ws * p.Hs * p.Cs * 4};
+        uint32_t xb[3] = {(uint32_t)(p.PH * p.Ws), 32, 1};
+        ok = make_tmap_f32(&tx, src, 3, xd, xs, xb, 2);
+    } else {
+        uint64_t xd[4] = {(uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.Cs, (uint64_t)p.B};
+        uint64_t xs[3] = {(uint64_t)p.Ws * 4, (uint64_t)p.Ws * p.Hs * 4, (uint64_t)p.Ws * p.Hs * p.Cs * 4};
+        uint32_t xb[4] = {(uint32_t)p.Ws, (uint32_t)p.PH, 32, 1};
+        ok = make_tmap_f32(&tx, src, 4, xd, xs, xb, 2);
+    }
+    if (!ok) return set_err(DNB_ERR_CUDA, "%s: cuTensorMapEncodeTiled (source) failed", name);
     switch (bn) {
         case 16: return sv_launch<16>(name, tw, tx, p, st);
         case 32: return sv_launch<32>(name, tw, tx, p, st);

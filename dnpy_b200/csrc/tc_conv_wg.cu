@@ -29,9 +29,11 @@ struct WgSvParams {
     float* gw; float* gb;
     int B, H, W, F, OH, OW, pt, pl;
     int PW;                  // padded row pitch in pixels: OW + 2
-    int KR;                  // reduction rows per image: round_up(OH*PW, 8)
+    int TH, nbands;          // output rows per unit (band), bands per image
+    int KR;                  // reduction rows per unit: round_up(TH*PW, 8)
     int xs_rows;             // rows of one staged X buffer (padded image + tap/chunk overhang), multiple of 8
     int fr;                  // 32-filter regions of dY: F / 32
+    int flat;                // tensor maps are (H*W, C, B): a band of a channel is one contiguous box row
     float inv_m;
 };
 
@@ -60,6 +62,8 @@ __device__ __forceinline__ uint32_t sw32_off(int row, int q8) {
     return (uint32_t)row * 128 + ((((q8 >> 1) ^ (row & 3)) & 3) << 5) + ((q8 & 1) << 4);
 }
 
+// M64: F <= 64 -> M=64 MMAs (half the A-operand shared-memory traffic); D row r then lives in TMEM lane (r/16)*32 + r%16
+template <bool M64>
 __global__ void __launch_bounds__(WGSV_THREADS, 1)
 tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, WgSvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -67,22 +71,24 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     const uint32_t dreg_bytes = (uint32_t)p.KR * 128;                    // one 32-filter region of a dY buffer
     const uint32_t dbuf_bytes = dreg_bytes * p.fr;
     const uint32_t xbuf_bytes = (uint32_t)p.xs_rows * 128;
-    const uint32_t rawx_bytes = (uint32_t)p.H * p.W * 32 * 4, rawd_box = (uint32_t)p.OH * p.OW * 32 * 4;
+    const int XH = p.TH + 2;                                             // x rows of a band (with halo)
+    const uint32_t rawx_bytes = (uint32_t)XH * p.W * 32 * 4, rawd_box = (uint32_t)p.TH * p.OW * 32 * 4;
+    const uint32_t raw_bytes = rawx_bytes + rawd_box * p.fr;             // one raw stage: x band, then fr dY bands
     uint8_t* sD = smem;                                    // 2 x fr regions (A operand; chunks >= fr of the M=128 MMA alias what follows)
     uint8_t* sX = sD + 2 * (size_t)dbuf_bytes;             // 2 buffers (B operand)
-    uint8_t* sRx = sX + 2 * (size_t)xbuf_bytes;            // raw x image   [32][H][W]
-    uint8_t* sRd = sRx + rawx_bytes;                       // raw dY image  [F][OH][OW]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sRd + (size_t)rawd_box * p.fr);
-    uint64_t* raw_full = bars;         // tx
-    uint64_t* raw_empty = bars + 1;    // WG_TR
-    uint64_t* xd_full = bars + 2;      // [2] WG_TR
-    uint64_t* xd_empty = bars + 4;     // [2] commit
-    uint64_t* acc_full = bars + 6;     // commit
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-    float* s_gb = reinterpret_cast<float*>(bars + 8);      // [128]
+    uint8_t* sR = sX + 2 * (size_t)xbuf_bytes;             // 2 raw stages: x band [32][TH+2][W], dY band [F][TH][OW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + 2 * (size_t)raw_bytes);
+    uint64_t* raw_full = bars;         // [2] tx
+    uint64_t* raw_empty = bars + 2;    // [2] WG_TR
+    uint64_t* xd_full = bars + 4;      // [2] WG_TR
+    uint64_t* xd_empty = bars + 6;     // [2] commit
+    uint64_t* acc_full = bars + 8;     // commit
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* s_gb = reinterpret_cast<float*>(bars + 10);     // [128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-    const int nimg = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long units = (long)p.B * p.nbands;
+    const int nimg = (int)((units - (long)blockIdx.x + (long)gridDim.x - 1) / (long)gridDim.x);     // units of this CTA
 
     // zero the staged buffers once: pad ring / pad columns / overhang rows are never written afterwards
     for (uint32_t e = tid; e < (2 * dbuf_bytes + 2 * xbuf_bytes) / 16; e += WGSV_THREADS)
@@ -91,8 +97,10 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     if (tid == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmD);
-        mbar_init(raw_full, 1); mbar_init(raw_empty, WG_TR);
-        for (int s = 0; s < 2; ++s) { mbar_init(&xd_full[s], WG_TR); mbar_init(&xd_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], WG_TR);
+            mbar_init(&xd_full[s], WG_TR); mbar_init(&xd_empty[s], 1);
+        }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -110,16 +118,25 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         // ===================== TMA producer =====================
         if (elect_one()) {
             for (int n = 0; n < nimg; ++n) {
-                if (n >= 1) mbar_wait(raw_empty, (n - 1) & 1);
-                const int b = (int)blockIdx.x + n * (int)gridDim.x;
-                mbar_arrive_expect_tx(raw_full, rawx_bytes + rawd_box * p.fr);
-                wg_tma_load_4d(sRx, &tmX, 0, 0, 0, b, raw_full);
-                for (int r = 0; r < p.fr; ++r) wg_tma_load_4d(sRd + (size_t)r * rawd_box, &tmD, 0, 0, r * 32, b, raw_full);
+                const int s = n & 1;
+                if (n >= 2) mbar_wait(&raw_empty[s], ((n >> 1) - 1) & 1);
+                const long u = (long)blockIdx.x + (long)n * gridDim.x;
+                const int b = (int)(u / p.nbands), band = (int)(u % p.nbands);
+                uint8_t* rs = sR + (size_t)s * raw_bytes;
+                mbar_arrive_expect_tx(&raw_full[s], raw_bytes);
+                // x rows [band*TH - pt, +TH+2) and dY rows [band*TH, +TH): whatever falls outside the image is zero filled
+                if (p.flat) {
+                    tma_load_3d(rs, &tmX, (band * p.TH - p.pt) * p.W, 0, b, &raw_full[s]);
+                    for (int r = 0; r < p.fr; ++r) tma_load_3d(rs + rawx_bytes + (size_t)r * rawd_box, &tmD, band * p.TH * p.OW, r * 32, b, &raw_full[s]);
+                } else {
+                    wg_tma_load_4d(rs, &tmX, 0, band * p.TH - p.pt, 0, b, &raw_full[s]);
+                    for (int r = 0; r < p.fr; ++r) wg_tma_load_4d(rs + rawx_bytes + (size_t)r * rawd_box, &tmD, 0, band * p.TH, r * 32, b, &raw_full[s]);
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issue =====================
-        const uint32_t idesc = make_idesc_tf32(128, 96, 1, 1);
+        const uint32_t idesc = make_idesc_tf32(M64 ? 64 : 128, 96, 1, 1);
         const int ksteps = p.KR >> 3;
         const uint32_t pw8 = (uint32_t)p.PW * 8;
         for (int n = 0; n < nimg; ++n) {
@@ -147,7 +164,7 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         // ===================== transposers =====================
         const int ttid = tid - 64;
         constexpr int LT = WG_TR * 32;
-        const int npx_x = p.H * p.W, npx_d = p.OH * p.OW;
+        const int npx_x = XH * p.W, npx_d = p.TH * p.OW;
         const int tasks_x = npx_x * 8, tasks_d = npx_d * 8 * p.fr;
         const uint32_t chx = (uint32_t)npx_x * 4, chd = (uint32_t)npx_d * 4;        // bytes between channels of the raw images
         uint32_t xs_src[WG_TBX], xs_dst[WG_TBX], ds_src[WG_TBD], ds_dst[WG_TBD];
@@ -158,7 +175,7 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             if (t < tasks_x) {
                 const int pp = t % npx_x, quad = t / npx_x;
                 const int y = pp / p.W, x = pp - y * p.W;
-                const int row = (y + p.pt) * p.PW + x + p.pl;
+                const int row = y * p.PW + x + p.pl;            // band-local padded row (the halo / pad rows arrive zero filled)
                 xs_src[r] = (uint32_t)(quad * 4) * chx + (uint32_t)pp * 4;
                 xs_dst[r] = sw32_off(row, quad);
             }
@@ -178,11 +195,11 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         float gbs[WG_TBD][4];
 #pragma unroll
         for (int r = 0; r < WG_TBD; ++r) { gbs[r][0] = 0.f; gbs[r][1] = 0.f; gbs[r][2] = 0.f; gbs[r][3] = 0.f; }
-        const uint32_t rx = smem_u32(sRx), rd = smem_u32(sRd);
         for (int n = 0; n < nimg; ++n) {
             const int s = n & 1;
-            mbar_wait(raw_full, n & 1);
+            mbar_wait(&raw_full[s], (n >> 1) & 1);
             if (n >= 2) mbar_wait(&xd_empty[s], ((n >> 1) - 1) & 1);
+            const uint32_t rx = smem_u32(sR + (size_t)s * raw_bytes), rd = rx + rawx_bytes;
             const uint32_t xb = smem_u32(sX + (size_t)s * xbuf_bytes), db = smem_u32(sD + (size_t)s * dbuf_bytes);
 #pragma unroll
             for (int r0 = 0; r0 < WG_TBX; r0 += 3) {
@@ -215,7 +232,7 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&xd_full[s]); mbar_arrive(raw_empty); }
+            if (lane == 0) { mbar_arrive(&xd_full[s]); mbar_arrive(&raw_empty[s]); }
         }
         // ---- bias gradient: per-slot sums -> shared -> global
         if (p.gb) {
@@ -236,8 +253,8 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             mbar_wait(acc_full, 0);
             tc_fence_after();
             const int q = warp & 3, half = (warp - 2) >> 2;           // lane quadrant, column half (144 columns each)
-            const int f = q * 32 + lane;
-            if (q * 32 < p.F) {
+            const int f = M64 ? (lane < 16 ? q * 16 + lane : p.F) : q * 32 + lane;
+            if (M64 || q * 32 < p.F) {
 #pragma unroll 1
                 for (int c0 = half * 144; c0 < half * 144 + 144; c0 += 16) {
                     uint32_t v[16];
@@ -260,9 +277,9 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+static size_t wgsv_raw(const WgSvParams& p) { return (size_t)(p.TH + 2) * p.W * 32 * 4 + (size_t)p.TH * p.OW * 32 * 4 * p.fr; }
 static size_t wgsv_smem(const WgSvParams& p) {
-    return 2 * (size_t)p.KR * 128 * p.fr + 2 * (size_t)p.xs_rows * 128 + (size_t)p.H * p.W * 32 * 4 +
-           (size_t)p.OH * p.OW * 32 * 4 * p.fr + 64 + 128 * 4 + 1024;
+    return 2 * (size_t)p.KR * 128 * p.fr + 2 * (size_t)p.xs_rows * 128 + 2 * wgsv_raw(p) + 128 + 128 * 4 + 1024;
 }
 
 static bool wgsv_plan(const dnb_win_t* g, WgSvParams& p) {
@@ -271,16 +288,22 @@ static bool wgsv_plan(const dnb_win_t* g, WgSvParams& p) {
     if (g->OH != g->H + g->pt + g->pb - 2 || g->OW != g->W + g->pl + g->pr - 2) return false;
     p.B = g->B; p.H = g->H; p.W = g->W; p.F = g->F; p.OH = g->OH; p.OW = g->OW; p.pt = g->pt; p.pl = g->pl;
     p.PW = g->OW + 2;
-    p.KR = (g->OH * p.PW + 7) & ~7;
-    p.xs_rows = (p.KR + 2 * p.PW + 2 + 8 + 7) & ~7;
     p.fr = g->F / 32;
-    if ((g->H + g->pt) * p.PW + g->pl > p.xs_rows) return false;
-    if (g->H * g->W * 8 > WG_TBX * WG_TR * 32 || g->OH * g->OW * 8 * p.fr > WG_TBD * WG_TR * 32) return false;
-    if (g->H > 256 || g->W > 256 || g->OH > 256 || g->OW > 256) return false;
-    // chunks fr..3 of the M=128 A operand alias the memory behind the dY buffers: it must exist
-    const size_t behind = 2 * (size_t)p.xs_rows * 128 + (size_t)g->H * g->W * 128 + (size_t)g->OH * g->OW * 128 * p.fr;
-    if ((size_t)(4 - p.fr) * p.KR * 128 > behind) return false;
-    return wgsv_smem(p) <= 225 * 1024;
+    if (g->W > 256 || g->OW > 256) return false;
+    // tallest band (fewest units, least halo) whose double-buffered staging fits
+    for (int th = g->OH; th >= 1; --th) {
+        p.TH = th; p.nbands = (g->OH + th - 1) / th;
+        if (p.nbands > 1 && th * p.nbands - g->OH >= th / 2 + 1) continue;          // badly unbalanced last band
+        p.KR = (th * p.PW + 7) & ~7;
+        p.xs_rows = (p.KR + 2 * p.PW + 2 + 8 + 7) & ~7;
+        if ((th + 2) * p.PW > p.xs_rows || th + 2 > 256) continue;
+        if ((th + 2) * g->W * 8 > WG_TBX * WG_TR * 32 || th * g->OW * 8 * p.fr > WG_TBD * WG_TR * 32) continue;
+        // chunks fr.. of the A operand (M=128: 4 chunks, M=64: 2) alias the memory behind the dY buffers: it must exist
+        const size_t behind = 2 * (size_t)p.xs_rows * 128 + 2 * wgsv_raw(p);
+        if ((size_t)3 * p.KR * 128 > behind) continue;
+        if (wgsv_smem(p) <= 225 * 1024) return true;
+    }
+    return false;
 }
 
 }  // namespace tc
@@ -299,18 +322,38 @@ int tc_conv_wgrad_sv(const float* x, const float* dy, float* gw, float* gb, cons
         return set_err(DNB_ERR_UNSUPPORTED, "conv2d_bwd_weight(sv): tensors must be 16-byte aligned");
     p.gw = gw; p.gb = gb; p.inv_m = inv_m;
     CUtensorMap tx, td;
-    uint64_t xd[4] = {(uint64_t)g->W, (uint64_t)g->H, 32, (uint64_t)g->B};
-    uint64_t xs[3] = {(uint64_t)g->W * 4, (uint64_t)g->W * g->H * 4, (uint64_t)g->W * g->H * 32 * 4};
-    uint32_t xb[4] = {(uint32_t)g->W, (uint32_t)g->H, 32, 1};
-    if (!make_tmap_f32(&tx, x, 4, xd, xs, xb, 2)) return set_err(DNB_ERR_CUDA, "conv2d_bwd_weight(sv): cuTensorMapEncodeTiled(x) failed");
-    uint64_t dd[4] = {(uint64_t)g->OW, (uint64_t)g->OH, (uint64_t)g->F, (uint64_t)g->B};
-    uint64_t ds[3] = {(uint64_t)g->OW * 4, (uint64_t)g->OW * g->OH * 4, (uint64_t)g->OW * g->OH * g->F * 4};
-    uint32_t dbx[4] = {(uint32_t)g->OW, (uint32_t)g->OH, 32, 1};
-    if (!make_tmap_f32(&td, dy, 4, dd, ds, dbx, 2)) return set_err(DNB_ERR_CUDA, "conv2d_bwd_weight(sv): cuTensorMapEncodeTiled(dy) failed");
+    p.flat = ((p.TH + 2) * g->W <= 256 && p.TH * g->OW <= 256) && !getenv("DNB_SV_NOFLAT");
+    bool ok1, ok2;
+    if (p.flat) {
+        // a band of a channel is contiguous in NCHW: maps over (H*W, C, B), one contiguous box row per channel
+        uint64_t xd[3] = {(uint64_t)g->W * g->H, 32, (uint64_t)g->B};
+        uint64_t xs[2] = {(uint64_t)g->W * g->H * 4, (uint64_t)g->W * g->H * 32 * 4};
+        uint32_t xb[3] = {(uint32_t)((p.TH + 2) * g->W), 32, 1};
+        ok1 = make_tmap_f32(&tx, x, 3, xd, xs, xb, 2);
+        uint64_t dd[3] = {(uint64_t)g->OW * g->OH, (uint64_t)g->F, (uint64_t)g->B};
+        uint64_t ds[2] = {(uint64_t)g->OW * g->OH * 4, (uint64_t)g->OW * g->OH * g->F * 4};
+        uint32_t dbx[3] = {(uint32_t)(p.TH * g->OW), 32, 1};
+        ok2 = make_tmap_f32(&td, dy, 3, dd, ds, dbx, 2);
+    } else {
+        uint64_t xd[4] = {(uint64_t)g->W, (uint64_t)g->H, 32, (uint64_t)g->B};
+        uint64_t xs[3] = {(uint64_t)g->W * 4, (uint64_t)g->W * g->H * 4, (uint64_t)g->W * g->H * 32 * 4};
+        uint32_t xb[4] = {(uint32_t)g->W, (uint32_t)(p.TH + 2), 32, 1};
+        ok1 = make_tmap_f32(&tx, x, 4, xd, xs, xb, 2);
+        uint64_t dd[4] = {(uint64_t)g->OW, (uint64_t)g->OH, (uint64_t)g->F, (uint64_t)g->B};
+        uint64_t ds[3] = {(uint64_t)g->OW * 4, (uint64_t)g->OW * g->OH * 4, (uint64_t)g->OW * g->OH * g->F * 4};
+        uint32_t dbx[4] = {(uint32_t)g->OW, (uint32_t)p.TH, 32, 1};
+        ok2 = make_tmap_f32(&td, dy, 4, dd, ds, dbx, 2);
+    }
+    if (!ok1 || !ok2) return set_err(DNB_ERR_CUDA, "conv2d_bwd_weight(sv): cuTensorMapEncodeTiled failed");
     const size_t smem = wgsv_smem(p);
-    cudaFuncSetAttribute(tc_conv_wgrad_sv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int grid = std::min(g->B, kNumSMs);
-    tc_conv_wgrad_sv_kernel<<<grid, WGSV_THREADS, smem, st>>>(tx, td, p);
+    const int grid = (int)std::min<long>((long)g->B * p.nbands, kNumSMs);
+    if (g->F <= 64 && !getenv("DNB_WGSV_M128")) {
+        cudaFuncSetAttribute(tc_conv_wgrad_sv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc_conv_wgrad_sv_kernel<true><<<grid, WGSV_THREADS, smem, st>>>(tx, td, p);
+    } else {
+        cudaFuncSetAttribute(tc_conv_wgrad_sv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc_conv_wgrad_sv_kernel<false><<<grid, WGSV_THREADS, smem, st>>>(tx, td, p);
+    }
     DNB_LAUNCH_CHECK("tc_conv2d_bwd_weight_sv");
     return DNB_OK;
 }
