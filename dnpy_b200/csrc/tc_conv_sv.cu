@@ -12,6 +12,14 @@
 //   M index  m = oy*PW + ox   (columns ox >= OW / rows oy >= TH are garbage, never stored)
 //   A(tap,cb) = region[cb] rows [m0 + i*PW + j, +128)        B(tap,cb) = filters [BN x 32], resident in smem
 //
+// Column-tap folding (JF, 3x3 kernels, padded pitch PW = 16 or 32, BN <= 64): the kernel is bound by the shared-memory
+// traffic of the A operand, which every tap re-reads.  With JF the three column taps j of a kernel row are folded into
+// the N extent instead: ONE MMA per (i, 32-channel block, k-step) computes E_j[m][f] = sum_c X[m + i*PW][c] W[f][c][i][j]
+// for j = 0,1,2 (N = 3*BN; the three filter blocks are contiguous in shared memory) and the epilogue adds the row-shifted
+// blocks y[m] = E_0[m] + E_1[m+1] + E_2[m+2] with two warp shuffles per value.  Because PW divides 32, the rows m whose
+// m+1 / m+2 fall into the next TMEM lane quadrant are exactly the garbage columns ox >= PW-2: nothing is lost.
+// A 3x less often read A operand; the tail tile of a unit uses M=64.
+//
 // Persistent, warp-specialised CTA (1 per SM), every stage decoupled by mbarriers:
 //   warp 0      TMA producer: the raw NCHW band [32 c][PH rows][W] of a unit per 32-channel block (4-D tiled
 //               tensor map, rows outside the image zero-filled by the hardware), double buffered; global
@@ -37,7 +45,8 @@ struct SvParams {
     int off_y, off_x;            // placement of the source inside the padded plane
     int TH, nbands;              // output rows per band, bands per image
     int PH, PW;                  // padded band: TH + kh - 1, Wd + kw - 1
-    int tiles;                   // ceil(TH*PW / 128)
+    int tiles;                   // M tiles per unit
+    int last64;                  // the last tile of a unit is an M=64 MMA (<= 64 rows left)
     int region_rows;             // rows per 32-channel region of an image buffer: tiles*128 + (kh-1)*PW + kw (multiple of 8)
     int nkb;                     // kh*kw*(Cs/32)
     long units;                  // B * nbands
@@ -78,12 +87,15 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NC]) 
     }
 }
 
-template <int BN, bool K33, int CB>
+template <int BN, bool K33, int CB, bool JF>
 __global__ void __launch_bounds__(SV_THREADS, 1)
 tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, SvParams p) {
-    constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    constexpr int ACC = JF ? 3 * BN : BN;                 // TMEM columns of one accumulator stage
+    constexpr uint32_t TMEM_COLS = (2 * ACC <= 32) ? 32 : (2 * ACC <= 64) ? 64 : (2 * ACC <= 128) ? 128 : (2 * ACC <= 256) ? 256 : 512;
+    static_assert(2 * ACC <= 512, "two accumulator stages must fit TMEM");
+    static_assert(!JF || (K33 && CB > 0), "column-tap folding is a 3x3 specialisation");
     constexpr int W_KB = BN * 128;                        // bytes of one K block of filters
-    constexpr int NC = BN >= 64 ? 32 : BN / 2;            // TMEM columns per epilogue pass
+    constexpr int NC = JF ? (BN >= 32 ? 16 : BN / 2) : (BN >= 64 ? 32 : BN / 2);      // TMEM columns per epilogue pass
     constexpr int NPASS = BN / 2 / NC;                    // passes per epilogue warp (its half of the BN columns)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -153,11 +165,16 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // ===================== filter TMA (once) + MMA issue =====================
         if (elect_one()) {
             mbar_arrive_expect_tx(w_full, (uint32_t)(p.nkb * W_KB));
-            for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(sW + (size_t)kb * W_KB, &tmW, kb * 32, 0, w_full);
+            // global K order is (tap, channel block); JF keeps the three j blocks of an (i, cb) contiguous: slot (i*CB+cb)*3 + j
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                int slot = kb;
+                if (JF) { const int tap = kb / CB, cb = kb - tap * CB; slot = ((tap / 3) * CB + cb) * 3 + tap % 3; }
+                tma_load_2d(sW + (size_t)slot * W_KB, &tmW, kb * 32, 0, w_full);
+            }
         }
         __syncwarp();
         mbar_wait(w_full, 0);
-        const uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
+        const uint32_t idesc = make_idesc_tf32(128, ACC, 0, 0), idesc64 = make_idesc_tf32(64, ACC, 0, 0);
         const uint64_t w_d0 = make_smem_desc(smem_u32(sW), 16, 1024);
         const uint32_t pw8 = (uint32_t)p.PW * 8, region16 = region_bytes >> 4;
         int it = 0, tcount = 0;
@@ -169,13 +186,26 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             for (int t = 0; t < p.tiles; ++t, ++tcount) {
                 const int as = tcount & 1;
                 if (tcount >= 2) { mbar_wait(&acc_empty[as], ((tcount >> 1) - 1) & 1); tc_fence_after(); }
-                const uint32_t d_t = tmem_base + as * BN;
+                const uint32_t d_t = tmem_base + as * ACC;
+                const uint32_t idc = (p.last64 && t == p.tiles - 1) ? idesc64 : idesc;
                 // descriptor address fields only ever grow by < 256 KB >> 4: a plain 64-bit add never carries out
                 const uint64_t a_t = x_d0 + (uint64_t)((uint32_t)t * (128 * 8));
                 // ONE elected-thread region per tile (ptxas keeps the operands in uniform registers only when the
                 // branch is on the elect itself); inside it the 3x3 case is a straight line of MMAs
                 if (elect_one()) {
-                    if (K33 && CB > 0) {
+                    if (JF) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int cb = 0; cb < CB; ++cb) {
+                                const uint64_t a = a_t + (uint64_t)((uint32_t)i * pw8) + (uint64_t)((uint32_t)cb * region16);
+                                const uint64_t bw = w_d0 + (uint64_t)((i * CB + cb) * 3 * (W_KB >> 4));
+                                if (i == 0 && cb == 0) mma_tf32_init(d_t, a, bw, idc); else mma_tf32_acc(d_t, a, bw, idc);
+                                mma_tf32_acc(d_t, a + 2, bw + 2, idc);
+                                mma_tf32_acc(d_t, a + 4, bw + 4, idc);
+                                mma_tf32_acc(d_t, a + 6, bw + 6, idc);
+                            }
+                    } else if (K33 && CB > 0) {
 #pragma unroll
                         for (int i = 0; i < 3; ++i) {
                             const uint64_t a_i = a_t + (uint64_t)((uint32_t)i * pw8);
@@ -186,10 +216,10 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                                     const int kb = (i * 3 + j) * CB + cb;
                                     const uint64_t a = a_i + (uint64_t)(j * 8) + (uint64_t)((uint32_t)cb * region16);
                                     const uint64_t bw = w_d0 + (uint64_t)(kb * (W_KB >> 4));
-                                    if (kb == 0) mma_tf32_init(d_t, a, bw, idesc); else mma_tf32_acc(d_t, a, bw, idesc);
-                                    mma_tf32_acc(d_t, a + 2, bw + 2, idesc);
-                                    mma_tf32_acc(d_t, a + 4, bw + 4, idesc);
-                                    mma_tf32_acc(d_t, a + 6, bw + 6, idesc);
+                                    if (kb == 0) mma_tf32_init(d_t, a, bw, idc); else mma_tf32_acc(d_t, a, bw, idc);
+                                    mma_tf32_acc(d_t, a + 2, bw + 2, idc);
+                                    mma_tf32_acc(d_t, a + 4, bw + 4, idc);
+                                    mma_tf32_acc(d_t, a + 6, bw + 6, idc);
                                 }
                         }
                     } else {
@@ -200,10 +230,10 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                                 for (int cb = 0; cb < cblks; ++cb, ++kb) {
                                     const uint64_t a = a_ij + (uint64_t)((uint32_t)cb * region16);
                                     const uint64_t bw = w_d0 + (uint64_t)(kb * (W_KB >> 4));
-                                    if (kb == 0) mma_tf32_init(d_t, a, bw, idesc); else mma_tf32_acc(d_t, a, bw, idesc);
-                                    mma_tf32_acc(d_t, a + 2, bw + 2, idesc);
-                                    mma_tf32_acc(d_t, a + 4, bw + 4, idesc);
-                                    mma_tf32_acc(d_t, a + 6, bw + 6, idesc);
+                                    if (kb == 0) mma_tf32_init(d_t, a, bw, idc); else mma_tf32_acc(d_t, a, bw, idc);
+                                    mma_tf32_acc(d_t, a + 2, bw + 2, idc);
+                                    mma_tf32_acc(d_t, a + 4, bw + 4, idc);
+                                    mma_tf32_acc(d_t, a + 6, bw + 6, idc);
                                 }
                             }
                     }
@@ -272,34 +302,54 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const int b = (int)(u / p.nbands), band = (int)(u % p.nbands);
             for (int t = 0; t < p.tiles; ++t, ++tcount) {
                 const int as = tcount & 1;
-                const int m = t * 128 + q * 32 + lane;
+                // M=128 tile: D row r = TMEM lane r; M=64 tile: row r = lane (r/16)*32 + r%16 (16 rows per quadrant)
+                const bool t64 = p.last64 && t == p.tiles - 1;
+                const int m = t * 128 + (t64 ? q * 16 + lane : q * 32 + lane);
                 const int oy = m / p.PW, ox = m - oy * p.PW;
                 const int y = band * p.TH + oy;
-                const bool valid = oy < p.TH && y < p.Hd && ox < p.Wd;
+                const bool valid = (!t64 || lane < 16) && oy < p.TH && y < p.Hd && ox < p.Wd;
                 float* dp = p.dst + ((size_t)b * p.Cd) * plane_d + (valid ? (size_t)y * p.Wd + ox : 0);
                 mbar_wait(&acc_full[as], (tcount >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int ps = 0; ps < NPASS; ++ps) {
                     const int c0 = half * (BN / 2) + ps * NC;
+                    const uint32_t tad = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC + c0);
                     uint32_t v[NC];
-                    tmem_ld_cols<NC>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
+                    tmem_ld_cols<NC>(tad, v);
                     float bv[NC];                           // K*bias of these channels: broadcast LDS.128 under the TMEM load
 #pragma unroll
                     for (int j4 = 0; j4 < NC / 4; ++j4) {
                         const float4 b4 = lds128_ro(s_bias_u32 + (uint32_t)(c0 + 4 * j4) * 4);
                         bv[4 * j4] = b4.x; bv[4 * j4 + 1] = b4.y; bv[4 * j4 + 2] = b4.z; bv[4 * j4 + 3] = b4.w;
                     }
-                    tmem_ld_wait();
+                    if (JF) {
+                        // y[m] = E_0[m] + E_1[m+1] + E_2[m+2]: the partner rows sit one / two lanes up (same quadrant for every
+                        // row that is stored: PW divides 32, the lanes that would cross are the garbage columns)
+                        uint32_t v1[NC], v2[NC];
+                        tmem_ld_cols<NC>(tad + BN, v1);
+                        tmem_ld_cols<NC>(tad + 2 * BN, v2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < NC; ++j) {
+                            const float e1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[j]), 1);
+                            const float e2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 2);
+                            bv[j] += (__uint_as_float(v[j]) + e1) + e2;
+                        }
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < NC; ++j) bv[j] += __uint_as_float(v[j]);
+                    }
                     if (valid) {
                         float* o = dp + (size_t)c0 * plane_d;
                         if (c0 + NC <= p.Cd) {
 #pragma unroll
-                            for (int j = 0; j < NC; ++j) { *o = __uint_as_float(v[j]) + bv[j]; o += plane_d; }
+                            for (int j = 0; j < NC; ++j) { *o = bv[j]; o += plane_d; }
                         } else {
 #pragma unroll
                             for (int j = 0; j < NC; ++j)
-                                if (c0 + j < p.Cd) { *o = __uint_as_float(v[j]) + bv[j]; o += plane_d; }
+                                if (c0 + j < p.Cd) { *o = bv[j]; o += plane_d; }
                         }
                     }
                 }
@@ -322,48 +372,64 @@ static size_t sv_smem_bytes(const SvParams& p, int bn) {
     return (size_t)p.nkb * bn * 128 + 2 * buf + 2 * raw + 128 + (size_t)(bn < 32 ? 32 : bn) * 4 + 1024;
 }
 
-// choose the band height: fewest 128-row MMA tiles per image that fit in 227 KB (ties -> the taller band: less halo)
+// column-tap folding applies to 3x3 kernels whose padded row fits a pitch that divides 32, with 3*BN*2 <= 512 TMEM columns
+static bool sv_jfold(const SvParams& p, int bn) {
+    return p.kh == 3 && p.kw == 3 && (p.Cs == 32 || p.Cs == 64) && bn <= 64 && p.Wd + 2 <= 32 && !getenv("DNB_SV_NOJF");
+}
+
+// choose the band height: fewest MMA tile-halves per image that fit in 227 KB (ties -> the taller band: less halo)
 static bool sv_plan(SvParams& p, int bn) {
-    p.PW = p.Wd + p.kw - 1;
+    const bool jf = sv_jfold(p, bn);
+    p.PW = jf ? (p.Wd + 2 <= 16 ? 16 : 32) : p.Wd + p.kw - 1;
     p.nkb = p.kh * p.kw * (p.Cs / 32);
     const size_t budget = 225 * 1024;
-    long best_tiles = -1; int best_th = 0;
+    long best_cost = -1; int best_th = 0;
+    auto shape = [&](SvParams& q, int th) {
+        q.TH = th; q.nbands = (p.Hd + th - 1) / th; q.PH = th + p.kh - 1;
+        const int rows = th * q.PW;
+        q.tiles = (rows + 127) / 128;
+        // an M=64 tail tile keeps 16 rows per lane quadrant: with folding its rows 14,15 (mod 16) must be garbage columns
+        q.last64 = (rows - (q.tiles - 1) * 128) <= 64 && !(jf && q.PW != 16);
+        q.region_rows = (q.tiles * 128 + (p.kh - 1) * q.PW + p.kw + 7) & ~7;
+    };
     for (int th = p.Hd; th >= 1; --th) {
         SvParams q = p;
-        q.TH = th; q.nbands = (p.Hd + th - 1) / th; q.PH = th + p.kh - 1;
-        q.tiles = (th * q.PW + 127) / 128;
-        q.region_rows = (q.tiles * 128 + (p.kh - 1) * q.PW + p.kw + 7) & ~7;
+        shape(q, th);
         if (q.PH > 256 || p.Ws > 256) continue;                                            // TMA box limits
         if ((long)q.PH * p.Ws * 8 * (p.Cs / 32) > (long)SV_TB * SV_TR * 32) continue;      // transposer task table
         if (sv_smem_bytes(q, bn) > budget) continue;
-        const long tiles_img = (long)q.nbands * q.tiles;
-        if (best_tiles < 0 || tiles_img < best_tiles) { best_tiles = tiles_img; best_th = th; }
+        const long cost = (long)q.nbands * (2 * q.tiles - q.last64);                       // in units of 64 MMA rows
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_th = th; }
     }
     if (!best_th) return false;
-    p.TH = best_th; p.nbands = (p.Hd + best_th - 1) / best_th; p.PH = best_th + p.kh - 1;
-    p.tiles = (best_th * p.PW + 127) / 128;
-    p.region_rows = (p.tiles * 128 + (p.kh - 1) * p.PW + p.kw + 7) & ~7;
+    shape(p, best_th);
     p.units = (long)p.B * p.nbands;
     return true;
 }
 
 static int pick_bn_sv(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128)); }
 
-template <int BN, bool K33, int CB>
+template <int BN, bool K33, int CB, bool JF>
 static int sv_launch_k(const char* name, const CUtensorMap& tw, const CUtensorMap& tx, const SvParams& p, cudaStream_t st) {
     const size_t smem = sv_smem_bytes(p, BN);
-    cudaFuncSetAttribute(tc_conv_sv_kernel<BN, K33, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(tc_conv_sv_kernel<BN, K33, CB, JF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = (int)std::min<long>(p.units, kNumSMs);
-    tc_conv_sv_kernel<BN, K33, CB><<<grid, SV_THREADS, smem, st>>>(tw, tx, p);
+    tc_conv_sv_kernel<BN, K33, CB, JF><<<grid, SV_THREADS, smem, st>>>(tw, tx, p);
     DNB_LAUNCH_CHECK(name);
     return DNB_OK;
 }
 
 template <int BN>
 static int sv_launch(const char* name, const CUtensorMap& tw, const CUtensorMap& tx, const SvParams& p, cudaStream_t st) {
-    if (p.kh == 3 && p.kw == 3 && p.Cs == 32) return sv_launch_k<BN, true, 1>(name, tw, tx, p, st);
-    if (p.kh == 3 && p.kw == 3 && p.Cs == 64) return sv_launch_k<BN, true, 2>(name, tw, tx, p, st);
-    return sv_launch_k<BN, false, 0>(name, tw, tx, p, st);
+    if constexpr (BN <= 64) {
+        if (sv_jfold(p, BN)) {
+            if (p.Cs == 32) return sv_launch_k<BN, true, 1, true>(name, tw, tx, p, st);
+            return sv_launch_k<BN, true, 2, true>(name, tw, tx, p, st);
+        }
+    }
+    if (p.kh == 3 && p.kw == 3 && p.Cs == 32) return sv_launch_k<BN, true, 1, false>(name, tw, tx, p, st);
+    if (p.kh == 3 && p.kw == 3 && p.Cs == 64) return sv_launch_k<BN, true, 2, false>(name, tw, tx, p, st);
+    return sv_launch_k<BN, false, 0, false>(name, tw, tx, p, st);
 }
 
 }  // namespace tc

@@ -1,3 +1,3 @@
-python scratch/prof_step.py > gpurun_out/prof_step_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/step_times.csv python scratch/prof_step.py > gpurun_out/ncu_step.log 2>&1
-tail -2 gpurun_out/ncu_step.log
+python scratch/sv_bench.py 0 > gpurun_out/svb_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"tc_conv_sv_kernel|wgrad_sv" -c 6 -o gpurun_out/prof_sv2_r01 -f python scratch/sv_bench.py 0 > gpurun_out/ncu_sv2.log 2>&1
+tail -2 gpurun_out/ncu_sv2.log
