@@ -50,7 +50,9 @@ struct SvParams {
     int region_rows;             // rows per 32-channel region of an image buffer: tiles*128 + (kh-1)*PW + kw (multiple of 8)
     int nkb;                     // kh*kw*(Cs/32)
     long units;                  // B * nbands
+    int nraw;                    // raw TMA stages in flight (2..4): as many as fit, the loads are latency bound
     int flat;                    // source map is (H*W, C, B): a band of a channel is ONE contiguous row of the box
+    int debug;                   // timing experiments (DNB_SV_DEBUG): 1 no stores, 2 no MMAs, 4 no row-shift shuffles, 8 no transposition
     float bias_k;
 };
 
@@ -106,17 +108,17 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const uint32_t raw_bytes = ((box_bytes * cblks + 127) / 128) * 128;
     uint8_t* sW = smem;                                    // [nkb][BN x 128 B]
     uint8_t* sX = sW + (size_t)p.nkb * W_KB;               // 2 buffers x cblks regions (swizzled NHWC)
-    uint8_t* sR = sX + 2 * (size_t)buf_bytes;              // 2 raw NCHW bands
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + 2 * (size_t)raw_bytes);
+    uint8_t* sR = sX + 2 * (size_t)buf_bytes;              // nraw raw NCHW bands
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (size_t)p.nraw * raw_bytes);
     uint64_t* w_full = bars;
-    uint64_t* raw_full = bars + 1;     // [2]
-    uint64_t* raw_empty = bars + 3;    // [2]
-    uint64_t* x_full = bars + 5;       // [2]
-    uint64_t* x_empty = bars + 7;      // [2]
-    uint64_t* acc_full = bars + 9;     // [2]
-    uint64_t* acc_empty = bars + 11;   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-    float* s_bias = reinterpret_cast<float*>(bars + 14);   // [max(BN,32)]  K*bias (0 without a bias)
+    uint64_t* raw_full = bars + 1;     // [4]
+    uint64_t* raw_empty = bars + 5;    // [4]
+    uint64_t* x_full = bars + 9;       // [2]
+    uint64_t* x_empty = bars + 11;     // [2]
+    uint64_t* acc_full = bars + 13;    // [2]
+    uint64_t* acc_empty = bars + 15;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    float* s_bias = reinterpret_cast<float*>(bars + 18);   // [max(BN,32)]  K*bias (0 without a bias)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
 
@@ -127,8 +129,8 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmX);
         mbar_init(w_full, 1);
+        for (int s = 0; s < 4; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], SV_TR); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], SV_TR);
             mbar_init(&x_full[s], SV_TR); mbar_init(&x_empty[s], 1);
             mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], SV_EPI);
         }
@@ -147,18 +149,18 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     if (warp == SV_W_TMA) {
         // ===================== TMA producer: raw NCHW band of every unit =====================
         if (elect_one()) {
-            int it = 0;
+            int it = 0, rs = 0, rph = 0;                              // raw stage and its phase parity
             for (long u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
-                const int s = it & 1;
-                if (it >= 2) mbar_wait(&raw_empty[s], ((it >> 1) - 1) & 1);
+                if (it >= p.nraw) mbar_wait(&raw_empty[rs], rph ^ 1);
                 const int b = (int)(u / p.nbands), band = (int)(u % p.nbands);
                 const int y0 = band * p.TH - p.off_y;                     // may be negative / run past Hs: zero filled
-                mbar_arrive_expect_tx(&raw_full[s], box_bytes * cblks);
+                mbar_arrive_expect_tx(&raw_full[rs], box_bytes * cblks);
                 for (int cb = 0; cb < cblks; ++cb) {
-                    void* dstp = sR + (size_t)s * raw_bytes + (size_t)cb * box_bytes;
-                    if (p.flat) tma_load_3d(dstp, &tmX, y0 * p.Ws, cb * 32, b, &raw_full[s]);
-                    else tma_load_4d(dstp, &tmX, 0, y0, cb * 32, b, &raw_full[s]);
+                    void* dstp = sR + (size_t)rs * raw_bytes + (size_t)cb * box_bytes;
+                    if (p.flat) tma_load_3d(dstp, &tmX, y0 * p.Ws, cb * 32, b, &raw_full[rs]);
+                    else tma_load_4d(dstp, &tmX, 0, y0, cb * 32, b, &raw_full[rs]);
                 }
+                if (++rs == p.nraw) { rs = 0; rph ^= 1; }
             }
         }
     } else if (warp == SV_W_MMA) {
@@ -193,7 +195,8 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 // ONE elected-thread region per tile (ptxas keeps the operands in uniform registers only when the
                 // branch is on the elect itself); inside it the 3x3 case is a straight line of MMAs
                 if (elect_one()) {
-                    if (JF) {
+                    if (p.debug & 2) {
+                    } else if (JF) {
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -267,12 +270,13 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 t_dst[r] = (uint32_t)cb * region_bytes + (uint32_t)row * 128 + (((quad ^ (row & 7)) & 7) << 4);
             }
         }
-        int it = 0;
+        int it = 0, rs = 0, rph = 0;
         for (long u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
             const int s = it & 1;
-            mbar_wait(&raw_full[s], (it >> 1) & 1);
+            mbar_wait(&raw_full[rs], rph);
             if (it >= 2) mbar_wait(&x_empty[s], ((it >> 1) - 1) & 1);
-            const uint32_t raw_s = smem_u32(sR + (size_t)s * raw_bytes), buf_s = smem_u32(sX + (size_t)s * buf_bytes);
+            const uint32_t raw_s = smem_u32(sR + (size_t)rs * raw_bytes), buf_s = smem_u32(sX + (size_t)s * buf_bytes);
+            if (!(p.debug & 8))
 #pragma unroll
             for (int r0 = 0; r0 < SV_TB; r0 += 4) {               // 16 loads in flight, then 4 stores
                 float4 v[4];
@@ -289,7 +293,8 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&x_full[s]); mbar_arrive(&raw_empty[s]); }
+            if (lane == 0) { mbar_arrive(&x_full[s]); mbar_arrive(&raw_empty[rs]); }
+            if (++rs == p.nraw) { rs = 0; rph ^= 1; }
         }
     } else {
         // ===================== epilogue: TMEM -> NCHW global (8 warps: lane quadrant x column half) =====================
@@ -330,18 +335,23 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         tmem_ld_cols<NC>(tad + BN, v1);
                         tmem_ld_cols<NC>(tad + 2 * BN, v2);
                         tmem_ld_wait();
+                        if (p.debug & 4) {
+#pragma unroll
+                            for (int j = 0; j < NC; ++j) bv[j] += (__uint_as_float(v[j]) + __uint_as_float(v1[j])) + __uint_as_float(v2[j]);
+                        } else {
 #pragma unroll
                         for (int j = 0; j < NC; ++j) {
                             const float e1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[j]), 1);
                             const float e2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 2);
                             bv[j] += (__uint_as_float(v[j]) + e1) + e2;
                         }
+                        }
                     } else {
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < NC; ++j) bv[j] += __uint_as_float(v[j]);
                     }
-                    if (valid) {
+                    if (valid && !(p.debug & 1)) {
                         float* o = dp + (size_t)c0 * plane_d;
                         if (c0 + NC <= p.Cd) {
 #pragma unroll
@@ -369,7 +379,7 @@ static size_t sv_smem_bytes(const SvParams& p, int bn) {
     const size_t region = (size_t)p.region_rows * 128;
     const size_t buf = ((region * cblks + 1023) / 1024) * 1024;
     const size_t raw = (((size_t)p.Ws * p.PH * 32 * 4) * cblks + 127) / 128 * 128;
-    return (size_t)p.nkb * bn * 128 + 2 * buf + 2 * raw + 128 + (size_t)(bn < 32 ? 32 : bn) * 4 + 1024;
+    return (size_t)p.nkb * bn * 128 + 2 * buf + (size_t)p.nraw * raw + 192 + (size_t)(bn < 32 ? 32 : bn) * 4 + 1024;
 }
 
 // column-tap folding applies to 3x3 kernels whose padded row fits a pitch that divides 32, with 3*BN*2 <= 512 TMEM columns
@@ -390,7 +400,8 @@ static bool sv_plan(SvParams& p, int bn) {
         q.tiles = (rows + 127) / 128;
         // an M=64 tail tile keeps 16 rows per lane quadrant: with folding its rows 14,15 (mod 16) must be garbage columns
         q.last64 = (rows - (q.tiles - 1) * 128) <= 64 && !(jf && q.PW != 16);
-        q.region_rows = (q.tiles * 128 + (p.kh - 1) * q.PW + p.kw + 7) & ~7;
+        q.region_rows = ((q.tiles - 1) * 128 + (q.last64 ? 64 : 128) + (p.kh - 1) * q.PW + p.kw + 7) & ~7;
+        q.nraw = 2;
     };
     for (int th = p.Hd; th >= 1; --th) {
         SvParams q = p;
@@ -403,6 +414,7 @@ static bool sv_plan(SvParams& p, int bn) {
     }
     if (!best_th) return false;
     shape(p, best_th);
+    while (p.nraw < 4) { ++p.nraw; if (sv_smem_bytes(p, bn) > budget) { --p.nraw; break; } }
     p.units = (long)p.B * p.nbands;
     return true;
 }
@@ -462,6 +474,7 @@ int tc_conv_sv_run(const char* name, const float* src, const float* wprep, int n
                    float* dst, const dnb_win_t* g, bool dgrad, cudaStream_t st) {
     SvParams p = sv_make(g, dgrad);
     p.dst = dst; p.bias = bias; p.bias_k = bias_k;
+    p.debug = getenv("DNB_SV_DEBUG") ? atoi(getenv("DNB_SV_DEBUG")) : 0;
     if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) return set_err(DNB_ERR_UNSUPPORTED, "%s: source tensor is not 16-byte aligned", name);
     const int bn = pick_bn_sv(p.Cd);
     if (!sv_plan(p, bn)) return set_err(DNB_ERR_UNSUPPORTED, "%s: shape does not fit the shifted-view kernel", name);

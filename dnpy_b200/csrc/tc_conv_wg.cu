@@ -33,7 +33,9 @@ struct WgSvParams {
     int KR;                  // reduction rows per unit: round_up(TH*PW, 8)
     int xs_rows;             // rows of one staged X buffer (padded image + tap/chunk overhang), multiple of 8
     int fr;                  // 32-filter regions of dY: F / 32
+    int nraw;                // raw TMA stages (2..4)
     int flat;                // tensor maps are (H*W, C, B): a band of a channel is one contiguous box row
+    int debug;               // timing experiments (DNB_WG_DEBUG): 1 no epilogue atomics, 2 no MMAs, 4 no transposition
     float inv_m;
 };
 
@@ -77,14 +79,14 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     uint8_t* sD = smem;                                    // 2 x fr regions (A operand; chunks >= fr of the M=128 MMA alias what follows)
     uint8_t* sX = sD + 2 * (size_t)dbuf_bytes;             // 2 buffers (B operand)
     uint8_t* sR = sX + 2 * (size_t)xbuf_bytes;             // 2 raw stages: x band [32][TH+2][W], dY band [F][TH][OW]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + 2 * (size_t)raw_bytes);
-    uint64_t* raw_full = bars;         // [2] tx
-    uint64_t* raw_empty = bars + 2;    // [2] WG_TR
-    uint64_t* xd_full = bars + 4;      // [2] WG_TR
-    uint64_t* xd_empty = bars + 6;     // [2] commit
-    uint64_t* acc_full = bars + 8;     // commit
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-    float* s_gb = reinterpret_cast<float*>(bars + 10);     // [128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (size_t)p.nraw * raw_bytes);
+    uint64_t* raw_full = bars;         // [4] tx
+    uint64_t* raw_empty = bars + 4;    // [4] WG_TR
+    uint64_t* xd_full = bars + 8;      // [2] WG_TR
+    uint64_t* xd_empty = bars + 10;    // [2] commit
+    uint64_t* acc_full = bars + 12;    // commit
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    float* s_gb = reinterpret_cast<float*>(bars + 14);     // [128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const long units = (long)p.B * p.nbands;
@@ -97,10 +99,8 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     if (tid == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmD);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], WG_TR);
-            mbar_init(&xd_full[s], WG_TR); mbar_init(&xd_empty[s], 1);
-        }
+        for (int s = 0; s < 4; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], WG_TR); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&xd_full[s], WG_TR); mbar_init(&xd_empty[s], 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -117,9 +117,9 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
+            int s = 0, rph = 0;
             for (int n = 0; n < nimg; ++n) {
-                const int s = n & 1;
-                if (n >= 2) mbar_wait(&raw_empty[s], ((n >> 1) - 1) & 1);
+                if (n >= p.nraw) mbar_wait(&raw_empty[s], rph ^ 1);
                 const long u = (long)blockIdx.x + (long)n * gridDim.x;
                 const int b = (int)(u / p.nbands), band = (int)(u % p.nbands);
                 uint8_t* rs = sR + (size_t)s * raw_bytes;
@@ -132,6 +132,7 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                     wg_tma_load_4d(rs, &tmX, 0, band * p.TH - p.pt, 0, b, &raw_full[s]);
                     for (int r = 0; r < p.fr; ++r) wg_tma_load_4d(rs + rawx_bytes + (size_t)r * rawd_box, &tmD, 0, band * p.TH, r * 32, b, &raw_full[s]);
                 }
+                if (++s == p.nraw) { s = 0; rph ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -147,7 +148,7 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             const uint64_t a0 = make_smem_desc(smem_u32(sD + (size_t)s * dbuf_bytes), dreg_bytes, 512, LAYOUT_SW128_BASE32B);
             const uint64_t b0 = make_smem_desc(smem_u32(sX + (size_t)s * xbuf_bytes), 128, 512, LAYOUT_SW128_BASE32B);
             if (elect_one()) {
-                for (int ks = 0; ks < ksteps; ++ks) {
+                for (int ks = 0; ks < ((p.debug & 2) ? 0 : ksteps); ++ks) {
                     const uint64_t a = a0 + (uint64_t)((uint32_t)ks * 64);                 // 8 rows = 1024 B
                     const uint64_t bq = b0 + (uint64_t)((uint32_t)ks * 64);
                     const uint32_t acc = (n > 0 || ks > 0) ? 1u : 0u;
@@ -195,12 +196,14 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         float gbs[WG_TBD][4];
 #pragma unroll
         for (int r = 0; r < WG_TBD; ++r) { gbs[r][0] = 0.f; gbs[r][1] = 0.f; gbs[r][2] = 0.f; gbs[r][3] = 0.f; }
+        int rs = 0, rph = 0;
         for (int n = 0; n < nimg; ++n) {
             const int s = n & 1;
-            mbar_wait(&raw_full[s], (n >> 1) & 1);
+            mbar_wait(&raw_full[rs], rph);
             if (n >= 2) mbar_wait(&xd_empty[s], ((n >> 1) - 1) & 1);
-            const uint32_t rx = smem_u32(sR + (size_t)s * raw_bytes), rd = rx + rawx_bytes;
+            const uint32_t rx = smem_u32(sR + (size_t)rs * raw_bytes), rd = rx + rawx_bytes;
             const uint32_t xb = smem_u32(sX + (size_t)s * xbuf_bytes), db = smem_u32(sD + (size_t)s * dbuf_bytes);
+            if (!(p.debug & 4)) {
 #pragma unroll
             for (int r0 = 0; r0 < WG_TBX; r0 += 3) {
                 float4 v[3];
@@ -230,9 +233,11 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                         gbs[r0 + r][0] += v[r].x; gbs[r0 + r][1] += v[r].y; gbs[r0 + r][2] += v[r].z; gbs[r0 + r][3] += v[r].w;
                     }
             }
+            }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&xd_full[s]); mbar_arrive(&raw_empty[s]); }
+            if (lane == 0) { mbar_arrive(&xd_full[s]); mbar_arrive(&raw_empty[rs]); }
+            if (++rs == p.nraw) { rs = 0; rph ^= 1; }
         }
         // ---- bias gradient: per-slot sums -> shared -> global
         if (p.gb) {
@@ -260,7 +265,7 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
                     uint32_t v[16];
                     tmem_ld_16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                     tmem_ld_wait();
-                    if (f < p.F) {
+                    if (f < p.F && !(p.debug & 1)) {
 #pragma unroll
                         for (int u = 0; u < 16; ++u) {
                             const int col = c0 + u;
@@ -279,7 +284,7 @@ tc_conv_wgrad_sv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 
 static size_t wgsv_raw(const WgSvParams& p) { return (size_t)(p.TH + 2) * p.W * 32 * 4 + (size_t)p.TH * p.OW * 32 * 4 * p.fr; }
 static size_t wgsv_smem(const WgSvParams& p) {
-    return 2 * (size_t)p.KR * 128 * p.fr + 2 * (size_t)p.xs_rows * 128 + 2 * wgsv_raw(p) + 128 + 128 * 4 + 1024;
+    return 2 * (size_t)p.KR * 128 * p.fr + 2 * (size_t)p.xs_rows * 128 + (size_t)p.nraw * wgsv_raw(p) + 128 + 128 * 4 + 1024;
 }
 
 static bool wgsv_plan(const dnb_win_t* g, WgSvParams& p) {
@@ -292,7 +297,7 @@ static bool wgsv_plan(const dnb_win_t* g, WgSvParams& p) {
     if (g->W > 256 || g->OW > 256) return false;
     // tallest band (fewest units, least halo) whose double-buffered staging fits
     for (int th = g->OH; th >= 1; --th) {
-        p.TH = th; p.nbands = (g->OH + th - 1) / th;
+        p.TH = th; p.nbands = (g->OH + th - 1) / th; p.nraw = 2;
         if (p.nbands > 1 && th * p.nbands - g->OH >= th / 2 + 1) continue;          // badly unbalanced last band
         p.KR = (th * p.PW + 7) & ~7;
         p.xs_rows = (p.KR + 2 * p.PW + 2 + 8 + 7) & ~7;
@@ -301,7 +306,10 @@ static bool wgsv_plan(const dnb_win_t* g, WgSvParams& p) {
         // chunks fr.. of the A operand (M=128: 4 chunks, M=64: 2) alias the memory behind the dY buffers: it must exist
         const size_t behind = 2 * (size_t)p.xs_rows * 128 + 2 * wgsv_raw(p);
         if ((size_t)3 * p.KR * 128 > behind) continue;
-        if (wgsv_smem(p) <= 225 * 1024) return true;
+        if (wgsv_smem(p) <= 225 * 1024) {
+            while (p.nraw < 4) { ++p.nraw; if (wgsv_smem(p) > 225 * 1024) { --p.nraw; break; } }
+            return true;
+        }
     }
     return false;
 }
@@ -321,6 +329,7 @@ int tc_conv_wgrad_sv(const float* x, const float* dy, float* gw, float* gb, cons
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15))
         return set_err(DNB_ERR_UNSUPPORTED, "conv2d_bwd_weight(sv): tensors must be 16-byte aligned");
     p.gw = gw; p.gb = gb; p.inv_m = inv_m;
+    p.debug = getenv("DNB_WG_DEBUG") ? atoi(getenv("DNB_WG_DEBUG")) : 0;
     CUtensorMap tx, td;
     p.flat = ((p.TH + 2) * g->W <= 256 && p.TH * g->OW <= 256) && !getenv("DNB_SV_NOFLAT");
     bool ok1, ok2;
