@@ -321,11 +321,18 @@ def main():
     # warm-up: at least W steps, at least 0.5 s under load, and enough calls for every (minibatch buffer) step
     # graph to be captured (2 eager calls + 1 capture per buffer) so no capture lands in the timed region
     min_warm = max(3, args.warmup, 3 * n_mb + 4)
-    while i_w < min_warm or (time.perf_counter() - t_w) < 0.5:
+    while True:
         step_resident(i_w)
         i_w += 1
         if i_w % 8 == 0:
             torch.cuda.synchronize()
+            more = i_w < min_warm or (time.perf_counter() - t_w) < 0.5
+            if world > 1:                # every rank must run the SAME number of steps (one all-reduce each)
+                flag = torch.tensor([1 if more else 0], device="cuda")
+                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+                more = bool(flag.item())
+            if not more:
+                break
     ms, launches = timed(step_resident, args.steps)
     loss = float(last["o"][0][0].item())
     if world > 1:
@@ -406,7 +413,7 @@ def main():
     if rank == 0:
         line = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype=args.math, data="synthetic", config=dict(config, warmup_steps_run=i_w, cuda_graph=bool(net.use_graph and world == 1)),
+                    dtype=args.math, data="synthetic", config=dict(config, warmup_steps_run=i_w, cuda_graph=bool(net.use_graph and net._graph_ok_for_world())),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
                              ms_per_step=ms_e2e / args.steps),
@@ -414,7 +421,13 @@ def main():
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
     if world > 1:
-        parallel.shutdown()
+        # every rank has finished its collectives; tear down without the NCCL destructor dance (captured step graphs
+        # still reference the communicator, and a blocking destroy_process_group has been seen to wait forever)
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        real_stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

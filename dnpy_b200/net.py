@@ -363,7 +363,7 @@ class Net:
         work per step is then the input copies, the Dropout draws and one graph launch."""
         xs = [self._stage_in(("x", j), x_mb[j], self._input_is_int(j)) for j in range(len(self.l_in))]
         ys = [self._stage_in(("y", i), y_mb[i]) for i in range(len(self.losses))]
-        if not (self.use_graph and config.world == 1 and not self.debug):
+        if not (self.use_graph and not self.debug and self._graph_ok_for_world()):
             return self._step_body(xs, ys)
         key = (tuple(x.ptr() for x in xs), tuple(y.ptr() for y in ys), tuple(x.shape for x in xs), self.mode,
                config.math, config.maxpool_route, self._layer_generation())
@@ -393,6 +393,17 @@ class Net:
         self.graph_launches += ent["launches"]
         self._mark_written()
         return ent["outs"]
+
+    @staticmethod
+    def _graph_ok_for_world():
+        """Data parallel: the gradient all-reduce is captured inside the step graph when the group runs on NCCL
+        (capturable); other backends (gloo in the CPU/1-GPU tests) keep the eager step."""
+        if config.world == 1:
+            return True
+        if os.environ.get("DNPY_B200_DP_GRAPH", "1") == "0":
+            return False
+        import torch.distributed as dist
+        return dist.is_initialized() and dist.get_backend() == "nccl"
 
     def _step_body(self, xs, ys):
         for j in range(len(self.l_in)):
