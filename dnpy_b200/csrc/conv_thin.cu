@@ -440,7 +440,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
 }
 
-template <int C>
+// ONEQ: plane/4 <= consumers, so a thread owns ONE quad for the whole kernel and its window geometry (4 shared
+// offsets + validity bits) is computed once, outside the image loop; NOPAD additionally drops the validity tests.
+template <int C, bool ONEQ, bool NOPAD>
 __global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(ThinArgs a) {
     constexpr int K = C * 9, FT = flat_wg_ft(C), ST = FLAT_WG_STAGES;
     extern __shared__ __align__(128) uint8_t smraw[];
@@ -481,6 +483,25 @@ __global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(Thi
     for (int f = 0; f < FT; ++f)
 #pragma unroll
         for (int k = 0; k <= K; ++k) acc[f][k] = 0.f;
+    // ONEQ geometry of this thread's quad (image independent)
+    int xo[4] = {0, 0, 0, 0};
+    uint32_t vm[4] = {0u, 0u, 0u, 0u};
+    if (ONEQ) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int p = min(4 * tid + e, plane - 1);
+            const int oy = p / a.OW, ox = p - oy * a.OW;
+            xo[e] = (oy - a.pt) * a.W + (ox - a.pl);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int iy = oy - a.pt + i, ix = ox - a.pl + j;
+                    if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) vm[e] |= 1u << (i * 3 + j);
+                }
+        }
+    }
+    const int hw = a.H * a.W;
     for (int n = 0; n < nimg; ++n) {
         const int s = n % ST;
         tc::mbar_wait(&full[s], (n / ST) & 1);
@@ -488,6 +509,21 @@ __global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(Thi
         const float* sd = sx + xsz;
         for (int q = tid; q < qpi; q += FLAT_WG_CONSUMERS) {
             float xin[4][K];
+            if (ONEQ) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float* xe = sx + xo[e];
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+                                if (NOPAD) xin[e][(c * 3 + i) * 3 + j] = xe[c * hw + i * a.W + j];
+                                else xin[e][(c * 3 + i) * 3 + j] = ((vm[e] >> (i * 3 + j)) & 1u) ? xe[c * hw + i * a.W + j] : 0.f;
+                            }
+                }
+            } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int p = 4 * q + e;
@@ -504,6 +540,7 @@ __global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(Thi
                             xin[e][(c * 3 + i) * 3 + j] = (rok && ix >= 0 && ix < a.W) ? sx[(c * a.H + iy) * a.W + ix] : 0.f;
                         }
                     }
+            }
             }
 #pragma unroll
             for (int f = 0; f < FT; ++f) {
@@ -726,12 +763,19 @@ static int thin_wgrad_flat(const ThinArgs& a, cudaStream_t st) {
     constexpr int FT = flat_wg_ft(C);
     const size_t stage = (((size_t)C * a.H * a.W + (size_t)FT * a.OH * a.OW) * 4 + 127) & ~(size_t)127;
     const size_t smem = 128 + FLAT_WG_STAGES * stage;
-    cudaFuncSetAttribute(thin_wgrad_flat_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (!getenv("DNB_NO_CARVEOUT")) cudaFuncSetAttribute(thin_wgrad_flat_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     const int fgroups = (a.F + FT - 1) / FT;
     const int splits = (int)std::max<long>(1, std::min<long>(a.B, (2L * kNumSMs + fgroups - 1) / fgroups));
     dim3 grid(splits, fgroups);
-    thin_wgrad_flat_kernel<C><<<grid, FLAT_WG_THREADS, smem, st>>>(a);
+    const bool oneq = ((a.OH * a.OW) >> 2) <= FLAT_WG_CONSUMERS && !getenv("DNB_NO_THIN_ONEQ");
+    const bool nopad = a.pt == 0 && a.pl == 0 && a.OH + 2 <= a.H && a.OW + 2 <= a.W;
+    auto launch = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (!getenv("DNB_NO_CARVEOUT")) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        kern<<<grid, FLAT_WG_THREADS, smem, st>>>(a);
+    };
+    if (!oneq) launch(thin_wgrad_flat_kernel<C, false, false>);
+    else if (nopad) launch(thin_wgrad_flat_kernel<C, true, true>);
+    else launch(thin_wgrad_flat_kernel<C, true, false>);
     DNB_LAUNCH_CHECK("thin_conv2d_bwd_weight");
     return DNB_OK;
 }

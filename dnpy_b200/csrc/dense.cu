@@ -304,6 +304,13 @@ __global__ void __launch_bounds__(256) skinny_dw_kernel(const float* __restrict_
     }
 }
 
+// dense_head.cu
+bool head_supported(int B, int in, int out);
+bool head_fwd(const float* x, const float* w, const float* b, float* y, int B, int in, int out, cudaStream_t st);
+bool head_dx(const float* dy, const float* w, float* dx, int B, int in, int out, cudaStream_t st);
+bool head_dw(const float* x, const float* dy, const float* w, float* gw, const float* b, float* gb, int B, int in, int out,
+             float inv_m, float l1, float l2, float bl1, float bl2, cudaStream_t st);
+
 }  // namespace dnb
 
 using namespace dnb;
@@ -315,6 +322,10 @@ int dnb_dense_fwd(const float* x, const float* w, const float* b, float* y,
     DNB_CHECK_ARG(B >= 0 && in > 0 && out > 0, "dense_fwd: bad shape B=%d in=%d out=%d", B, in, out);
     if (B == 0) return DNB_OK;
     DNB_CHECK_ARG(x && w && y, "dense_fwd: null pointer");
+    if (head_supported(B, in, out) && head_fwd(x, w, b, y, B, in, out, S(stream))) {
+        DNB_LAUNCH_CHECK("dense_fwd");
+        return DNB_OK;
+    }
     if (out <= SKN && B >= 64) {
         skinny_fwd_kernel<<<(B + 8 * RPW - 1) / (8 * RPW), 256, 0, S(stream)>>>(x, w, b, y, B, in, out);
         DNB_LAUNCH_CHECK("dense_fwd");
@@ -338,7 +349,10 @@ int dnb_dense_bwd(const float* x, const float* w, const float* b, const float* d
     int rc;
     if (out <= SKN && B >= 64) {
         const size_t dx_smem = ((size_t)out * in + 32 * SKN) * sizeof(float);
-        if (dx && (in & 3) == 0 && dx_smem <= 160 * 1024 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+        const bool head = head_supported(B, in, out);
+        if (dx && head && head_dx(dy, w, dx, B, in, out, st)) {
+            DNB_LAUNCH_CHECK("dense_bwd_dx");
+        } else if (dx && (in & 3) == 0 && dx_smem <= 160 * 1024 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
             cudaFuncSetAttribute(skinny_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dx_smem);
             skinny_dx_kernel<<<(B + 31) / 32, 256, dx_smem, st>>>(dy, w, dx, B, in, out, 32);
             DNB_LAUNCH_CHECK("dense_bwd_dx");
@@ -346,6 +360,11 @@ int dnb_dense_bwd(const float* x, const float* w, const float* b, const float* d
             GemmArgs a{dy, out, 1, w, 1, out, dx, B, in, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0};
             rc = launch_sgemm<EPI_STORE>("dense_bwd_dx", a, st);
             if (rc) return rc;
+        }
+        if (head && head_dw(x, dy, w, gw, b, gb, B, in, out, inv_m, reg_w.l1 * reg_scale, reg_w.l2 * reg_scale,
+                            reg_b.l1 * reg_scale, reg_b.l2 * reg_scale, st)) {
+            DNB_LAUNCH_CHECK("dense_bwd_dw");
+            return DNB_OK;
         }
         const int itiles = (in + 511) / 512;
         int bsplit = std::max(1, std::min((B + 127) / 128, (4 * kNumSMs + itiles - 1) / itiles));

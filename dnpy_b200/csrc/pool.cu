@@ -8,6 +8,8 @@
 //   * AvgPool2D.backward ASSIGNS delta/(py*px) to the window, later windows overwrite.
 // All kernels are gather-style (no atomics on the data path), coalesced along x.  Roofline: HBM.
 #include "common.cuh"
+#include "tc_common.cuh"
+#include <algorithm>
 
 namespace dnb {
 
@@ -77,6 +79,149 @@ __global__ void __launch_bounds__(256) maxpool_fwd_strip_kernel(const float* __r
         for (int p = 0; p < 4; ++p)
             if (ox0 + p < OW) { y[o + p] = best[p]; idx[o + p] = bi[p]; }
     }
+}
+
+// Ring path for unpadded pools whose planes are whole 16-byte quads: ALL global traffic is bulk-asynchronous (TMA 1-D
+// copies).  The (b,c) planes are contiguous, so a chunk of G planes is one cp.async.bulk into a 4-stage shared ring
+// (a producer lane keeps it full); 256 consumer threads take the windows out of shared memory (geometry per thread is
+// chunk independent and lives in registers), put values and argmax offsets into a double-buffered shared output
+// chunk, and one thread writes each finished chunk back with two bulk stores.  No L1/LSU pressure from the
+// overlapping, row-strided window reads (the strip kernel above is l1tex bound at ~54% of HBM peak).
+constexpr int MPR_CONS = 256, MPR_THREADS = MPR_CONS + 32, MPR_ST = 4, MPR_MAXR = 6;
+
+__device__ __forceinline__ void mp_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mp_bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst), "r"(tc::smem_u32(src)), "r"(bytes) : "memory");
+}
+
+template <int K, int S, bool VEC2>
+__global__ void __launch_bounds__(MPR_THREADS, 2) maxpool_fwd_ring_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                           int32_t* __restrict__ idx, int nchunks, int G,
+                                                                           int H, int W, int OH, int OW) {
+    extern __shared__ __align__(128) uint8_t smraw[];
+    const int plane = H * W, oplane = OH * OW;
+    const int n_in = G * plane, n_out = G * oplane;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw);
+    uint64_t* empty = full + MPR_ST;
+    float* sin = reinterpret_cast<float*>(smraw + 128);                 // [ST][n_in]
+    float* sy = sin + (size_t)MPR_ST * n_in;                            // [2][n_out]
+    int32_t* si = reinterpret_cast<int32_t*>(sy + 2 * n_out);           // [2][n_out]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < MPR_ST; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], MPR_CONS / 32); }
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+    const int mine = (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // chunks blockIdx.x + n*gridDim.x
+
+    if (wid == MPR_CONS / 32) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)n_in * 4u;
+            for (int n = 0; n < mine; ++n) {
+                const int s = n % MPR_ST;
+                if (n >= MPR_ST) tc::mbar_wait(&empty[s], ((n / MPR_ST) - 1) & 1);
+                const long c = (long)blockIdx.x + (long)n * gridDim.x;
+                tc::mbar_arrive_expect_tx(&full[s], bytes);
+                mp_bulk_g2s(sin + (size_t)s * n_in, x + c * n_in, bytes, &full[s]);
+            }
+        }
+        return;
+    }
+    // chunk-independent geometry: output e = tid + r*256 of the chunk reads its window at in_off[r]
+    int in_off[MPR_MAXR];
+#pragma unroll
+    for (int r = 0; r < MPR_MAXR; ++r) {
+        const int e = min(tid + r * MPR_CONS, n_out - 1);
+        const int p = e / oplane, o = e - p * oplane;
+        const int oy = o / OW, ox = o - oy * OW;
+        in_off[r] = p * plane + oy * S * W + ox * S;
+    }
+    for (int n = 0; n < mine; ++n) {
+        const int s = n % MPR_ST, ob = n & 1;
+        tc::mbar_wait(&full[s], (n / MPR_ST) & 1);
+        const float* in = sin + (size_t)s * n_in;
+        float* oy_ = sy + ob * n_out;
+        int32_t* oi_ = si + ob * n_out;
+#pragma unroll
+        for (int r = 0; r < MPR_MAXR; ++r) {
+            const int e = tid + r * MPR_CONS;
+            if (e < n_out) {
+                const float* wp = in + in_off[r];
+                float best = 0.f; int bi = -1;
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    float v[K];
+                    if (VEC2) {          // S == 2, W even, plane even: the window row starts on an 8-byte boundary
+#pragma unroll
+                        for (int j = 0; j + 1 < K; j += 2) {
+                            const float2 f = *reinterpret_cast<const float2*>(wp + i * W + j);
+                            v[j] = f.x; v[j + 1] = f.y;
+                        }
+                        if (K & 1) v[K - 1] = wp[i * W + K - 1];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < K; ++j) v[j] = wp[i * W + j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        const float c = v[j];
+                        // np.argmax: first maximum wins; NaN propagates as the maximum
+                        if (bi < 0 || c > best || (c != c && best == best)) { best = c; bi = i * K + j; }
+                    }
+                }
+                oy_[e] = best;
+                oi_[e] = bi;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&empty[s]);
+        // hand the finished output chunk to the bulk-store engine; the OTHER output buffer must be drained before the
+        // next chunk overwrites it (its store was committed one chunk ago)
+        tc::fence_proxy_async_smem();
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(MPR_CONS) : "memory");
+        if (tid == 0) {
+            const long c = (long)blockIdx.x + (long)n * gridDim.x;
+            mp_bulk_s2g(y + c * n_out, oy_, (uint32_t)n_out * 4u);
+            mp_bulk_s2g(idx + c * n_out, oi_, (uint32_t)n_out * 4u);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// planes per chunk for the ring kernel (0: shape not eligible)
+static int mpr_chunk_planes(long planes, int H, int W, int OH, int OW) {
+    const long plane = (long)H * W, oplane = (long)OH * OW;
+    if (plane % 4) return 0;
+    const long gmax = std::min<long>({planes, (24 * 1024) / (plane * 4), (long)(MPR_MAXR * MPR_CONS) / oplane});
+    for (long G = gmax; G >= 1; --G)
+        if (planes % G == 0 && (G * oplane) % 4 == 0) return (int)G;
+    return 0;
+}
+template <int K, int S>
+static bool maxpool_fwd_ring(const float* x, float* y, int32_t* idx, const dnb_win_t* g, cudaStream_t st) {
+    const long planes = (long)g->B * g->C;
+    const int G = mpr_chunk_planes(planes, g->H, g->W, g->OH, g->OW);
+    if (!G || getenv("DNB_NO_POOL_RING")) return false;
+    const long nchunks = planes / G;
+    if (nchunks > 0x7fffffffL) return false;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(idx)) & 15) return false;
+    const size_t smem = 128 + ((size_t)MPR_ST * G * g->H * g->W + 4ull * G * g->OH * g->OW) * 4;
+    const int grid = (int)std::min<long>(nchunks, 2L * kNumSMs);
+    const bool v2 = (S == 2) && (g->W % 2 == 0);
+    if (v2) {
+        cudaFuncSetAttribute(maxpool_fwd_ring_kernel<K, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        maxpool_fwd_ring_kernel<K, S, true><<<grid, MPR_THREADS, smem, st>>>(x, y, idx, (int)nchunks, G, g->H, g->W, g->OH, g->OW);
+    } else {
+        cudaFuncSetAttribute(maxpool_fwd_ring_kernel<K, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        maxpool_fwd_ring_kernel<K, S, false><<<grid, MPR_THREADS, smem, st>>>(x, y, idx, (int)nchunks, G, g->H, g->W, g->OH, g->OW);
+    }
+    return true;
 }
 
 // PER_SAMPLE: dx[b,c,iy,ix] = sum over windows covering it whose argmax points here.
@@ -261,6 +406,14 @@ int dnb_maxpool2d_fwd(const float* x, float* y, int32_t* idx, const dnb_win_t* g
     if (n == 0) return DNB_OK;
     DNB_CHECK_ARG(x && y && idx, "maxpool2d_fwd: null pointer");
     const bool nopad = !(g->pt | g->pb | g->pl | g->pr);
+    if (nopad && g->kh == g->kw && g->sy == g->sx && (g->OH - 1) * g->sy + g->kh <= g->H && (g->OW - 1) * g->sx + g->kw <= g->W) {
+        bool done = false;
+        if (g->kh == 3 && g->sy == 2) done = maxpool_fwd_ring<3, 2>(x, y, idx, g, S(stream));
+        else if (g->kh == 2 && g->sy == 2) done = maxpool_fwd_ring<2, 2>(x, y, idx, g, S(stream));
+        else if (g->kh == 3 && g->sy == 1) done = maxpool_fwd_ring<3, 1>(x, y, idx, g, S(stream));
+        else if (g->kh == 2 && g->sy == 1) done = maxpool_fwd_ring<2, 1>(x, y, idx, g, S(stream));
+        if (done) { DNB_LAUNCH_CHECK("maxpool2d_fwd"); return DNB_OK; }
+    }
     const bool even = (g->W % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
     if (nopad && even && g->kh == g->kw && g->sy == g->sx && g->sy == 2 && (g->kh == 2 || g->kh == 3) &&
         (g->OH - 1) * g->sy + g->kh <= g->H) {

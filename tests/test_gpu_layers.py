@@ -116,6 +116,10 @@ def _oracle_pair(ns, case, route="literal"):
 BIG_CASES = [
     dict(name="big_dense", kind="Dense", in_shape=(784,), batch=256, kw=dict(units=512)),
     dict(name="big_dense_head", kind="Dense", in_shape=(1600,), batch=128, kw=dict(units=10, kernel_regularizer=["L2", 0.01])),
+    # classifier-head kernels (out <= 16, in % 4 == 0): row tails, a W-chunk tail (520 = 512 + 8), out = 1 / 3 / 16
+    dict(name="head_out3_rowtail", kind="Dense", in_shape=(300,), batch=70, kw=dict(units=3, kernel_regularizer=["L1", 0.02])),
+    dict(name="head_out16_chunktail", kind="Dense", in_shape=(520,), batch=65, kw=dict(units=16)),
+    dict(name="head_out1_wide", kind="Dense", in_shape=(4096,), batch=300, kw=dict(units=1)),
     dict(name="big_conv1", kind="Conv2D", in_shape=(1, 28, 28), batch=64,
          kw=dict(filters=32, kernel_size=(3, 3), strides=(1, 1), padding="none")),
     # flat thin-conv kernels (C <= 2, plane % 4 == 0): filter-count tails, padding, many images per CTA, W % 4 != 0
@@ -137,6 +141,18 @@ BIG_CASES = [
     dict(name="big_maxpool", kind="MaxPool2D", in_shape=(32, 26, 26), batch=130,
          kw=dict(pool_size=(3, 3), strides=(2, 2), padding="none")),
     dict(name="big_maxpool_ties", kind="MaxPool2D", in_shape=(8, 12, 12), batch=200, quantize=True,
+         kw=dict(pool_size=(3, 3), strides=(2, 2), padding="none")),
+    # bulk-copy ring forward (unpadded, plane % 4 == 0): 2x2 pools, 5x5 outputs (chunk size from divisibility),
+    # stride 1, a one-chunk launch; odd planes fall back to the strip / generic kernels
+    dict(name="ring_maxpool_2x2", kind="MaxPool2D", in_shape=(16, 32, 32), batch=8,
+         kw=dict(pool_size=(2, 2), strides=(2, 2), padding="none")),
+    dict(name="ring_maxpool_5x5out", kind="MaxPool2D", in_shape=(64, 12, 12), batch=24, quantize=True,
+         kw=dict(pool_size=(3, 3), strides=(2, 2), padding="none")),
+    dict(name="ring_maxpool_s1", kind="MaxPool2D", in_shape=(4, 10, 10), batch=6,
+         kw=dict(pool_size=(3, 3), strides=(1, 1), padding="none")),
+    dict(name="ring_maxpool_many_chunks", kind="MaxPool2D", in_shape=(32, 12, 12), batch=1300,
+         kw=dict(pool_size=(3, 3), strides=(2, 2), padding="none")),
+    dict(name="maxpool_odd_plane", kind="MaxPool2D", in_shape=(3, 13, 13), batch=5,
          kw=dict(pool_size=(3, 3), strides=(2, 2), padding="none")),
     dict(name="big_avgpool", kind="AvgPool2D", in_shape=(16, 16, 16), batch=32,
          kw=dict(pool_size=(2, 2), strides=(2, 2), padding="none")),
