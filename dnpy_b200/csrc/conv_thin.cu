@@ -507,23 +507,39 @@ __global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(Thi
         tc::mbar_wait(&full[s], (n / ST) & 1);
         const float* sx = reinterpret_cast<const float*>(stages + (size_t)s * stage_bytes);
         const float* sd = sx + xsz;
+        if (ONEQ) {
+            // two pixel pairs per quad: 2 x K window values live at a time (acc + window fit the register budget)
+            if (tid < qpi) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float xin[2][K];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float* xe = sx + xo[2 * h + e];
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+#pragma unroll
+                            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                                for (int j = 0; j < 3; ++j) {
+                                    if (NOPAD) xin[e][(c * 3 + i) * 3 + j] = xe[c * hw + i * a.W + j];
+                                    else xin[e][(c * 3 + i) * 3 + j] = ((vm[2 * h + e] >> (i * 3 + j)) & 1u) ? xe[c * hw + i * a.W + j] : 0.f;
+                                }
+                    }
+#pragma unroll
+                    for (int f = 0; f < FT; ++f) {
+                        if (f < nf) {
+                            const float2 d = *reinterpret_cast<const float2*>(sd + f * plane + 4 * tid + 2 * h);
+                            acc[f][K] += d.x + d.y;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) acc[f][k] = fmaf(d.y, xin[1][k], fmaf(d.x, xin[0][k], acc[f][k]));
+                        }
+                    }
+                }
+            }
+        } else {
         for (int q = tid; q < qpi; q += FLAT_WG_CONSUMERS) {
             float xin[4][K];
-            if (ONEQ) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float* xe = sx + xo[e];
-#pragma unroll
-                    for (int c = 0; c < C; ++c)
-#pragma unroll
-                        for (int i = 0; i < 3; ++i)
-#pragma unroll
-                            for (int j = 0; j < 3; ++j) {
-                                if (NOPAD) xin[e][(c * 3 + i) * 3 + j] = xe[c * hw + i * a.W + j];
-                                else xin[e][(c * 3 + i) * 3 + j] = ((vm[e] >> (i * 3 + j)) & 1u) ? xe[c * hw + i * a.W + j] : 0.f;
-                            }
-                }
-            } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int p = 4 * q + e;
@@ -541,7 +557,6 @@ __global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(Thi
                         }
                     }
             }
-            }
 #pragma unroll
             for (int f = 0; f < FT; ++f) {
                 if (f < nf) {
@@ -556,6 +571,7 @@ __global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(Thi
                     }
                 }
             }
+        }
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty[s]);
