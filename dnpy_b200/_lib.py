@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdnpy_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
-MATH_FP32, MATH_TF32 = 0, 1
+MATH_FP32, MATH_TF32, MATH_BF16 = 0, 1, 2
 ROUTE_LITERAL, ROUTE_PER_SAMPLE = 0, 1
 
 

@@ -403,7 +403,7 @@ extern "C" {
 
 size_t dnb_conv2d_ws_bytes(const dnb_win_t* g, int math) {
     if (!g) return 0;
-    return math == DNB_MATH_TF32 ? tc_conv_ws_bytes(g) : 0;
+    return math >= DNB_MATH_TF32 ? tc_conv_ws_bytes(g) : 0;
 }
 
 int dnb_conv2d_fwd(const float* x, const float* w, const float* b, float* y,
@@ -413,8 +413,8 @@ int dnb_conv2d_fwd(const float* x, const float* w, const float* b, float* y,
     if (g->B == 0) return DNB_OK;
     DNB_CHECK_ARG(x && w && b && y, "conv2d_fwd: null pointer");
     if (thin_conv_supported(g)) return thin_conv_fwd(x, w, b, y, g, S(stream));
-    if (math == DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_FWD))
-        return tc_conv_fwd(x, w, b, y, g, ws, S(stream));
+    if (math >= DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_FWD))
+        return tc_conv_fwd(x, w, b, y, g, ws, math == DNB_MATH_BF16, S(stream));
     GatherArgs a{x, w, b, y, g->B, g->C, g->H, g->W, g->F, g->OH, g->OW, g->kh, g->kw,
                  g->sy, g->sx, 1, 1, g->pt, g->pl, 0, (float)(g->C * g->kh * g->kw)};
     return launch_gather<false>("conv2d_fwd", a, S(stream));
@@ -432,14 +432,14 @@ int dnb_conv2d_bwd(const float* x, const float* w, const float* b, const float* 
     const bool thin = thin_conv_supported(g);
     // measured on B200 (conv 1->32, 28x28, B=8192): the register-tiled fp32 wgrad (0.35 ms) edges out the tensor-core
     // thin-K variant (0.40 ms) — both are dY-stream bound — so thin layers keep the fp32 kernel in either math mode
-    const bool tc_wgrad = !thin && math == DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_WGRAD);
+    const bool tc_wgrad = !thin && math >= DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_WGRAD);
     if (thin) {
         rc = thin_conv_bwd(x, w, dy, dx, gw, gb, g, inv_m, /*skip_wgrad=*/tc_wgrad, st);
         if (rc) return rc;
     }
     if (dx && !thin) {
-        if (math == DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_DGRAD)) {
-            rc = tc_conv_dgrad(dy, w, dx, g, ws, st);
+        if (math >= DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_DGRAD)) {
+            rc = tc_conv_dgrad(dy, w, dx, g, ws, math == DNB_MATH_BF16, st);
         } else {
             GatherArgs a{dy, w, nullptr, dx, g->B, g->F, g->OH, g->OW, g->C, g->H, g->W, g->kh, g->kw,
                          1, 1, g->sy, g->sx, g->kh - 1 - g->pt, g->kw - 1 - g->pl, 0, 0.f};
@@ -450,7 +450,7 @@ int dnb_conv2d_bwd(const float* x, const float* w, const float* b, const float* 
     if (thin && !tc_wgrad) {
         // gradients already accumulated above
     } else if (tc_wgrad) {
-        rc = tc_conv_wgrad(x, dy, gw, gb, g, inv_m, ws, st);
+        rc = tc_conv_wgrad(x, dy, gw, gb, g, inv_m, ws, math == DNB_MATH_BF16, st);
     } else {
         WgradArgs wa{x, dy, gw, gb, g->B, g->C, g->H, g->W, g->F, g->OH, g->OW, g->kh, g->kw, g->sy, g->sx,
                      g->pt, g->pl, g->C * g->kh * g->kw, inv_m, 0};

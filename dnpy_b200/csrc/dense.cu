@@ -331,7 +331,7 @@ int dnb_dense_fwd(const float* x, const float* w, const float* b, float* y,
         DNB_LAUNCH_CHECK("dense_fwd");
         return DNB_OK;
     }
-    if (math == DNB_MATH_TF32 && tc_gemm_supported(B, out, in, /*a_kmajor*/ true, /*b_kmajor*/ false)) {
+    if (math >= DNB_MATH_TF32 && tc_gemm_supported(B, out, in, /*a_kmajor*/ true, /*b_kmajor*/ false)) {
         // Y[B,out] = X[B,in] . W[in,out]: A is K-major, B is N-major (row-major [K,N])
         return tc_gemm(x, w, y, B, out, in, TC_A_KMAJOR | TC_B_NMAJOR, b, nullptr, 0.f, 0.f, 0.f, S(stream));
     }
@@ -377,7 +377,7 @@ int dnb_dense_bwd(const float* x, const float* w, const float* b, const float* d
     }
     if (dx) {
         // dX[B,in] = dY[B,out] . W^T : B(k=o, n=i) = W[i*out + o]  -> K-major B
-        if (math == DNB_MATH_TF32 && tc_gemm_supported(B, in, out, true, true)) {
+        if (math >= DNB_MATH_TF32 && tc_gemm_supported(B, in, out, true, true)) {
             rc = tc_gemm(dy, w, dx, B, in, out, TC_A_KMAJOR | TC_B_KMAJOR, nullptr, nullptr, 0.f, 0.f, 0.f, st);
         } else {
             GemmArgs a{dy, out, 1, w, 1, out, dx, B, in, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0};
@@ -386,7 +386,7 @@ int dnb_dense_bwd(const float* x, const float* w, const float* b, const float* d
         if (rc) return rc;
     }
     // gW[in,out] += (X^T[in,B] . dY[B,out] + reg) * inv_m : A(m=i,k=b) = X[b*in + i]  -> M-major A
-    if (math == DNB_MATH_TF32 && tc_gemm_supported(in, out, B, false, false)) {
+    if (math >= DNB_MATH_TF32 && tc_gemm_supported(in, out, B, false, false)) {
         rc = tc_gemm(x, dy, gw, in, out, B, TC_A_MMAJOR | TC_B_NMAJOR | TC_ACCUM_GRAD, nullptr, w, inv_m,
                      reg_w.l1 * reg_scale, reg_w.l2 * reg_scale, st);
     } else {

@@ -37,8 +37,9 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k) {
 // 16-byte chunk of the im2col tile (4 consecutive k) belongs to ONE tap: one bounds test per chunk.
 // mode 0 (forward): Wp[f][tap*cp + c]  = W[f][c][i][j]
 // mode 1 (dgrad)  : Wp[c][tap*fp + f]  = W[f][c][kh-1-i][kw-1-j]
+// bf: write BF16 (operands of the BF16 shifted-view kernels) instead of fp32
 __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int F, int C, int kh, int kw,
-                                    int n_pad, int k_pad, int cp, int mode) {
+                                    int n_pad, int k_pad, int cp, int mode, int bf) {
     const int total = n_pad * k_pad;
     const int khw = kh * kw;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -53,7 +54,8 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restri
                 if (n < C && ch < F) v = w[(((size_t)ch * C + n) * kh + (kh - 1 - i)) * kw + (kw - 1 - j)];
             }
         }
-        wp[e] = v;
+        if (bf) reinterpret_cast<__nv_bfloat16*>(wp)[e] = __float2bfloat16_rn(v);
+        else wp[e] = v;
     }
 }
 
@@ -586,27 +588,29 @@ bool tc_conv_supported(const dnb_win_t* g, int kind) {
     return mt <= 3 && mt * bn <= 512 && g->F <= 128 * 8;
 }
 
-int tc_conv_fwd(const float* x, const float* w, const float* b, float* y, const dnb_win_t* g, void* ws, cudaStream_t st) {
+int tc_conv_fwd(const float* x, const float* w, const float* b, float* y, const dnb_win_t* g, void* ws, bool bf16, cudaStream_t st) {
     if (!ws) return set_err(DNB_ERR_INVALID, "conv2d_fwd(tf32): workspace required");
     const int cp = round_up(g->C, 4), Kp = round_up(cp * g->kh * g->kw, CBK), n_pad = round_up(g->F, 128);
     float* wp = static_cast<float*>(ws);
-    prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, cp, 0);
+    const bool sv = !getenv("DNB_NO_SV") && tc_conv_sv_supported(g, false);
+    const bool bf = bf16 && sv && tc_conv_sv_bf16_supported(g, false);
+    prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, cp, 0, bf);
     DNB_LAUNCH_CHECK("conv2d_prep_weights");
-    if (!getenv("DNB_NO_SV") && tc_conv_sv_supported(g, false))
-        return tc_conv_sv_run("tc_conv2d_fwd_sv", x, wp, n_pad, Kp, b, (float)(g->C * g->kh * g->kw), y, g, false, st);
+    if (sv) return tc_conv_sv_run("tc_conv2d_fwd_sv", x, wp, n_pad, Kp, b, (float)(g->C * g->kh * g->kw), y, g, false, bf, st);
     ConvGemmParams p{x, y, b, g->B, g->C, g->H, g->W, g->F, g->OH, g->OW, g->kh, g->kw, cp, Kp,
                      g->sy, g->sx, 1, 1, g->pt, g->pl, (float)(g->C * g->kh * g->kw)};
     return run_gather("tc_conv2d_fwd", wp, n_pad, p, st);
 }
 
-int tc_conv_dgrad(const float* dy, const float* w, float* dx, const dnb_win_t* g, void* ws, cudaStream_t st) {
+int tc_conv_dgrad(const float* dy, const float* w, float* dx, const dnb_win_t* g, void* ws, bool bf16, cudaStream_t st) {
     if (!ws) return set_err(DNB_ERR_INVALID, "conv2d_bwd(tf32): workspace required");
     const int cp = round_up(g->F, 4), Kp = round_up(cp * g->kh * g->kw, CBK), n_pad = round_up(g->C, 128);
     float* wp = static_cast<float*>(ws) + ws_fwd_floats(g);
-    prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, cp, 1);
+    const bool sv = !getenv("DNB_NO_SV") && tc_conv_sv_supported(g, true);
+    const bool bf = bf16 && sv && tc_conv_sv_bf16_supported(g, true);
+    prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, cp, 1, bf);
     DNB_LAUNCH_CHECK("conv2d_prep_weights_t");
-    if (!getenv("DNB_NO_SV") && tc_conv_sv_supported(g, true))
-        return tc_conv_sv_run("tc_conv2d_bwd_data_sv", dy, wp, n_pad, Kp, nullptr, 0.f, dx, g, true, st);
+    if (sv) return tc_conv_sv_run("tc_conv2d_bwd_data_sv", dy, wp, n_pad, Kp, nullptr, 0.f, dx, g, true, bf, st);
     ConvGemmParams p{dy, dx, nullptr, g->B, g->F, g->OH, g->OW, g->C, g->H, g->W, g->kh, g->kw, cp, Kp,
                      1, 1, g->sy, g->sx, g->kh - 1 - g->pt, g->kw - 1 - g->pl, 0.f};
     return run_gather("tc_conv2d_bwd_data", wp, n_pad, p, st);
@@ -630,9 +634,9 @@ static int launch_wgrad(const CUtensorMap& td, WgradParams p, int fb, cudaStream
 }
 
 int tc_conv_wgrad(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, void* ws,
-                  cudaStream_t st) {
+                  bool bf16, cudaStream_t st) {
     (void)ws;
-    if (tc_conv_wgrad_sv_supported(g)) return tc_conv_wgrad_sv(x, dy, gw, gb, g, inv_m, st);
+    if (tc_conv_wgrad_sv_supported(g)) return tc_conv_wgrad_sv(x, dy, gw, gb, g, inv_m, bf16, st);
     const int K = g->C * g->kh * g->kw;
     const int npx = g->OH * g->OW;
     const int mt = (K + 1 + CBM - 1) / CBM;

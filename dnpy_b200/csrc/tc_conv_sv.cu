@@ -35,12 +35,13 @@
 #include "tc_conv.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 
 namespace dnb {
 namespace tc {
 
 struct SvParams {
-    float* dst; const float* bias;
+    float* dst; const float* bias; const float* src;
     int B, Cs, Hs, Ws, Cd, Hd, Wd, kh, kw;
     int off_y, off_x;            // placement of the source inside the padded plane
     int TH, nbands;              // output rows per band, bands per image
@@ -52,9 +53,16 @@ struct SvParams {
     long units;                  // B * nbands
     int nraw;                    // raw TMA stages in flight (2..4): as many as fit, the loads are latency bound
     int flat;                    // source map is (H*W, C, B): a band of a channel is ONE contiguous row of the box
+    int bf;                      // operands staged as BF16: 64-byte rows (64B swizzle), K = 16 per MMA — half the shared-memory
+                                 // operand traffic (what these kernels are bound by) and half the MMA issue count
+    int bulk;                    // one band per image: the unit's source (all channels) is ONE contiguous 1-D bulk copy, the
+                                 // halo rows are never staged (they are part of the zero ring of the image buffers)
     int debug;                   // timing experiments (DNB_SV_DEBUG): 1 no stores, 2 no MMAs, 4 no row-shift shuffles, 8 no transposition
     float bias_k;
+    unsigned long long* prof;    // DNB_SV_PROF: per-role clock64 totals of CTA 0 (wait vs work), see tc_conv_sv_run
 };
+#define SV_T0() const long long _t0 = p.prof ? clock64() : 0
+#define SV_ACC(var) do { if (p.prof) var += clock64() - _t0; } while (0)
 
 constexpr int SV_TR = 4, SV_EPI = 8;                      // transposer / epilogue warps
 constexpr int SV_W_TMA = 0, SV_W_MMA = 1, SV_W_TR0 = 2, SV_W_EPI0 = SV_W_TR0 + SV_TR;
@@ -89,22 +97,35 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NC]) 
     }
 }
 
-template <int BN, bool K33, int CB, bool JF>
+template <bool BF> __device__ __forceinline__ void sv_mma_init(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc) {
+    if constexpr (BF) mma_bf16_init(d, a, b, idesc); else mma_tf32_init(d, a, b, idesc);
+}
+template <bool BF> __device__ __forceinline__ void sv_mma_acc(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc) {
+    if constexpr (BF) mma_bf16_acc(d, a, b, idesc); else mma_tf32_acc(d, a, b, idesc);
+}
+
+template <int BN, bool K33, int CB, bool JF, bool BF>
 __global__ void __launch_bounds__(SV_THREADS, 1)
 tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, SvParams p) {
     constexpr int ACC = JF ? 3 * BN : BN;                 // TMEM columns of one accumulator stage
     constexpr uint32_t TMEM_COLS = (2 * ACC <= 32) ? 32 : (2 * ACC <= 64) ? 64 : (2 * ACC <= 128) ? 128 : (2 * ACC <= 256) ? 256 : 512;
     static_assert(2 * ACC <= 512, "two accumulator stages must fit TMEM");
     static_assert(!JF || (K33 && CB > 0), "column-tap folding is a 3x3 specialisation");
-    constexpr int W_KB = BN * 128;                        // bytes of one K block of filters
+    constexpr int ROWB = BF ? 64 : 128;                   // bytes of a staged row: 32 channels of one pixel / one filter
+    constexpr int ROWU = ROWB >> 4;                       // ... in descriptor address units
+    constexpr int KS = BF ? 2 : 4;                        // MMAs per 32-channel block (K = 16 bf16 / 8 tf32 = 32 bytes each)
+    constexpr uint32_t SBO = BF ? 512 : 1024, LAYOUT = BF ? LAYOUT_SW64 : LAYOUT_SW128;
+    static_assert(!BF || JF, "the BF16 variant is instantiated for the column-folded 3x3 case only");
+    constexpr int W_KB = BN * ROWB;                       // bytes of one K block of filters
     constexpr int NC = JF ? (BN >= 32 ? 16 : BN / 2) : (BN >= 64 ? 32 : BN / 2);      // TMEM columns per epilogue pass
     constexpr int NPASS = BN / 2 / NC;                    // passes per epilogue warp (its half of the BN columns)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int cblks = p.Cs >> 5;
-    const uint32_t region_bytes = (uint32_t)p.region_rows * 128;
+    const uint32_t region_bytes = (uint32_t)p.region_rows * ROWB;
     const uint32_t buf_bytes = ((region_bytes * cblks + 1023) / 1024) * 1024;
-    const uint32_t box_bytes = (uint32_t)p.Ws * p.PH * 32 * 4;                 // one 32-channel raw block
+    const int raw_rows = p.bulk ? p.Hs : p.PH;                                 // rows of a raw band
+    const uint32_t box_bytes = (uint32_t)p.Ws * raw_rows * 32 * 4;             // one 32-channel raw block
     const uint32_t raw_bytes = ((box_bytes * cblks + 127) / 128) * 128;
     uint8_t* sW = smem;                                    // [nkb][BN x 128 B]
     uint8_t* sX = sW + (size_t)p.nkb * W_KB;               // 2 buffers x cblks regions (swizzled NHWC)
@@ -150,11 +171,14 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // ===================== TMA producer: raw NCHW band of every unit =====================
         if (elect_one()) {
             int it = 0, rs = 0, rph = 0;                              // raw stage and its phase parity
+            long long w_re = 0;
             for (long u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
-                if (it >= p.nraw) mbar_wait(&raw_empty[rs], rph ^ 1);
+                if (it >= p.nraw) { SV_T0(); mbar_wait(&raw_empty[rs], rph ^ 1); SV_ACC(w_re); }
                 const int b = (int)(u / p.nbands), band = (int)(u % p.nbands);
                 const int y0 = band * p.TH - p.off_y;                     // may be negative / run past Hs: zero filled
                 mbar_arrive_expect_tx(&raw_full[rs], box_bytes * cblks);
+                if (p.bulk) bulk_load_1d(sR + (size_t)rs * raw_bytes, p.src + (size_t)b * p.Cs * p.Hs * p.Ws, box_bytes * cblks, &raw_full[rs]);
+                else
                 for (int cb = 0; cb < cblks; ++cb) {
                     void* dstp = sR + (size_t)rs * raw_bytes + (size_t)cb * box_bytes;
                     if (p.flat) tma_load_3d(dstp, &tmX, y0 * p.Ws, cb * 32, b, &raw_full[rs]);
@@ -162,6 +186,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 }
                 if (++rs == p.nraw) { rs = 0; rph ^= 1; }
             }
+            if (p.prof && blockIdx.x == 0) p.prof[0] = w_re;
         }
     } else if (warp == SV_W_MMA) {
         // ===================== filter TMA (once) + MMA issue =====================
@@ -176,22 +201,25 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         }
         __syncwarp();
         mbar_wait(w_full, 0);
-        const uint32_t idesc = make_idesc_tf32(128, ACC, 0, 0), idesc64 = make_idesc_tf32(64, ACC, 0, 0);
-        const uint64_t w_d0 = make_smem_desc(smem_u32(sW), 16, 1024);
-        const uint32_t pw8 = (uint32_t)p.PW * 8, region16 = region_bytes >> 4;
+        const uint32_t idesc = BF ? make_idesc_bf16(128, ACC, 0, 0) : make_idesc_tf32(128, ACC, 0, 0);
+        const uint32_t idesc64 = BF ? make_idesc_bf16(64, ACC, 0, 0) : make_idesc_tf32(64, ACC, 0, 0);
+        const uint64_t w_d0 = make_smem_desc(smem_u32(sW), 16, SBO, LAYOUT);
+        const uint32_t pw8 = (uint32_t)p.PW * ROWU, region16 = region_bytes >> 4;
         int it = 0, tcount = 0;
+        long long w_xf = 0, w_ae = 0;
+        const long long t_begin = p.prof ? clock64() : 0;
         for (long u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
             const int s = it & 1;
-            mbar_wait(&x_full[s], (it >> 1) & 1);
+            { SV_T0(); mbar_wait(&x_full[s], (it >> 1) & 1); SV_ACC(w_xf); }
             tc_fence_after();
-            const uint64_t x_d0 = make_smem_desc(smem_u32(sX + (size_t)s * buf_bytes), 16, 1024);
+            const uint64_t x_d0 = make_smem_desc(smem_u32(sX + (size_t)s * buf_bytes), 16, SBO, LAYOUT);
             for (int t = 0; t < p.tiles; ++t, ++tcount) {
                 const int as = tcount & 1;
-                if (tcount >= 2) { mbar_wait(&acc_empty[as], ((tcount >> 1) - 1) & 1); tc_fence_after(); }
+                if (tcount >= 2) { SV_T0(); mbar_wait(&acc_empty[as], ((tcount >> 1) - 1) & 1); tc_fence_after(); SV_ACC(w_ae); }
                 const uint32_t d_t = tmem_base + as * ACC;
                 const uint32_t idc = (p.last64 && t == p.tiles - 1) ? idesc64 : idesc;
                 // descriptor address fields only ever grow by < 256 KB >> 4: a plain 64-bit add never carries out
-                const uint64_t a_t = x_d0 + (uint64_t)((uint32_t)t * (128 * 8));
+                const uint64_t a_t = x_d0 + (uint64_t)((uint32_t)t * (128 * ROWU));
                 // ONE elected-thread region per tile (ptxas keeps the operands in uniform registers only when the
                 // branch is on the elect itself); inside it the 3x3 case is a straight line of MMAs
                 if (elect_one()) {
@@ -203,10 +231,9 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                             for (int cb = 0; cb < CB; ++cb) {
                                 const uint64_t a = a_t + (uint64_t)((uint32_t)i * pw8) + (uint64_t)((uint32_t)cb * region16);
                                 const uint64_t bw = w_d0 + (uint64_t)((i * CB + cb) * 3 * (W_KB >> 4));
-                                if (i == 0 && cb == 0) mma_tf32_init(d_t, a, bw, idc); else mma_tf32_acc(d_t, a, bw, idc);
-                                mma_tf32_acc(d_t, a + 2, bw + 2, idc);
-                                mma_tf32_acc(d_t, a + 4, bw + 4, idc);
-                                mma_tf32_acc(d_t, a + 6, bw + 6, idc);
+                                if (i == 0 && cb == 0) sv_mma_init<BF>(d_t, a, bw, idc); else sv_mma_acc<BF>(d_t, a, bw, idc);
+#pragma unroll
+                                for (int ks = 1; ks < KS; ++ks) sv_mma_acc<BF>(d_t, a + 2 * ks, bw + 2 * ks, idc);
                             }
                     } else if (K33 && CB > 0) {
 #pragma unroll
@@ -246,6 +273,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 __syncwarp();
             }
         }
+        if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[1] = w_xf; p.prof[2] = w_ae; p.prof[3] = clock64() - t_begin; }
     } else if (warp < SV_W_EPI0) {
         // ===================== transposers: raw NCHW (shared) -> swizzled NHWC (shared) =====================
         // task = (pixel pp of the PH x Ws band, channel quad, channel block); lanes run along pp: the four LDS of a task
@@ -253,8 +281,11 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // every unit (fixed geometry): decode it ONCE.
         const int ttid = tid - SV_W_TR0 * 32;
         constexpr int LT = SV_TR * 32;
-        const int npix = p.PH * p.Ws;
-        const int tasks = npix * 8 * cblks;
+        constexpr int CPT = BF ? 8 : 4;                      // channels per task: one 16-byte chunk of the staged row
+        constexpr int NCH = 32 / CPT;                        // chunks per 32-channel block
+        constexpr int GRP = 16 / CPT;                        // tasks per batch: 16 loads in flight, then GRP stores
+        const int npix = raw_rows * p.Ws;
+        const int tasks = npix * NCH * cblks;
         const uint32_t ch_stride = (uint32_t)npix * 4;       // bytes between channels of the raw band
         uint32_t t_src[SV_TB], t_dst[SV_TB];
 #pragma unroll
@@ -263,39 +294,49 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             t_src[r] = 0; t_dst[r] = 0xffffffffu;
             if (t < tasks) {
                 const int pp = t % npix, qc = t / npix;
-                const int quad = qc & 7, cb = qc >> 3;
+                const int quad = qc % NCH, cb = qc / NCH;
                 const int rr = pp / p.Ws, x = pp - rr * p.Ws;
-                const int row = rr * p.PW + x + p.off_x;     // row of the padded band inside a region
-                t_src[r] = (uint32_t)cb * box_bytes + (uint32_t)(quad * 4) * ch_stride + (uint32_t)pp * 4;
-                t_dst[r] = (uint32_t)cb * region_bytes + (uint32_t)row * 128 + (((quad ^ (row & 7)) & 7) << 4);
+                const int row = (rr + (p.bulk ? p.off_y : 0)) * p.PW + x + p.off_x;     // row of the padded band inside a region
+                t_src[r] = (uint32_t)cb * box_bytes + (uint32_t)(quad * CPT) * ch_stride + (uint32_t)pp * 4;
+                t_dst[r] = (uint32_t)cb * region_bytes + (uint32_t)row * ROWB
+                         + (BF ? (((quad ^ (row >> 1)) & 3) << 4) : (((quad ^ (row & 7)) & 7) << 4));
             }
         }
         int it = 0, rs = 0, rph = 0;
+        long long w_rf = 0, w_xe = 0;
+        const long long t_begin = p.prof ? clock64() : 0;
         for (long u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
             const int s = it & 1;
-            mbar_wait(&raw_full[rs], rph);
-            if (it >= 2) mbar_wait(&x_empty[s], ((it >> 1) - 1) & 1);
+            { SV_T0(); mbar_wait(&raw_full[rs], rph); SV_ACC(w_rf); }
+            if (it >= 2) { SV_T0(); mbar_wait(&x_empty[s], ((it >> 1) - 1) & 1); SV_ACC(w_xe); }
             const uint32_t raw_s = smem_u32(sR + (size_t)rs * raw_bytes), buf_s = smem_u32(sX + (size_t)s * buf_bytes);
             if (!(p.debug & 8))
 #pragma unroll
-            for (int r0 = 0; r0 < SV_TB; r0 += 4) {               // 16 loads in flight, then 4 stores
-                float4 v[4];
+            for (int r0 = 0; r0 < SV_TB; r0 += GRP) {             // 16 loads in flight, then GRP stores
+                float v[GRP][CPT];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                for (int r = 0; r < GRP; ++r) {
                     if (t_dst[r0 + r] != 0xffffffffu) {
                         const uint32_t a = raw_s + t_src[r0 + r];
-                        v[r].x = lds32(a); v[r].y = lds32(a + ch_stride); v[r].z = lds32(a + 2 * ch_stride); v[r].w = lds32(a + 3 * ch_stride);
+#pragma unroll
+                        for (int c = 0; c < CPT; ++c) v[r][c] = lds32(a + c * ch_stride);
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    if (t_dst[r0 + r] != 0xffffffffu) sts128(buf_s + t_dst[r0 + r], v[r]);
+                for (int r = 0; r < GRP; ++r)
+                    if (t_dst[r0 + r] != 0xffffffffu) {
+                        if constexpr (BF)
+                            sts128u(buf_s + t_dst[r0 + r], pack_bf16x2(v[r][0], v[r][1]), pack_bf16x2(v[r][2], v[r][3]),
+                                    pack_bf16x2(v[r][4 % CPT], v[r][5 % CPT]), pack_bf16x2(v[r][6 % CPT], v[r][7 % CPT]));
+                        else sts128(buf_s + t_dst[r0 + r], make_float4(v[r][0], v[r][1], v[r][2], v[r][3]));
+                    }
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) { mbar_arrive(&x_full[s]); mbar_arrive(&raw_empty[rs]); }
             if (++rs == p.nraw) { rs = 0; rph ^= 1; }
         }
+        if (p.prof && blockIdx.x == 0 && ttid == 0) { p.prof[4] = w_rf; p.prof[5] = w_xe; p.prof[6] = clock64() - t_begin; }
     } else {
         // ===================== epilogue: TMEM -> NCHW global (8 warps: lane quadrant x column half) =====================
         const int q = warp & 3;                             // TMEM lane quadrant this warp may access
@@ -303,6 +344,8 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const size_t plane_d = (size_t)p.Hd * p.Wd;
         const uint32_t s_bias_u32 = smem_u32(s_bias);
         int tcount = 0;
+        long long w_af = 0;
+        const long long t_begin = p.prof ? clock64() : 0;
         for (long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const int b = (int)(u / p.nbands), band = (int)(u % p.nbands);
             for (int t = 0; t < p.tiles; ++t, ++tcount) {
@@ -314,7 +357,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 const int y = band * p.TH + oy;
                 const bool valid = (!t64 || lane < 16) && oy < p.TH && y < p.Hd && ox < p.Wd;
                 float* dp = p.dst + ((size_t)b * p.Cd) * plane_d + (valid ? (size_t)y * p.Wd + ox : 0);
-                mbar_wait(&acc_full[as], (tcount >> 1) & 1);
+                { SV_T0(); mbar_wait(&acc_full[as], (tcount >> 1) & 1); SV_ACC(w_af); }
                 tc_fence_after();
 #pragma unroll
                 for (int ps = 0; ps < NPASS; ++ps) {
@@ -368,6 +411,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 if (lane == 0) mbar_arrive(&acc_empty[as]);
             }
         }
+        if (p.prof && blockIdx.x == 0 && lane == 0 && warp == SV_W_EPI0) { p.prof[7] = w_af; p.prof[8] = clock64() - t_begin; p.prof[9] = tcount; }
     }
     tc_fence_before();
     __syncthreads();
@@ -376,10 +420,11 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
 static size_t sv_smem_bytes(const SvParams& p, int bn) {
     const int cblks = p.Cs / 32;
-    const size_t region = (size_t)p.region_rows * 128;
+    const size_t rowb = p.bf ? 64 : 128;
+    const size_t region = (size_t)p.region_rows * rowb;
     const size_t buf = ((region * cblks + 1023) / 1024) * 1024;
-    const size_t raw = (((size_t)p.Ws * p.PH * 32 * 4) * cblks + 127) / 128 * 128;
-    return (size_t)p.nkb * bn * 128 + 2 * buf + (size_t)p.nraw * raw + 192 + (size_t)(bn < 32 ? 32 : bn) * 4 + 1024;
+    const size_t raw = (((size_t)p.Ws * (p.bulk ? p.Hs : p.PH) * 32 * 4) * cblks + 127) / 128 * 128;
+    return (size_t)p.nkb * bn * rowb + 2 * buf + (size_t)p.nraw * raw + 192 + (size_t)(bn < 32 ? 32 : bn) * 4 + 1024;
 }
 
 // column-tap folding applies to 3x3 kernels whose padded row fits a pitch that divides 32, with 3*BN*2 <= 512 TMEM columns
@@ -402,12 +447,13 @@ static bool sv_plan(SvParams& p, int bn) {
         q.last64 = (rows - (q.tiles - 1) * 128) <= 64 && !(jf && q.PW != 16);
         q.region_rows = ((q.tiles - 1) * 128 + (q.last64 ? 64 : 128) + (p.kh - 1) * q.PW + p.kw + 7) & ~7;
         q.nraw = 2;
+        q.bulk = q.nbands == 1 && ((long)p.Cs * p.Hs * p.Ws) % 4 == 0 && !getenv("DNB_SV_NOBULK");
     };
     for (int th = p.Hd; th >= 1; --th) {
         SvParams q = p;
         shape(q, th);
         if (q.PH > 256 || p.Ws > 256) continue;                                            // TMA box limits
-        if ((long)q.PH * p.Ws * 8 * (p.Cs / 32) > (long)SV_TB * SV_TR * 32) continue;      // transposer task table
+        if ((long)(q.bulk ? p.Hs : q.PH) * p.Ws * 8 * (p.Cs / 32) > (long)SV_TB * SV_TR * 32) continue;      // transposer task table
         if (sv_smem_bytes(q, bn) > budget) continue;
         const long cost = (long)q.nbands * (2 * q.tiles - q.last64);                       // in units of 64 MMA rows
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_th = th; }
@@ -421,12 +467,12 @@ static bool sv_plan(SvParams& p, int bn) {
 
 static int pick_bn_sv(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128)); }
 
-template <int BN, bool K33, int CB, bool JF>
+template <int BN, bool K33, int CB, bool JF, bool BF = false>
 static int sv_launch_k(const char* name, const CUtensorMap& tw, const CUtensorMap& tx, const SvParams& p, cudaStream_t st) {
     const size_t smem = sv_smem_bytes(p, BN);
-    cudaFuncSetAttribute(tc_conv_sv_kernel<BN, K33, CB, JF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(tc_conv_sv_kernel<BN, K33, CB, JF, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = (int)std::min<long>(p.units, kNumSMs);
-    tc_conv_sv_kernel<BN, K33, CB, JF><<<grid, SV_THREADS, smem, st>>>(tw, tx, p);
+    tc_conv_sv_kernel<BN, K33, CB, JF, BF><<<grid, SV_THREADS, smem, st>>>(tw, tx, p);
     DNB_LAUNCH_CHECK(name);
     return DNB_OK;
 }
@@ -435,6 +481,10 @@ template <int BN>
 static int sv_launch(const char* name, const CUtensorMap& tw, const CUtensorMap& tx, const SvParams& p, cudaStream_t st) {
     if constexpr (BN <= 64) {
         if (sv_jfold(p, BN)) {
+            if (p.bf) {
+                if (p.Cs == 32) return sv_launch_k<BN, true, 1, true, true>(name, tw, tx, p, st);
+                return sv_launch_k<BN, true, 2, true, true>(name, tw, tx, p, st);
+            }
             if (p.Cs == 32) return sv_launch_k<BN, true, 1, true>(name, tw, tx, p, st);
             return sv_launch_k<BN, true, 2, true>(name, tw, tx, p, st);
         }
@@ -457,6 +507,13 @@ static SvParams sv_make(const dnb_win_t* g, bool dgrad) {
     return p;
 }
 
+bool tc_conv_sv_bf16_supported(const dnb_win_t* g, bool dgrad) {
+    if (getenv("DNB_SV_NOBF16") || !tc_conv_sv_supported(g, dgrad)) return false;
+    SvParams p = sv_make(g, dgrad);
+    const int bn = pick_bn_sv(p.Cd);
+    return bn <= 64 && sv_jfold(p, bn);
+}
+
 bool tc_conv_sv_supported(const dnb_win_t* g, bool dgrad) {
     if (g->sy != 1 || g->sx != 1) return false;
     SvParams p = sv_make(g, dgrad);
@@ -470,18 +527,20 @@ bool tc_conv_sv_supported(const dnb_win_t* g, bool dgrad) {
     return sv_plan(p, pick_bn_sv(p.Cd));
 }
 
-int tc_conv_sv_run(const char* name, const float* src, const float* wprep, int n_pad, int Kp, const float* bias, float bias_k,
-                   float* dst, const dnb_win_t* g, bool dgrad, cudaStream_t st) {
+int tc_conv_sv_run(const char* name, const float* src, const void* wprep, int n_pad, int Kp, const float* bias, float bias_k,
+                   float* dst, const dnb_win_t* g, bool dgrad, bool bf16, cudaStream_t st) {
     SvParams p = sv_make(g, dgrad);
-    p.dst = dst; p.bias = bias; p.bias_k = bias_k;
+    p.bf = bf16 ? 1 : 0;
+    p.dst = dst; p.bias = bias; p.bias_k = bias_k; p.src = src;
     p.debug = getenv("DNB_SV_DEBUG") ? atoi(getenv("DNB_SV_DEBUG")) : 0;
     if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) return set_err(DNB_ERR_UNSUPPORTED, "%s: source tensor is not 16-byte aligned", name);
     const int bn = pick_bn_sv(p.Cd);
     if (!sv_plan(p, bn)) return set_err(DNB_ERR_UNSUPPORTED, "%s: shape does not fit the shifted-view kernel", name);
     CUtensorMap tw, tx;
-    uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)n_pad}, str[1] = {(uint64_t)Kp * 4};
+    uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)n_pad}, str[1] = {(uint64_t)Kp * (bf16 ? 2 : 4)};
     uint32_t box[2] = {32, (uint32_t)bn};
-    if (!make_tmap_f32(&tw, wprep, 2, dims, str, box)) return set_err(DNB_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", name);
+    if (!(bf16 ? make_tmap_bf16_sw64(&tw, wprep, 2, dims, str, box) : make_tmap_f32(&tw, wprep, 2, dims, str, box)))
+        return set_err(DNB_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed", name);
     // one box = a PH-row band of 32 channels, unswizzled, zero filled outside the image.  The rows of a band are
     // contiguous in NCHW: when they fit a box row (<= 256 elements) the map is (H*W, C, B) and a channel's band is ONE
     // contiguous box row (TMA moves 48-byte image rows an order of magnitude slower); otherwise (W, H, C, B).
@@ -499,12 +558,28 @@ int tc_conv_sv_run(const char* name, const float* src, const float* wprep, int n
         ok = make_tmap_f32(&tx, src, 4, xd, xs, xb, 2);
     }
     if (!ok) return set_err(DNB_ERR_CUDA, "%s: cuTensorMapEncodeTiled (source) failed", name);
-    switch (bn) {
-        case 16: return sv_launch<16>(name, tw, tx, p, st);
-        case 32: return sv_launch<32>(name, tw, tx, p, st);
-        case 64: return sv_launch<64>(name, tw, tx, p, st);
-        default: return sv_launch<128>(name, tw, tx, p, st);
+    if (getenv("DNB_SV_PROF")) {               // debugging aid (synchronises!): where each role of CTA 0 spends its clocks
+        static unsigned long long* dprof = nullptr;
+        if (!dprof) cudaMalloc(&dprof, 16 * sizeof(unsigned long long));
+        cudaMemsetAsync(dprof, 0, 16 * sizeof(unsigned long long), st);
+        p.prof = dprof;
     }
+    int rc;
+    switch (bn) {
+        case 16: rc = sv_launch<16>(name, tw, tx, p, st); break;
+        case 32: rc = sv_launch<32>(name, tw, tx, p, st); break;
+        case 64: rc = sv_launch<64>(name, tw, tx, p, st); break;
+        default: rc = sv_launch<128>(name, tw, tx, p, st); break;
+    }
+    if (p.prof && rc == DNB_OK) {
+        unsigned long long h[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, p.prof, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[sv prof] %s: tma wait raw_empty %llu | mma wait x_full %llu wait acc_empty %llu total %llu | "
+                        "transposer wait raw_full %llu wait x_empty %llu total %llu | epilogue wait acc_full %llu total %llu tiles %llu\n",
+                name, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
+    }
+    return rc;
 }
 
 }  // namespace dnb

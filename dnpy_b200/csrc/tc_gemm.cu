@@ -48,6 +48,20 @@ bool make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t*
     return r == CUDA_SUCCESS;
 }
 
+bool make_tmap_bf16_sw64(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 constexpr int BM = 128, BK = 32, STAGES = 4;
 constexpr int GEMM_THREADS = 192;     // warp 0: TMA, warp 1: MMA issue, warps 2-5: epilogue
 

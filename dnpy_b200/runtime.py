@@ -2,7 +2,10 @@
 
 ``math``          "fp32" — SIMT fp32 FMA kernels, parity rel 1e-5 vs the float64 reference;
                   "tf32" — tcgen05 tensor-core kernels for Dense / Conv2D / Pointwise (fp32
-                  storage, TF32 operands, fp32 accumulation in TMEM), parity rel 2e-2.
+                  storage, TF32 operands, fp32 accumulation in TMEM), parity rel 2e-2;
+                  "bf16" — as "tf32", with BF16 operands (fp32 storage and accumulation) in the
+                  shifted-view convolution kernels: half the shared-memory operand traffic those
+                  kernels are bound by; parity rel 2e-2.
                   Chosen once, before ``Net.build`` (env DNPY_B200_MATH or ``set_math``).
 ``maxpool_route`` "literal" (default) reproduces dnpy/layers/pooling.py:95 exactly (SURVEY Q5);
                   "per_sample" is the intended scatter-add.
@@ -15,9 +18,12 @@ import os
 from . import _lib
 
 
+_MATH_CODES = {"fp32": _lib.MATH_FP32, "tf32": _lib.MATH_TF32, "bf16": _lib.MATH_BF16}
+
+
 class _Config:
     def __init__(self):
-        self.math = _lib.MATH_TF32 if os.environ.get("DNPY_B200_MATH", "fp32").lower() == "tf32" else _lib.MATH_FP32
+        self.math = _MATH_CODES.get(os.environ.get("DNPY_B200_MATH", "fp32").lower(), _lib.MATH_FP32)
         self.maxpool_route = (_lib.ROUTE_PER_SAMPLE if os.environ.get("DNPY_B200_MAXPOOL", "literal").lower() == "per_sample"
                               else _lib.ROUTE_LITERAL)
         self.world = 1
@@ -38,13 +44,13 @@ config = _Config()
 
 def set_math(mode):
     mode = str(mode).lower()
-    if mode not in ("fp32", "tf32"):
-        raise ValueError("math must be 'fp32' or 'tf32'")
-    config.math = _lib.MATH_TF32 if mode == "tf32" else _lib.MATH_FP32
+    if mode not in _MATH_CODES:
+        raise ValueError("math must be 'fp32', 'tf32' or 'bf16'")
+    config.math = _MATH_CODES[mode]
 
 
 def get_math():
-    return "tf32" if config.math == _lib.MATH_TF32 else "fp32"
+    return {v: k for k, v in _MATH_CODES.items()}[config.math]
 
 
 def set_maxpool_route(route):

@@ -22,7 +22,9 @@
  *     DNB_ERR_CUDA -> RuntimeError — the reference's own exception types;
  *   - `math`: DNB_MATH_FP32 = SIMT fp32 FMA path (parity rel 1e-5 vs the float64
  *     reference); DNB_MATH_TF32 = tcgen05 tensor-core path, fp32 storage, TF32
- *     operands, fp32 accumulate in TMEM (parity rel 2e-2).  Chosen once per net.
+ *     operands, fp32 accumulate in TMEM (parity rel 2e-2); DNB_MATH_BF16 = the same
+ *     path with BF16 operands (still fp32 storage and fp32 accumulation, parity rel
+ *     2e-2) in the shifted-view convolution kernels, TF32 elsewhere.  Chosen once per net.
  *   - there is NO CPU fallback anywhere behind this ABI.
  */
 #ifndef DNPY_B200_H
@@ -42,6 +44,7 @@ extern "C" {
 
 #define DNB_MATH_FP32 0
 #define DNB_MATH_TF32 1
+#define DNB_MATH_BF16 2
 
 /* MaxPool2D.backward batch routing (dnpy/layers/pooling.py:95) */
 #define DNB_ROUTE_LITERAL    0   /* every sample's delta lands in sample 0, last sample wins */

@@ -8,7 +8,7 @@ from dnpy_b200.darray import DArray, stream_ptr
 from tests import topologies
 ns = topologies.product_ns(); L = ns.L
 lib = _lib.load()
-dnpy_b200.set_math("tf32")
+dnpy_b200.set_math(os.environ.get("SVMATH", "tf32"))
 B = int(os.environ.get("SVB", "8192"))
 def setup(cin, h, w, f, k, s, pad):
     l0 = L.Input(shape=(cin, h, w))

@@ -131,6 +131,10 @@ BIG_CASES = [
          kw=dict(filters=12, kernel_size=(3, 3), strides=(1, 1), padding="none")),
     dict(name="big_conv2", kind="Conv2D", in_shape=(32, 12, 12), batch=48,
          kw=dict(filters=64, kernel_size=(3, 3), strides=(1, 1), padding="same")),
+    dict(name="big_conv2_tall", kind="Conv2D", in_shape=(32, 28, 12), batch=5,       # several bands per image (no bulk path)
+         kw=dict(filters=32, kernel_size=(3, 3), strides=(1, 1), padding="same")),
+    dict(name="big_conv2_c64", kind="Conv2D", in_shape=(64, 12, 12), batch=7,        # two 32-channel blocks forward
+         kw=dict(filters=16, kernel_size=(3, 3), strides=(1, 1), padding="same")),
     dict(name="big_conv_s2", kind="Conv2D", in_shape=(32, 16, 16), batch=16,
          kw=dict(filters=64, kernel_size=(3, 3), strides=(2, 2), padding="same")),
     dict(name="big_conv_c3", kind="Conv2D", in_shape=(3, 32, 32), batch=16,
@@ -188,13 +192,15 @@ TC_KINDS = ("Dense", "Conv2D", "PointwiseConv2D")
 TOL_TF32 = 2e-2
 
 
+@pytest.mark.parametrize("math", ["tf32", "bf16"])
 @pytest.mark.parametrize("case", [c for c in cases.LAYER_CASES + BIG_CASES if c["kind"] in TC_KINDS], ids=lambda c: c["name"])
-def test_tensor_core_path_vs_oracle(case, ns):
+def test_tensor_core_path_vs_oracle(case, math, ns):
     """math="tf32": tcgen05 kernels (TF32 operands, fp32 accumulation in TMEM) for Dense / Conv2D /
     PointwiseConv2D, tolerance rel 2e-2 (BASELINE north_star); shapes the tensor path does not take
-    (tiny reductions, N < 32) transparently run the fp32 kernels."""
+    (tiny reductions, N < 32) transparently run the fp32 kernels.  math="bf16": the same with BF16 operands in
+    the shifted-view 3x3 convolution kernels (forward, data gradient, weight gradient)."""
     import dnpy_b200
-    dnpy_b200.set_math("tf32")
+    dnpy_b200.set_math(math)
     try:
         got = drive.run_layer_case(ns, case)
     finally:

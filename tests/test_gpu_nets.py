@@ -162,8 +162,9 @@ TF32_NETS = [
 ]
 
 
+@pytest.mark.parametrize("math", ["tf32", "bf16"])
 @pytest.mark.parametrize("name,kw,batch,steps", TF32_NETS, ids=[c[0] for c in TF32_NETS])
-def test_tensor_core_steps_along_the_reference_trajectory(name, kw, batch, steps, ns):
+def test_tensor_core_steps_along_the_reference_trajectory(name, kw, batch, steps, math, ns):
     """Same protocol with math="tf32" (tcgen05 Dense/Conv kernels): the loss within rel 2e-2 of the
     float64 oracle at every visited parameter state, every gradient within 2e-2 of the largest gradient
     of its layer chain (errors of ~1e-3 per TF32 contraction accumulate through the backward chain).
@@ -171,7 +172,7 @@ def test_tensor_core_steps_along_the_reference_trajectory(name, kw, batch, steps
     and gradients are compared only for the layers ABOVE the lowest pool that flipped (everything below
     it legitimately sees a different delta, massively so under the LITERAL routing)."""
     import dnpy_b200
-    dnpy_b200.set_math("tf32")
+    dnpy_b200.set_math(math)
     try:
         np.random.seed(42)
         net = topologies.BUILDERS[name](ns, **kw)
@@ -191,7 +192,7 @@ def test_tensor_core_steps_along_the_reference_trajectory(name, kw, batch, steps
             for li, (l, n) in enumerate(zip(net.fts_layers, onet.fts)):
                 if "idx" in n.cache:
                     diff = float(np.mean(np.asarray(l.output_idxs) != n.cache["idx"]))
-                    assert diff <= 0.01, (s, l.name, diff)
+                    assert diff <= (0.03 if math == "bf16" else 0.01), (s, l.name, diff)   # bf16 resolves 4e-3: more near-ties
                     if diff > 0:
                         first_ok = li + 1
             gmax = max([float(np.max(np.abs(g))) for n in onet.fts for g in n.grads.values()] + [1e-30])
