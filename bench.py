@@ -214,7 +214,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="mnist_cnn_wide", choices=list(WORKLOADS))
-    ap.add_argument("--math", default=os.environ.get("DNPY_B200_BENCH_MATH", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--math", default=os.environ.get("DNPY_B200_BENCH_MATH", "tf32"), choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--route", default="literal", choices=["literal", "per_sample"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--cpu-steps", type=int, default=3)

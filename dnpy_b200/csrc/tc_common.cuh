@@ -28,13 +28,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// The suspend-time hint lets a waiting warp sleep in hardware until the phase completes: a dozen role warps polling
+// their barriers back to back otherwise flood the shared-memory pipe the transposer / epilogue warps need.
+#ifndef DNB_MBAR_SUSPEND_NS
+#define DNB_MBAR_SUSPEND_NS 20000u
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(DNB_MBAR_SUSPEND_NS) : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug must trap (the launch fails with an error) instead of hanging the GPU.

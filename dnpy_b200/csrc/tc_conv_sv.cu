@@ -55,6 +55,8 @@ struct SvParams {
     int flat;                    // source map is (H*W, C, B): a band of a channel is ONE contiguous row of the box
     int bf;                      // operands staged as BF16: 64-byte rows (64B swizzle), K = 16 per MMA — half the shared-memory
                                  // operand traffic (what these kernels are bound by) and half the MMA issue count
+    int nout;                    // 2: the unit's output image [Cd][Hd*Wd] is staged in shared memory (double buffered) and written
+                                 // with ONE bulk store per image instead of 4-byte scattered stores (single-band units only); 0: direct
     int bulk;                    // one band per image: the unit's source (all channels) is ONE contiguous 1-D bulk copy, the
                                  // halo rows are never staged (they are part of the zero ring of the image buffers)
     int debug;                   // timing experiments (DNB_SV_DEBUG): 1 no stores, 2 no MMAs, 4 no row-shift shuffles, 8 no transposition
@@ -64,10 +66,13 @@ struct SvParams {
 #define SV_T0() const long long _t0 = p.prof ? clock64() : 0
 #define SV_ACC(var) do { if (p.prof) var += clock64() - _t0; } while (0)
 
-constexpr int SV_TR = 4, SV_EPI = 8;                      // transposer / epilogue warps
+#ifndef DNB_SV_TR
+#define DNB_SV_TR 6
+#endif
+constexpr int SV_TR = DNB_SV_TR, SV_EPI = 8;              // transposer / epilogue warps
 constexpr int SV_W_TMA = 0, SV_W_MMA = 1, SV_W_TR0 = 2, SV_W_EPI0 = SV_W_TR0 + SV_TR;
 constexpr int SV_THREADS = (2 + SV_TR + SV_EPI) * 32;
-constexpr int SV_TB = 16;                                 // transposer task slots per thread (<= 2048 tasks per unit)
+constexpr int SV_TB = ((2048 / (SV_TR * 32)) + 3) & ~3;                                  // transposer task slots per thread (<= 2048 tasks per unit)
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, int c0, int c1, int c2, int c3, uint64_t* bar) {
     asm volatile(
@@ -130,7 +135,9 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     uint8_t* sW = smem;                                    // [nkb][BN x 128 B]
     uint8_t* sX = sW + (size_t)p.nkb * W_KB;               // 2 buffers x cblks regions (swizzled NHWC)
     uint8_t* sR = sX + 2 * (size_t)buf_bytes;              // nraw raw NCHW bands
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (size_t)p.nraw * raw_bytes);
+    const uint32_t out_bytes = ((uint32_t)p.Cd * p.Hd * p.Wd * 4 + 127) & ~127u;   // one staged output image
+    uint8_t* sO = sR + (size_t)p.nraw * raw_bytes;         // nout output images
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sO + (size_t)p.nout * out_bytes);
     uint64_t* w_full = bars;
     uint64_t* raw_full = bars + 1;     // [4]
     uint64_t* raw_empty = bars + 5;    // [4]
@@ -343,11 +350,15 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int half = (warp - SV_W_EPI0) >> 2;           // which half of the BN columns
         const size_t plane_d = (size_t)p.Hd * p.Wd;
         const uint32_t s_bias_u32 = smem_u32(s_bias);
-        int tcount = 0;
-        long long w_af = 0;
+        int tcount = 0, it = 0;
+        long long w_af = 0, e_ld = 0, e_sh = 0, e_st = 0;
         const long long t_begin = p.prof ? clock64() : 0;
-        for (long u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const bool staged = p.nout == 2;
+        for (long u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
             const int b = (int)(u / p.nbands), band = (int)(u % p.nbands);
+            float* so = reinterpret_cast<float*>(sO + (size_t)(it & 1) * out_bytes);
+            // staging buffer (it & 1) is free once the issuing thread has seen the bulk store of unit it-2 finish reading it
+            if (staged) asm volatile("bar.sync 2, %0;" ::"n"(SV_EPI * 32) : "memory");
             for (int t = 0; t < p.tiles; ++t, ++tcount) {
                 const int as = tcount & 1;
                 // M=128 tile: D row r = TMEM lane r; M=64 tile: row r = lane (r/16)*32 + r%16 (16 rows per quadrant)
@@ -361,6 +372,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 tc_fence_after();
 #pragma unroll
                 for (int ps = 0; ps < NPASS; ++ps) {
+                    long long tq0 = p.prof ? clock64() : 0, tq1 = 0, tq2 = 0;
                     const int c0 = half * (BN / 2) + ps * NC;
                     const uint32_t tad = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC + c0);
                     uint32_t v[NC];
@@ -378,6 +390,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         tmem_ld_cols<NC>(tad + BN, v1);
                         tmem_ld_cols<NC>(tad + 2 * BN, v2);
                         tmem_ld_wait();
+                        if (p.prof) tq1 = clock64();
                         if (p.debug & 4) {
 #pragma unroll
                             for (int j = 0; j < NC; ++j) bv[j] += (__uint_as_float(v[j]) + __uint_as_float(v1[j])) + __uint_as_float(v2[j]);
@@ -394,7 +407,15 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < NC; ++j) bv[j] += __uint_as_float(v[j]);
                     }
-                    if (valid && !(p.debug & 1)) {
+                    if (p.prof) tq2 = clock64();
+                    if (staged) {
+                        if (valid) {
+                            float* o = so + (size_t)c0 * plane_d + (size_t)y * p.Wd + ox;
+#pragma unroll
+                            for (int j = 0; j < NC; ++j)
+                                if (c0 + NC <= p.Cd || c0 + j < p.Cd) { *o = bv[j]; o += plane_d; }
+                        }
+                    } else if (valid && !(p.debug & 1)) {
                         float* o = dp + (size_t)c0 * plane_d;
                         if (c0 + NC <= p.Cd) {
 #pragma unroll
@@ -405,12 +426,26 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                                 if (c0 + j < p.Cd) { *o = bv[j]; o += plane_d; }
                         }
                     }
+                    if (p.prof) { const long long tq3 = clock64(); e_ld += tq1 - tq0; e_sh += tq2 - tq1; e_st += tq3 - tq2; }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[as]);
             }
+            if (staged) {
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 2, %0;" ::"n"(SV_EPI * 32) : "memory");
+                if (warp == SV_W_EPI0 && lane == 0) {
+                    if (!(p.debug & 1))
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(p.dst + (size_t)b * p.Cd * plane_d), "r"(smem_u32(so)), "r"((uint32_t)(p.Cd * plane_d * 4)) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                }
+            }
         }
+        if (staged && warp == SV_W_EPI0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (p.prof && blockIdx.x == 0 && lane == 0 && warp == SV_W_EPI0) { p.prof[10] = e_ld; p.prof[11] = e_sh; p.prof[12] = e_st; }
         if (p.prof && blockIdx.x == 0 && lane == 0 && warp == SV_W_EPI0) { p.prof[7] = w_af; p.prof[8] = clock64() - t_begin; p.prof[9] = tcount; }
     }
     tc_fence_before();
@@ -424,7 +459,8 @@ static size_t sv_smem_bytes(const SvParams& p, int bn) {
     const size_t region = (size_t)p.region_rows * rowb;
     const size_t buf = ((region * cblks + 1023) / 1024) * 1024;
     const size_t raw = (((size_t)p.Ws * (p.bulk ? p.Hs : p.PH) * 32 * 4) * cblks + 127) / 128 * 128;
-    return (size_t)p.nkb * bn * rowb + 2 * buf + (size_t)p.nraw * raw + 192 + (size_t)(bn < 32 ? 32 : bn) * 4 + 1024;
+    const size_t outb = p.nout ? (size_t)p.nout * (((size_t)p.Cd * p.Hd * p.Wd * 4 + 127) & ~(size_t)127) : 0;
+    return outb + (size_t)p.nkb * bn * rowb + 2 * buf + (size_t)p.nraw * raw + 192 + (size_t)(bn < 32 ? 32 : bn) * 4 + 1024;
 }
 
 // column-tap folding applies to 3x3 kernels whose padded row fits a pitch that divides 32, with 3*BN*2 <= 512 TMEM columns
@@ -447,6 +483,7 @@ static bool sv_plan(SvParams& p, int bn) {
         q.last64 = (rows - (q.tiles - 1) * 128) <= 64 && !(jf && q.PW != 16);
         q.region_rows = ((q.tiles - 1) * 128 + (q.last64 ? 64 : 128) + (p.kh - 1) * q.PW + p.kw + 7) & ~7;
         q.nraw = 2;
+        q.nout = 0;
         q.bulk = q.nbands == 1 && ((long)p.Cs * p.Hs * p.Ws) % 4 == 0 && !getenv("DNB_SV_NOBULK");
     };
     for (int th = p.Hd; th >= 1; --th) {
@@ -460,6 +497,14 @@ static bool sv_plan(SvParams& p, int bn) {
     }
     if (!best_th) return false;
     shape(p, best_th);
+    // staged output (bulk store per image): single-band units whose image is a whole number of 16-byte quads, if two
+    // staging buffers fit next to at least two raw stages
+    // (measured on B200: SLOWER than the direct stores — conv2 forward 149 -> 212 us — the store engine finishes reading a
+    // 37 KB image too late for two buffers to hide it; kept as an experiment switch, off by default)
+    if (p.nbands == 1 && ((long)p.Cd * p.Hd * p.Wd) % 4 == 0 && getenv("DNB_SV_STAGE")) {
+        p.nout = 2;
+        if (sv_smem_bytes(p, bn) > budget) p.nout = 0;
+    }
     while (p.nraw < 4) { ++p.nraw; if (sv_smem_bytes(p, bn) > budget) { --p.nraw; break; } }
     p.units = (long)p.B * p.nbands;
     return true;
@@ -536,6 +581,7 @@ int tc_conv_sv_run(const char* name, const float* src, const void* wprep, int n_
     if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) return set_err(DNB_ERR_UNSUPPORTED, "%s: source tensor is not 16-byte aligned", name);
     const int bn = pick_bn_sv(p.Cd);
     if (!sv_plan(p, bn)) return set_err(DNB_ERR_UNSUPPORTED, "%s: shape does not fit the shifted-view kernel", name);
+    if (reinterpret_cast<uintptr_t>(dst) & 15) p.nout = 0;                     // the bulk store needs a 16-byte aligned image
     CUtensorMap tw, tx;
     uint64_t dims[2] = {(uint64_t)Kp, (uint64_t)n_pad}, str[1] = {(uint64_t)Kp * (bf16 ? 2 : 4)};
     uint32_t box[2] = {32, (uint32_t)bn};
@@ -576,8 +622,9 @@ int tc_conv_sv_run(const char* name, const float* src, const void* wprep, int n_
         cudaStreamSynchronize(st);
         cudaMemcpy(h, p.prof, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[sv prof] %s: tma wait raw_empty %llu | mma wait x_full %llu wait acc_empty %llu total %llu | "
-                        "transposer wait raw_full %llu wait x_empty %llu total %llu | epilogue wait acc_full %llu total %llu tiles %llu\n",
-                name, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
+                        "transposer wait raw_full %llu wait x_empty %llu total %llu | epilogue wait acc_full %llu total %llu tiles %llu "
+                        "(tmem ld %llu, shuffle+add %llu, store %llu)\n",
+                name, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12]);
     }
     return rc;
 }

@@ -1,4 +1,15 @@
-timeout 900 python -m pytest tests/test_gpu_layers.py -m gpu -x -q -k "tensor_core" 2>&1 | tail -5
+cp dnpy_b200/libdnpy_b200.so /tmp/lib_tr8.so
+cp scratch/libdnpy_tr4.so /tmp/lib_tr4.so; cp scratch/libdnpy_tr6.so /tmp/lib_tr6.so
+for tr in 8 4 6; do
+cp /tmp/lib_tr$tr.so dnpy_b200/libdnpy_b200.so
+echo "=== TR $tr"
 SVMATH=bf16 python scratch/sv_bench.py 0 2>&1 | grep debug
-SVMATH=tf32 python scratch/sv_bench.py 0 2>&1 | grep debug
-SVMATH=bf16 DNB_SV_PROF=1 python scratch/sv_bench.py 0 2>&1 | grep -E "wg prof\]" | tail -1
+timeout 300 python bench.py --no-cpu --math bf16 > /tmp/b.json 2>/tmp/b.err
+python - <<PY
+import json
+d=json.load(open('/tmp/b.json'))
+print(d['ms_per_step'], d['e2e']['ms_per_step'])
+for t in d['top_kernels']:
+    if '_sv' in t['kernel']: print(f"{t['ms_per_step']*1e3:8.1f} us {t['kernel']}")
+PY
+done
