@@ -1,15 +1,10 @@
-cp dnpy_b200/libdnpy_b200.so /tmp/lib_tr8.so
-cp scratch/libdnpy_tr4.so /tmp/lib_tr4.so; cp scratch/libdnpy_tr6.so /tmp/lib_tr6.so
-for tr in 8 4 6; do
-cp /tmp/lib_tr$tr.so dnpy_b200/libdnpy_b200.so
-echo "=== TR $tr"
-SVMATH=bf16 python scratch/sv_bench.py 0 2>&1 | grep debug
-timeout 300 python bench.py --no-cpu --math bf16 > /tmp/b.json 2>/tmp/b.err
+timeout 300 python bench.py --no-cpu --math bf16 > gpurun_out/bench_c.json 2>gpurun_out/bench_c.err; echo rc $?
 python - <<PY
 import json
-d=json.load(open('/tmp/b.json'))
-print(d['ms_per_step'], d['e2e']['ms_per_step'])
+d=json.load(open('gpurun_out/bench_c.json'))
+print(d['ms_per_step'], d['e2e']['ms_per_step'], d['value'])
+tot=0
 for t in d['top_kernels']:
-    if '_sv' in t['kernel']: print(f"{t['ms_per_step']*1e3:8.1f} us {t['kernel']}")
+    tot+=t['ms_per_step']; print(f"{t['ms_per_step']*1e3:8.1f} us {t['share']*100:5.1f}% {t['kernel']}")
+print('sum top', tot)
 PY
-done
