@@ -3,10 +3,10 @@
 // large operand is X (forward, dW) or dX (backward), and each kernel streams it exactly once with 128-bit
 // accesses, OUT known at compile time so every accumulator and weight index is a register.
 //
-//   forward : CTA = 32 rows x 8 feature lanes; 8 consecutive threads read 128 contiguous bytes of one row
-//             (16 LDG.128 in flight per thread), W arrives in 512-feature chunks through a double-buffered
-//             cp.async.bulk (TMA) stage and is read back as the thread's 4*OUT contiguous floats; the 8 lanes
-//             of a row are reduced with 3 shuffle steps.  Deterministic (no atomics).
+//   forward : a warp owns 8 rows, its lanes the feature quads lane, lane+32, ... (512 contiguous bytes per row and load,
+//             16 LDG.128 in flight per thread); W arrives in 512-feature chunks through a double-buffered
+//             cp.async.bulk (TMA) stage, the 4*OUT weights of a quad are read once and reused for the 8 rows; the lanes
+//             of a row are reduced with 5 shuffle steps.  Deterministic (no atomics).
 //   dX      : a thread keeps the 4 x OUT weights of its feature quad in registers and walks 32 rows whose dY
 //             sits in shared memory; one STG.128 per row.
 //   dW / db : a warp owns 32 feature quads (512 contiguous bytes per row), the 8 warps of a CTA take
@@ -20,7 +20,7 @@
 namespace dnb {
 
 constexpr int HD_MAXOUT = 16;
-constexpr int HF_ROWS = 32, HF_CH = 512;          // forward: rows per CTA, features per W chunk
+constexpr int HF_CH = 512;                        // forward: features per W chunk
 constexpr int HX_ROWS = 32;                       // dX: rows per thread
 constexpr int HW_ROWS = 256;                      // dW: rows per CTA
 
@@ -30,17 +30,25 @@ __device__ __forceinline__ void hd_bulk_g2s(void* dst, const void* src, uint32_t
 }
 
 // ---- forward ---------------------------------------------------------------------------------------
+// A warp owns HF_RPW rows; its 32 lanes take the feature quads lane, lane+32, ... of every row (512 contiguous bytes per
+// row and load).  The 4*OUT weights of a quad are read ONCE from shared memory (OUT LDS.128) and reused for all HF_RPW
+// rows — the previous one-row-per-thread version re-read them for every row and was bound by shared-memory wavefronts
+// (LDS.128 is served a quarter-warp at a time): 43 us for 52 MB on B200.
+constexpr int HF_RPW = 8;                         // rows per warp
+constexpr int HF_WARPS = 8;
 template <int OUT>
-__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                       const float* __restrict__ bias, float* __restrict__ y, int B, int in) {
+__global__ void __launch_bounds__(HF_WARPS * 32) head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, float* __restrict__ y, int B, int in) {
     extern __shared__ __align__(128) uint8_t hsm[];
     float (*sw)[HF_CH * OUT] = reinterpret_cast<float (*)[HF_CH * OUT]>(hsm);          // [2][HF_CH * OUT]
     uint64_t* full = reinterpret_cast<uint64_t*>(hsm + 2 * HF_CH * OUT * sizeof(float));
-    const int tid = threadIdx.x, ks = tid & 7, rl = tid >> 3;
-    const int row = blockIdx.x * HF_ROWS + rl;
-    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)min(row, B - 1) * in);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = (blockIdx.x * HF_WARPS + warp) * HF_RPW;
     const int in4 = in >> 2;
     const int nch = (in + HF_CH - 1) / HF_CH;
+    const float4* xr[HF_RPW];
+#pragma unroll
+    for (int r = 0; r < HF_RPW; ++r) xr[r] = reinterpret_cast<const float4*>(x + (size_t)min(row0 + r, B - 1) * in);
     if (tid == 0) {
         tc::mbar_init(&full[0], 1); tc::mbar_init(&full[1], 1);
         tc::fence_barrier_init();
@@ -49,9 +57,11 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
         hd_bulk_g2s(sw[0], w, bytes, &full[0]);
     }
     __syncthreads();
-    float acc[OUT];
+    float acc[HF_RPW][OUT];
 #pragma unroll
-    for (int o = 0; o < OUT; ++o) acc[o] = 0.f;
+    for (int r = 0; r < HF_RPW; ++r)
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) acc[r][o] = 0.f;
     for (int c = 0; c < nch; ++c) {
         if (c + 1 < nch) {
             __syncthreads();                               // everyone is done with buffer (c+1)&1 (chunk c-1)
@@ -62,44 +72,58 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
                 hd_bulk_g2s(sw[(c + 1) & 1], w + (size_t)c1 * OUT, bytes, &full[(c + 1) & 1]);
             }
         }
-        const int q0 = c * (HF_CH / 4);                    // first quad of the chunk
-        float4 xv[HF_CH / 32];
-#pragma unroll
-        for (int t = 0; t < HF_CH / 32; ++t) {
-            const int q = q0 + ks + 8 * t;
-            xv[t] = q < in4 ? __ldg(xr + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        tc::mbar_wait(&full[c & 1], (c >> 1) & 1);
+        const int q0 = c * (HF_CH / 4);                    // first quad of the chunk (HF_CH / 4 = 128 quads = 4 per lane)
         const float* swc = sw[c & 1];
 #pragma unroll
-        for (int t = 0; t < HF_CH / 32; ++t) {
-            if (q0 + ks + 8 * t < in4) {
-                const float4* wq = reinterpret_cast<const float4*>(swc + (ks + 8 * t) * 4 * OUT);
-                const float xs[4] = {xv[t].x, xv[t].y, xv[t].z, xv[t].w};
+        for (int h = 0; h < 2; ++h) {                      // two quads per lane at a time: 2 * HF_RPW loads in flight
+            float4 xv[2][HF_RPW];
 #pragma unroll
-                for (int m = 0; m < OUT; ++m) {
-                    const float4 w4 = wq[m];
-                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+            for (int u = 0; u < 2; ++u) {
+                const int q = q0 + lane + 32 * (2 * h + u);
 #pragma unroll
-                    for (int n = 0; n < 4; ++n) {
-                        const int f = 4 * m + n;           // flat index into [4 features][OUT]
-                        acc[f % OUT] = fmaf(xs[f / OUT], wv[n], acc[f % OUT]);
+                for (int r = 0; r < HF_RPW; ++r) xv[u][r] = q < in4 ? __ldg(xr[r] + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (h == 0) tc::mbar_wait(&full[c & 1], (c >> 1) & 1);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int ql = lane + 32 * (2 * h + u);
+                if (q0 + ql < in4) {
+                    float wr[4 * OUT];                      // [4 features][OUT], contiguous in W
+                    const float4* wq = reinterpret_cast<const float4*>(swc + ql * 4 * OUT);
+#pragma unroll
+                    for (int m = 0; m < OUT; ++m) {
+                        const float4 w4 = wq[m];
+                        wr[4 * m] = w4.x; wr[4 * m + 1] = w4.y; wr[4 * m + 2] = w4.z; wr[4 * m + 3] = w4.w;
+                    }
+#pragma unroll
+                    for (int r = 0; r < HF_RPW; ++r) {
+                        const float xs[4] = {xv[u][r].x, xv[u][r].y, xv[u][r].z, xv[u][r].w};
+#pragma unroll
+                        for (int f = 0; f < 4 * OUT; ++f) acc[r][f % OUT] = fmaf(xs[f / OUT], wr[f], acc[r][f % OUT]);
                     }
                 }
             }
         }
     }
 #pragma unroll
-    for (int o = 0; o < OUT; ++o) {
-        float v = acc[o];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        acc[o] = v;
-    }
-    if (ks == 0 && row < B) {
+    for (int r = 0; r < HF_RPW; ++r)
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) y[(size_t)row * OUT + o] = acc[o] + (bias ? bias[o] : 0.f);
+        for (int o = 0; o < OUT; ++o) {
+            float v = acc[r][o];
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            acc[r][o] = v;
+        }
+    // lane r writes row r: select its row's sums without dynamic register indexing
+#pragma unroll
+    for (int r = 0; r < HF_RPW; ++r) {
+        if (lane == r && row0 + r < B) {
+#pragma unroll
+            for (int o = 0; o < OUT; ++o) y[(size_t)(row0 + r) * OUT + o] = acc[r][o] + (bias ? bias[o] : 0.f);
+        }
     }
 }
 
@@ -153,6 +177,17 @@ __global__ void __launch_bounds__(256) head_dw_kernel(const float* __restrict__ 
     float (*red)[32][PITCH] = reinterpret_cast<float (*)[32][PITCH]>(hsm + HW_ROWS * HD_MAXOUT * sizeof(float));   // [8][32][PITCH]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int b0 = blockIdx.y * HW_ROWS, nr = min(HW_ROWS, B - b0);
+    const int in4 = in >> 2;
+    const int q = blockIdx.x * 32 + lane;
+    const bool qok = q < in4;
+    const float4* xq = reinterpret_cast<const float4*>(x + (size_t)b0 * in) + min(q, in4 - 1);
+    // the first batch of X rows is requested BEFORE dY is staged: both DRAM latencies overlap
+    float4 xn[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int r = wid + 8 * u;
+        xn[u] = (r < nr && qok) ? __ldg(xq + (size_t)r * in4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     for (int e = threadIdx.x; e < HW_ROWS * HD_MAXOUT; e += 256) {
         const int r = e / HD_MAXOUT, o = e % HD_MAXOUT;
         sd[r][o] = (r < nr && o < OUT) ? __ldg(dy + (size_t)(b0 + r) * OUT + o) : 0.f;
@@ -165,19 +200,17 @@ __global__ void __launch_bounds__(256) head_dw_kernel(const float* __restrict__ 
         if (blockIdx.y == 0) g += reg_term(bvec[threadIdx.x], bl1, bl2) * inv_m;
         atomicAdd(gb + threadIdx.x, g);
     }
-    const int in4 = in >> 2;
-    const int q = blockIdx.x * 32 + lane;
-    const bool qok = q < in4;
     float acc[4 * OUT];                                     // [4 features][OUT]
 #pragma unroll
     for (int k = 0; k < 4 * OUT; ++k) acc[k] = 0.f;
-    const float4* xq = reinterpret_cast<const float4*>(x + (size_t)b0 * in) + min(q, in4 - 1);
-    for (int r0 = wid; r0 < nr; r0 += 64) {                 // rows wid, wid+8, ... : 8 in flight
+    for (int r0 = wid; r0 < nr; r0 += 64) {                 // rows wid, wid+8, ... : 8 in use, the next 8 in flight
         float4 xv[8];
 #pragma unroll
+        for (int u = 0; u < 8; ++u) xv[u] = xn[u];
+#pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int r = r0 + 8 * u;
-            xv[u] = (r < nr && qok) ? __ldg(xq + (size_t)r * in4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int r = r0 + 64 + 8 * u;
+            xn[u] = (r < nr && qok) ? __ldg(xq + (size_t)r * in4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -235,11 +268,11 @@ bool head_supported(int B, int in, int out) {
 // returns false when the pointers are not 16-byte aligned (caller falls back)
 bool head_fwd(const float* x, const float* w, const float* b, float* y, int B, int in, int out, cudaStream_t st) {
     if (!al16(x) || !al16(w)) return false;
-    const int grid = (B + HF_ROWS - 1) / HF_ROWS;
+    const int grid = (B + HF_WARPS * HF_RPW - 1) / (HF_WARPS * HF_RPW);
     HD_DISPATCH(out, {
         const size_t smem = 2 * HF_CH * O * sizeof(float) + 16;
         if (smem > 48 * 1024) cudaFuncSetAttribute(head_fwd_kernel<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        head_fwd_kernel<O><<<grid, 256, smem, st>>>(x, w, b, y, B, in);
+        head_fwd_kernel<O><<<grid, HF_WARPS * 32, smem, st>>>(x, w, b, y, B, in);
     });
     return true;
 }

@@ -284,7 +284,9 @@ __global__ void __launch_bounds__(256) maxpool_bwd_ps_strip_kernel(const float* 
 }
 
 // LITERAL step 1: last[c,oy,ox,p] = max b with idx[b,c,oy,ox] == p  (int32, pre-filled with -1)
-// step 1b: samples [0, b_end) in chunks, only for positions step 1a could not finish (constant windows ...)
+// step 1b: samples [0, b_end) in chunks, only for positions step 1a could not finish (windows with an offset that almost
+// never wins, e.g. the zero-padded border column of a "same" convolution's output).  16 loads in flight per thread: a
+// dependent chain of single loads made this kernel pure DRAM latency (40 us for 48 MB on B200).
 __global__ void __launch_bounds__(256) maxpool_last_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ last,
                                                            const int32_t* __restrict__ done, dnb_win_t g, int bchunk, int b_end) {
     const long npos = (long)g.C * g.OH * g.OW;
@@ -294,38 +296,57 @@ __global__ void __launch_bounds__(256) maxpool_last_kernel(const int32_t* __rest
     const int b_hi = min(b_end, (int)(blockIdx.y + 1) * bchunk) - 1, b_lo = blockIdx.y * bchunk;
     // walk this chunk from its last sample down; the first hit per offset is the chunk's last
     unsigned long long seen_lo = 0ull;      // offsets 0..63 tracked in a bitmask, the rest go straight to atomicMax
-    for (int b = b_hi; b >= b_lo; --b) {
-        int p = idx[(long)b * npos + pos];
-        if (p < 64) {
-            if (seen_lo >> p & 1ull) continue;
-            seen_lo |= 1ull << p;
+    for (int b0 = b_hi; b0 >= b_lo; b0 -= 16) {
+        int pv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) pv[u] = (b0 - u >= b_lo) ? __ldg(idx + (long)(b0 - u) * npos + pos) : -1;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int p = pv[u];
+            if (p < 0) continue;
+            if (p < 64) {
+                if (seen_lo >> p & 1ull) continue;
+                seen_lo |= 1ull << p;
+            }
+            atomicMax(last + pos * P + p, b0 - u);
         }
-        atomicMax(last + pos * P + p, b);
     }
 }
-// LITERAL step 1a: the newest TOP samples decide almost every (window, offset) pair — a thread walks its window
-// position from the last sample down and stops as soon as all kh*kw offsets have been seen (plain stores: no
-// other thread owns this position).  done[pos] tells step 1b (maxpool_last_kernel over the older samples) to skip it.
-__global__ void __launch_bounds__(128) maxpool_last_top_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ last,
-                                                               int32_t* __restrict__ done, dnb_win_t g, int top) {
+// LITERAL step 1a: the newest TOP samples decide almost every (window, offset) pair.  A CTA takes 32 consecutive window
+// positions (coalesced along the position axis) and its LT_WARPS warps split the TOP newest samples between them: ONE batch
+// of TOP / LT_WARPS loads per thread instead of a serial walk, merged with shared-memory atomicMax.  done[pos] tells step 1b
+// (maxpool_last_kernel over the older samples) to skip a position whose kh*kw offsets have all been seen.
+constexpr int LT_WARPS = 16, LT_TOP = 128, LT_PER = LT_TOP / LT_WARPS;
+__global__ void __launch_bounds__(LT_WARPS * 32) maxpool_last_top_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ last,
+                                                                         int32_t* __restrict__ done, dnb_win_t g) {
+    extern __shared__ int32_t slast[];                     // [32 positions][P]
     const long npos = (long)g.C * g.OH * g.OW;
-    const long pos = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= npos) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long pos = (long)blockIdx.x * 32 + lane;
     const int P = g.kh * g.kw;
-    const unsigned long long all = P >= 64 ? ~0ull : ((1ull << P) - 1ull);
-    unsigned long long seen = 0ull;
-    const int b_lo = max(0, g.B - top);
-    for (int b0 = g.B - 1; b0 >= b_lo && seen != all; b0 -= 8) {
-        int pv[8];
+    for (int e = threadIdx.x; e < 32 * P; e += LT_WARPS * 32) slast[e] = -1;
+    __syncthreads();
+    const int b_lo = max(0, g.B - LT_TOP);
+    if (pos < npos) {
+        int pv[LT_PER];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) pv[u] = (b0 - u >= b_lo) ? __ldg(idx + (long)(b0 - u) * npos + pos) : -1;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int p = pv[u];
-            if (p >= 0 && p < 64 && !(seen >> p & 1ull)) { seen |= 1ull << p; last[pos * P + p] = b0 - u; }
+        for (int u = 0; u < LT_PER; ++u) {
+            const int b = g.B - 1 - warp - u * LT_WARPS;
+            pv[u] = b >= b_lo ? __ldg(idx + (long)b * npos + pos) : -1;
         }
+#pragma unroll
+        for (int u = 0; u < LT_PER; ++u)
+            if (pv[u] >= 0) atomicMax(&slast[lane * P + pv[u]], g.B - 1 - warp - u * LT_WARPS);
     }
-    done[pos] = (P <= 64 && seen == all) || b_lo == 0;
+    __syncthreads();
+    const long pos0 = (long)blockIdx.x * 32;
+    for (int e = threadIdx.x; e < 32 * P; e += LT_WARPS * 32)
+        if (pos0 + e / P < npos && slast[e] >= 0) last[pos0 * P + e] = slast[e];
+    if (threadIdx.x < 32 && pos < npos) {
+        bool all = true;
+        for (int p = 0; p < P; ++p) all = all && slast[lane * P + p] >= 0;
+        done[pos] = all || b_lo == 0;
+    }
 }
 // LITERAL step 2: dx[0,c,iy,ix] = sum over covering windows of dy[last, c, oy, ox]; dx[b>0] = 0
 __global__ void __launch_bounds__(256) maxpool_bwd_literal_kernel(const float* __restrict__ dy, const int32_t* __restrict__ last,
@@ -463,8 +484,9 @@ int dnb_maxpool2d_bwd(const float* dy, const int32_t* idx, float* dx, const dnb_
     cudaError_t e = cudaMemsetAsync(last, 0xff, (size_t)npos * P * sizeof(int32_t), st);     // -1
     if (e != cudaSuccess) return set_err(DNB_ERR_CUDA, "maxpool2d_bwd: %s", cudaGetErrorString(e));
     int32_t* done = last + npos * P;
-    const int top = 128, bchunk = 64;
-    maxpool_last_top_kernel<<<(unsigned)((npos + 127) / 128), 128, 0, st>>>(idx, last, done, *g, top);
+    const int top = LT_TOP, bchunk = 64;
+    DNB_CHECK_ARG((size_t)32 * P * sizeof(int32_t) <= 48 * 1024, "maxpool2d_bwd: window of %d elements is too large for the literal route", P);
+    maxpool_last_top_kernel<<<(unsigned)((npos + 31) / 32), LT_WARPS * 32, (size_t)32 * P * sizeof(int32_t), st>>>(idx, last, done, *g);
     DNB_LAUNCH_CHECK("maxpool2d_bwd_last_top");
     if (g->B > top) {
         dim3 grid((unsigned)((npos + 255) / 256), (g->B - top + bchunk - 1) / bchunk);
