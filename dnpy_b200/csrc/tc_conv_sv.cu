@@ -50,7 +50,7 @@ struct SvParams {
     int last64;                  // the last tile of a unit is an M=64 MMA (<= 64 rows left)
     int region_rows;             // rows per 32-channel region of an image buffer: tiles*128 + (kh-1)*PW + kw (multiple of 8)
     int nkb;                     // kh*kw*(Cs/32)
-    long units;                  // B * nbands
+    int units;                   // B * nbands (< 2^31, checked by sv_plan)
     int nraw;                    // raw TMA stages in flight (2..4): as many as fit, the loads are latency bound
     int flat;                    // source map is (H*W, C, B): a band of a channel is ONE contiguous row of the box
     int bf;                      // operands staged as BF16: 64-byte rows (64B swizzle), K = 16 per MMA — half the shared-memory
@@ -69,7 +69,10 @@ struct SvParams {
 #ifndef DNB_SV_TR
 #define DNB_SV_TR 6
 #endif
-constexpr int SV_TR = DNB_SV_TR, SV_EPI = 8;              // transposer / epilogue warps
+#ifndef DNB_SV_EPI
+#define DNB_SV_EPI 8
+#endif
+constexpr int SV_TR = DNB_SV_TR, SV_EPI = DNB_SV_EPI;     // transposer / epilogue warps (epilogue: a multiple of 4)
 constexpr int SV_W_TMA = 0, SV_W_MMA = 1, SV_W_TR0 = 2, SV_W_EPI0 = SV_W_TR0 + SV_TR;
 constexpr int SV_THREADS = (2 + SV_TR + SV_EPI) * 32;
 constexpr int SV_TB = ((2048 / (SV_TR * 32)) + 3) & ~3;                                  // transposer task slots per thread (<= 2048 tasks per unit)
@@ -120,10 +123,14 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     constexpr int ROWU = ROWB >> 4;                       // ... in descriptor address units
     constexpr int KS = BF ? 2 : 4;                        // MMAs per 32-channel block (K = 16 bf16 / 8 tf32 = 32 bytes each)
     constexpr uint32_t SBO = BF ? 512 : 1024, LAYOUT = BF ? LAYOUT_SW64 : LAYOUT_SW128;
-    static_assert(!BF || JF, "the BF16 variant is instantiated for the column-folded 3x3 case only");
+    static_assert(!BF || (K33 && CB > 0), "the BF16 variant is instantiated for the 3x3 cases only");
     constexpr int W_KB = BN * ROWB;                       // bytes of one K block of filters
-    constexpr int NC = JF ? (BN >= 32 ? 16 : BN / 2) : (BN >= 64 ? 32 : BN / 2);      // TMEM columns per epilogue pass
-    constexpr int NPASS = BN / 2 / NC;                    // passes per epilogue warp (its half of the BN columns)
+    // epilogue: SV_EPI / 4 warps per TMEM lane quadrant split the BN columns into PARTS slices of CW >= 8 columns
+    constexpr int PARTS = (BN / 8 < SV_EPI / 4) ? BN / 8 : SV_EPI / 4;
+    constexpr int CW = BN / PARTS;
+    constexpr int NCMAX = JF ? 16 : 32;
+    constexpr int NC = CW > NCMAX ? NCMAX : CW;           // TMEM columns per epilogue pass
+    constexpr int NPASS = CW / NC;                        // passes per epilogue warp
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int cblks = p.Cs >> 5;
@@ -179,9 +186,9 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         if (elect_one()) {
             int it = 0, rs = 0, rph = 0;                              // raw stage and its phase parity
             long long w_re = 0;
-            for (long u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
+            for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
                 if (it >= p.nraw) { SV_T0(); mbar_wait(&raw_empty[rs], rph ^ 1); SV_ACC(w_re); }
-                const int b = (int)(u / p.nbands), band = (int)(u % p.nbands);
+                const int b = p.nbands == 1 ? u : u / p.nbands, band = p.nbands == 1 ? 0 : u - b * p.nbands;
                 const int y0 = band * p.TH - p.off_y;                     // may be negative / run past Hs: zero filled
                 mbar_arrive_expect_tx(&raw_full[rs], box_bytes * cblks);
                 if (p.bulk) bulk_load_1d(sR + (size_t)rs * raw_bytes, p.src + (size_t)b * p.Cs * p.Hs * p.Ws, box_bytes * cblks, &raw_full[rs]);
@@ -215,7 +222,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         int it = 0, tcount = 0;
         long long w_xf = 0, w_ae = 0;
         const long long t_begin = p.prof ? clock64() : 0;
-        for (long u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
+        for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
             const int s = it & 1;
             { SV_T0(); mbar_wait(&x_full[s], (it >> 1) & 1); SV_ACC(w_xf); }
             tc_fence_after();
@@ -251,12 +258,11 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
                                 for (int cb = 0; cb < CB; ++cb) {
                                     const int kb = (i * 3 + j) * CB + cb;
-                                    const uint64_t a = a_i + (uint64_t)(j * 8) + (uint64_t)((uint32_t)cb * region16);
+                                    const uint64_t a = a_i + (uint64_t)(j * ROWU) + (uint64_t)((uint32_t)cb * region16);
                                     const uint64_t bw = w_d0 + (uint64_t)(kb * (W_KB >> 4));
-                                    if (kb == 0) mma_tf32_init(d_t, a, bw, idc); else mma_tf32_acc(d_t, a, bw, idc);
-                                    mma_tf32_acc(d_t, a + 2, bw + 2, idc);
-                                    mma_tf32_acc(d_t, a + 4, bw + 4, idc);
-                                    mma_tf32_acc(d_t, a + 6, bw + 6, idc);
+                                    if (kb == 0) sv_mma_init<BF>(d_t, a, bw, idc); else sv_mma_acc<BF>(d_t, a, bw, idc);
+#pragma unroll
+                                    for (int ks = 1; ks < KS; ++ks) sv_mma_acc<BF>(d_t, a + 2 * ks, bw + 2 * ks, idc);
                                 }
                         }
                     } else {
@@ -312,7 +318,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         int it = 0, rs = 0, rph = 0;
         long long w_rf = 0, w_xe = 0;
         const long long t_begin = p.prof ? clock64() : 0;
-        for (long u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
+        for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
             const int s = it & 1;
             { SV_T0(); mbar_wait(&raw_full[rs], rph); SV_ACC(w_rf); }
             if (it >= 2) { SV_T0(); mbar_wait(&x_empty[s], ((it >> 1) - 1) & 1); SV_ACC(w_xe); }
@@ -347,15 +353,22 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     } else {
         // ===================== epilogue: TMEM -> NCHW global (8 warps: lane quadrant x column half) =====================
         const int q = warp & 3;                             // TMEM lane quadrant this warp may access
-        const int half = (warp - SV_W_EPI0) >> 2;           // which half of the BN columns
+        const int part = (warp - SV_W_EPI0) >> 2;           // which slice of the BN columns (slices >= PARTS idle along)
         const size_t plane_d = (size_t)p.Hd * p.Wd;
         const uint32_t s_bias_u32 = smem_u32(s_bias);
         int tcount = 0, it = 0;
         long long w_af = 0, e_ld = 0, e_sh = 0, e_st = 0;
         const long long t_begin = p.prof ? clock64() : 0;
         const bool staged = p.nout == 2;
-        for (long u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
-            const int b = (int)(u / p.nbands), band = (int)(u % p.nbands);
+        int t_oy[4], t_ox[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const bool t64 = p.last64 && t == p.tiles - 1;
+            const int m = t * 128 + (t64 ? q * 16 + lane : q * 32 + lane);
+            t_oy[t] = m / p.PW; t_ox[t] = m - t_oy[t] * p.PW;
+        }
+        for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
+            const int b = p.nbands == 1 ? u : u / p.nbands, band = p.nbands == 1 ? 0 : u - b * p.nbands;
             float* so = reinterpret_cast<float*>(sO + (size_t)(it & 1) * out_bytes);
             // staging buffer (it & 1) is free once the issuing thread has seen the bulk store of unit it-2 finish reading it
             if (staged) asm volatile("bar.sync 2, %0;" ::"n"(SV_EPI * 32) : "memory");
@@ -363,17 +376,22 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 const int as = tcount & 1;
                 // M=128 tile: D row r = TMEM lane r; M=64 tile: row r = lane (r/16)*32 + r%16 (16 rows per quadrant)
                 const bool t64 = p.last64 && t == p.tiles - 1;
-                const int m = t * 128 + (t64 ? q * 16 + lane : q * 32 + lane);
-                const int oy = m / p.PW, ox = m - oy * p.PW;
+                // geometry of the first tiles is unit independent (select chain: no dynamic register indexing)
+                int oy = t == 0 ? t_oy[0] : t == 1 ? t_oy[1] : t == 2 ? t_oy[2] : t_oy[3];
+                int ox = t == 0 ? t_ox[0] : t == 1 ? t_ox[1] : t == 2 ? t_ox[2] : t_ox[3];
+                if (t >= 4) {
+                    const int m = t * 128 + (t64 ? q * 16 + lane : q * 32 + lane);
+                    oy = m / p.PW; ox = m - oy * p.PW;
+                }
                 const int y = band * p.TH + oy;
                 const bool valid = (!t64 || lane < 16) && oy < p.TH && y < p.Hd && ox < p.Wd;
                 float* dp = p.dst + ((size_t)b * p.Cd) * plane_d + (valid ? (size_t)y * p.Wd + ox : 0);
                 { SV_T0(); mbar_wait(&acc_full[as], (tcount >> 1) & 1); SV_ACC(w_af); }
                 tc_fence_after();
 #pragma unroll
-                for (int ps = 0; ps < NPASS; ++ps) {
+                for (int ps = 0; ps < (part < PARTS ? NPASS : 0); ++ps) {
                     long long tq0 = p.prof ? clock64() : 0, tq1 = 0, tq2 = 0;
-                    const int c0 = half * (BN / 2) + ps * NC;
+                    const int c0 = part * CW + ps * NC;
                     const uint32_t tad = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC + c0);
                     uint32_t v[NC];
                     tmem_ld_cols<NC>(tad, v);
@@ -464,7 +482,10 @@ static size_t sv_smem_bytes(const SvParams& p, int bn) {
 }
 
 // column-tap folding applies to 3x3 kernels whose padded row fits a pitch that divides 32, with 3*BN*2 <= 512 TMEM columns
+// (BF16 operands with BN >= 64: the un-folded form wins — N = 64 MMAs are cheap at K = 16 and the epilogue loses its
+//  3x TMEM reads and 2 shuffles per value, which is what bounds the folded kernel)
 static bool sv_jfold(const SvParams& p, int bn) {
+    if (p.bf && bn >= 64 && !getenv("DNB_SV_BF_JF")) return false;
     return p.kh == 3 && p.kw == 3 && (p.Cs == 32 || p.Cs == 64) && bn <= 64 && p.Wd + 2 <= 32 && !getenv("DNB_SV_NOJF");
 }
 
@@ -506,7 +527,8 @@ static bool sv_plan(SvParams& p, int bn) {
         if (sv_smem_bytes(p, bn) > budget) p.nout = 0;
     }
     while (p.nraw < 4) { ++p.nraw; if (sv_smem_bytes(p, bn) > budget) { --p.nraw; break; } }
-    p.units = (long)p.B * p.nbands;
+    if ((long)p.B * p.nbands > 0x7fffffffL) return false;
+    p.units = p.B * p.nbands;
     return true;
 }
 
@@ -516,7 +538,7 @@ template <int BN, bool K33, int CB, bool JF, bool BF = false>
 static int sv_launch_k(const char* name, const CUtensorMap& tw, const CUtensorMap& tx, const SvParams& p, cudaStream_t st) {
     const size_t smem = sv_smem_bytes(p, BN);
     cudaFuncSetAttribute(tc_conv_sv_kernel<BN, K33, CB, JF, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int grid = (int)std::min<long>(p.units, kNumSMs);
+    const int grid = std::min(p.units, kNumSMs);
     tc_conv_sv_kernel<BN, K33, CB, JF, BF><<<grid, SV_THREADS, smem, st>>>(tw, tx, p);
     DNB_LAUNCH_CHECK(name);
     return DNB_OK;
@@ -533,6 +555,10 @@ static int sv_launch(const char* name, const CUtensorMap& tw, const CUtensorMap&
             if (p.Cs == 32) return sv_launch_k<BN, true, 1, true>(name, tw, tx, p, st);
             return sv_launch_k<BN, true, 2, true>(name, tw, tx, p, st);
         }
+    }
+    if (p.bf) {
+        if (p.Cs == 32) return sv_launch_k<BN, true, 1, false, true>(name, tw, tx, p, st);
+        return sv_launch_k<BN, true, 2, false, true>(name, tw, tx, p, st);
     }
     if (p.kh == 3 && p.kw == 3 && p.Cs == 32) return sv_launch_k<BN, true, 1, false>(name, tw, tx, p, st);
     if (p.kh == 3 && p.kw == 3 && p.Cs == 64) return sv_launch_k<BN, true, 2, false>(name, tw, tx, p, st);
@@ -555,8 +581,8 @@ static SvParams sv_make(const dnb_win_t* g, bool dgrad) {
 bool tc_conv_sv_bf16_supported(const dnb_win_t* g, bool dgrad) {
     if (getenv("DNB_SV_NOBF16") || !tc_conv_sv_supported(g, dgrad)) return false;
     SvParams p = sv_make(g, dgrad);
-    const int bn = pick_bn_sv(p.Cd);
-    return bn <= 64 && sv_jfold(p, bn);
+    p.bf = 1;
+    return p.kh == 3 && p.kw == 3 && (p.Cs == 32 || p.Cs == 64) && sv_plan(p, pick_bn_sv(p.Cd));
 }
 
 bool tc_conv_sv_supported(const dnb_win_t* g, bool dgrad) {
