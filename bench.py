@@ -120,6 +120,8 @@ def algo_work(layer, kernel, B):
             return (nin + nout) * s, fl
         if "reg" in kernel:
             return 3 * f * c * kh * kw * s, 0.0
+        if "prep_weights" in kernel:
+            return 2 * f * c * kh * kw * s, 0.0
         return (nin + nout) * s, fl
     if kind == "MaxPool2D":
         c, h, w = layer.parents[0].oshape
@@ -127,8 +129,10 @@ def algo_work(layer, kernel, B):
         nin, nout = B * c * h * w, B * c * oh * ow
         if kernel == "maxpool2d_fwd":
             return (nin + 2 * nout) * s, 0.0
-        if kernel in ("maxpool2d_bwd_last", "maxpool2d_bwd_last_top"):
-            return nout * s, 0.0
+        if kernel == "maxpool2d_bwd_last_top":
+            return min(B, 128) * c * oh * ow * s, 0.0       # argmax offsets of the newest 128 samples
+        if kernel == "maxpool2d_bwd_last":
+            return nout * s, 0.0                            # upper bound: only unfinished window positions are scanned
         if kernel == "maxpool2d_bwd_literal":
             # LITERAL route: every sample's dx is written (zeros for samples 1..B-1: the memset is part of this entry)
             return (nin + c * h * w + c * oh * ow * 10) * s, 0.0

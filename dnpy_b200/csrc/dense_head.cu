@@ -34,10 +34,10 @@ __device__ __forceinline__ void hd_bulk_g2s(void* dst, const void* src, uint32_t
 // row and load).  The 4*OUT weights of a quad are read ONCE from shared memory (OUT LDS.128) and reused for all HF_RPW
 // rows — the previous one-row-per-thread version re-read them for every row and was bound by shared-memory wavefronts
 // (LDS.128 is served a quarter-warp at a time): 43 us for 52 MB on B200.
-constexpr int HF_RPW = 8;                         // rows per warp
+constexpr int HF_RPW = 4;                         // rows per warp
 constexpr int HF_WARPS = 8;
 template <int OUT>
-__global__ void __launch_bounds__(HF_WARPS * 32) head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(HF_WARPS * 32, 2) head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                  const float* __restrict__ bias, float* __restrict__ y, int B, int in) {
     extern __shared__ __align__(128) uint8_t hsm[];
     float (*sw)[HF_CH * OUT] = reinterpret_cast<float (*)[HF_CH * OUT]>(hsm);          // [2][HF_CH * OUT]
