@@ -22,7 +22,12 @@ def launches(path):
     lines = [l for l in open(path) if not l.startswith('==')]
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
-        v = float(row['Metric Value'].replace(',', ''))
+        try:
+            v = float(row['Metric Value'].replace(',', ''))
+        except ValueError:
+            continue
+        if v != v:                       # ncu prints nan for a launch it could not time
+            continue
         u = row['Metric Unit']
         v = v / 1e3 if u == 'ns' else (v * 1e3 if u == 'ms' else v)
         a = agg.setdefault(row['Kernel Name'], [0, 0.0])
