@@ -123,6 +123,17 @@ def algo_work(layer, kernel, B):
         if "prep_weights" in kernel:
             return 2 * f * c * kh * kw * s, 0.0
         return (nin + nout) * s, fl
+    if kind == "DepthwiseConv2D":
+        c, h, w = layer.parents[0].oshape
+        _, oh, ow = layer.oshape
+        kh, kw = layer.kernel_size[-2:]
+        return (B * c * h * w + B * c * oh * ow) * s, 2.0 * B * c * oh * ow * kh * kw
+    if kind == "BatchNorm":
+        n = B * int(np.prod(layer.oshape))
+        return (5 if "bwd" in kernel else 3) * n * s, 0.0          # fwd: 2 reads + 1 write; bwd: x, dy twice, dx
+    if kind == "Add":
+        n = B * int(np.prod(layer.oshape))
+        return (len(layer.parents) + 1) * n * s, 0.0
     if kind == "MaxPool2D":
         c, h, w = layer.parents[0].oshape
         _, oh, ow = layer.oshape

@@ -14,6 +14,8 @@
 //   * split-K over gridDim.z (atomic accumulate epilogue) for the skinny dW shapes.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cstdio>
+#include <cstdlib>
 #include "tc_gemm.cuh"
 
 namespace dnb {
@@ -72,7 +74,14 @@ struct GemmParams {
     int grad;                   // epilogue: 0 store(+bias), 1 accumulate gradient
     float inv_m, l1, l2;
     int kb_per_split;           // k-blocks handled by one z-slice
+    unsigned long long* prof;   // DNB_GEMM_PROF: globaltimer stamps of CTA (0,0,0)
 };
+__device__ __forceinline__ void gemm_stamp(const GemmParams& p, int slot) {
+    if (p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        p.prof[slot] = g;
+    }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -90,6 +99,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) gemm_stamp(p, 0);
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int num_kb_total = (p.K + BK - 1) / BK;
     const int kb_begin = blockIdx.z * p.kb_per_split;
@@ -111,6 +121,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) gemm_stamp(p, 1);
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
@@ -136,6 +147,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int s = i % STAGES;
             mbar_wait(&full[s], (i / STAGES) & 1);
             tc_fence_after();
+            if (i == 0 && lane == 0) gemm_stamp(p, 2);
             const uint64_t a = a0 + (uint64_t)(s * (A_BYTES >> 4)), b = b0 + (uint64_t)(s * (B_BYTES >> 4));
             if (elect_one()) {
                 if (i == 0) mma_tf32_init(tmem_base, a, b, idesc); else mma_tf32_acc(tmem_base, a, b, idesc);
@@ -155,6 +167,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(acc_full, 0);
             tc_fence_after();
         }
+        if (warp == 2 && lane == 0) gemm_stamp(p, 3);
+        // The accumulator row of a thread is one row of C: storing it directly scatters every warp store over 32 rows
+        // (32 sectors per instruction — 9 us for a 128 x 128 tile on B200).  Stage the tile in the (now idle) operand ring,
+        // then every warp writes whole rows: 16 bytes per lane, one contiguous segment per instruction.
+        constexpr int PITCH = BN + 4;                       // floats; rows 16-byte aligned, conflict-free for 128-bit accesses
+        float* stg = reinterpret_cast<float*>(sA);
+        const int rl = q * 32 + lane;                       // tile row of this thread
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
@@ -165,20 +184,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-            if (row < p.M) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = n0 + c0 + j;
-                    if (col < p.N) {
-                        const float acc = __uint_as_float(v[j]);
-                        const size_t o = (size_t)row * p.N + col;
-                        if (!p.grad) {
-                            p.C[o] = acc + (p.bias ? p.bias[col] : 0.f);
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(stg + rl * PITCH + c0 + j) =
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps
+        const bool vec = (p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
+        for (int r = warp - 2; r < BM; r += 4) {
+            const int grow = m0 + r;
+            if (grow >= p.M) break;
+            for (int c4 = lane; c4 < BN / 4; c4 += 32) {
+                const int col = n0 + c4 * 4;
+                if (col >= p.N) continue;
+                const float4 a4 = *reinterpret_cast<const float4*>(stg + r * PITCH + c4 * 4);
+                float a[4] = {a4.x, a4.y, a4.z, a4.w};
+                const size_t o = (size_t)grow * p.N + col;
+                const int nv = min(4, p.N - col);
+                if (!p.grad) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) if (e < nv && p.bias) a[e] += __ldg(p.bias + col + e);
+                    if (vec) *reinterpret_cast<float4*>(p.C + o) = make_float4(a[0], a[1], a[2], a[3]);
+                    else for (int e = 0; e < nv; ++e) p.C[o + e] = a[e];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        a[e] *= p.inv_m;
+                        if (e < nv && blockIdx.z == 0 && (p.l1 != 0.f || p.l2 != 0.f)) a[e] += reg_term(p.W[o + e], p.l1, p.l2) * p.inv_m;
+                    }
+                    if (gridDim.z == 1) {
+                        if (vec) {
+                            float4 c4v = *reinterpret_cast<const float4*>(p.C + o);
+                            c4v.x += a[0]; c4v.y += a[1]; c4v.z += a[2]; c4v.w += a[3];
+                            *reinterpret_cast<float4*>(p.C + o) = c4v;
                         } else {
-                            float g = acc * p.inv_m;
-                            if (blockIdx.z == 0 && (p.l1 != 0.f || p.l2 != 0.f)) g += reg_term(p.W[o], p.l1, p.l2) * p.inv_m;
-                            if (gridDim.z == 1) p.C[o] += g; else atomicAdd(p.C + o, g);
+                            for (int e = 0; e < nv; ++e) p.C[o + e] += a[e];
                         }
+                    } else {
+                        for (int e = 0; e < nv; ++e) atomicAdd(p.C + o + e, a[e]);
                     }
                 }
             }
@@ -186,6 +229,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) gemm_stamp(p, 4);
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -239,10 +283,21 @@ int tc_gemm(const float* A, const float* B, float* C, int M, int N, int K, int f
     }
     int per = (nkb + splits - 1) / splits;
     splits = (nkb + per - 1) / per;
-    GemmParams p{C, bias, W, M, N, K, a_mn, b_mn, grad, inv_m, l1, l2, per};
-    if (BN == 128) return launch<128>(ta, tb, p, splits, st);
-    if (BN == 64) return launch<64>(ta, tb, p, splits, st);
-    return launch<32>(ta, tb, p, splits, st);
+    GemmParams p{C, bias, W, M, N, K, a_mn, b_mn, grad, inv_m, l1, l2, per, nullptr};
+    static unsigned long long* dprof = nullptr;
+    if (getenv("DNB_GEMM_PROF")) {
+        if (!dprof) cudaMalloc(&dprof, 8 * sizeof(unsigned long long));
+        p.prof = dprof;
+    }
+    const int rc = BN == 128 ? launch<128>(ta, tb, p, splits, st) : (BN == 64 ? launch<64>(ta, tb, p, splits, st) : launch<32>(ta, tb, p, splits, st));
+    if (p.prof && rc == DNB_OK) {
+        unsigned long long h[8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, p.prof, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[gemm prof] M=%d N=%d K=%d BN=%d splits=%d: setup %llu ns, first stage landed +%llu, accumulator complete +%llu, epilogue done +%llu\n",
+                M, N, K, BN, splits, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0]);
+    }
+    return rc;
 }
 
 }  // namespace dnb
