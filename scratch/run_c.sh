@@ -1,9 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_layers.py tests/test_gpu_nets.py -m gpu -x -q -k "tc_gemm or ense or mlp or tensor_core" 2>&1 | tail -3
-python scratch/gemm_lat.py 2>&1 | tail -10
-timeout 300 python bench.py --no-cpu --workload mnist_mlp > gpurun_out/bench_mnist_mlp_bf16.json 2> gpurun_out/bench_mnist_mlp_bf16.err; echo "rc $?"
-python - <<PY
-import json
-d=json.load(open('gpurun_out/bench_mnist_mlp_bf16.json'))
-print(round(d['value']), d['unit'], d['ms_per_step'], 'loss', d['final_loss'])
-for t in d['top_kernels'][:8]: print(f"   {t['ms_per_step']*1e3:8.1f} us {t['share']*100:5.1f}% {t['frac']} {t['kernel']}")
-PY
+SVMATH=bf16 DNB_SV_STAGE=1 python scratch/sv_bench.py 0 2>&1 | grep debug
+SVMATH=bf16 python scratch/sv_bench.py 0 2>&1 | grep debug
