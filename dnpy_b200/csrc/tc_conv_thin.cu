@@ -1,0 +1,247 @@
+// Tensor-core weight gradient for the single-channel 3x3 stride-1 convolution (conv1 of the MNIST CNN, 1 -> F filters):
+//     gW[f][tap] = (1/m) sum_{b,px} dY[b,f,px] * Xp[b, px + tap],     gb[f] = (1/m) sum_{b,px} dY[b,f,px]
+// The FP32 register-tiled kernel (conv_thin.cu) spends 10 FMA-pipe instructions per dY element and is bound by FP32
+// issue (67% of HBM peak on B200).  Here dY never touches a register:
+//   A = dY[b]  [F rows][K = pixels]   K-major, exactly the NCHW layout: one TMA box {32 px, F} per 32-pixel chunk, 128B swizzle
+//   B = Xcol   [16 rows][K = pixels]  rows 0-8 the nine shifted copies of the (3 KB) input image, row 9 all ones (its
+//                                      column of D is the bias gradient), rows 10-15 zero; built in shared memory by the
+//                                      transposer warps from the raw image (one 1-D bulk copy per image)
+//   D[f][16]   one TMEM accumulator (M=64, N=16), persistent over ALL images of the CTA; one tiny epilogue at the end.
+// Roles: warp 0 TMA producer, warp 1 MMA issue (tcgen05.mma.kind::tf32), warps 2-9 im2col transposers (+ epilogue).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_conv.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+namespace dnb {
+namespace tc {
+
+struct ThinWgParams {
+    const float* x; float* gw; float* gb;
+    int B, H, W, F, OH, OW, pt, pl;
+    int npx;                 // OH * OW
+    int nchunks;             // 32-pixel K chunks per image
+    float inv_m;
+};
+
+constexpr int TW_TR = 8;                                   // transposer warps
+constexpr int TW_THREADS = (2 + TW_TR) * 32;
+constexpr int TW_SLOTS = 16;                               // A ring: dY chunks in flight
+constexpr int TW_TB = 8;                                   // im2col task slots per transposer thread
+
+__global__ void __launch_bounds__(TW_THREADS, 1)
+tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, ThinWgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t slot_bytes = (uint32_t)p.F * 128;                       // one dY chunk: F rows x 32 px
+    const uint32_t xc_bytes = (uint32_t)p.nchunks * 2048;                  // one Xcol buffer: 16 rows x 32 px per chunk
+    const uint32_t xr_bytes = ((uint32_t)p.H * p.W * 4 + 127) & ~127u;     // one raw input image
+    uint8_t* sA = smem;                                    // TW_SLOTS chunks (+4 KB slack: an M=64 MMA over F=32 rows reads on)
+    uint8_t* sXc = sA + (size_t)TW_SLOTS * slot_bytes + 4096;              // 2 Xcol buffers
+    uint8_t* sXr = sXc + 2 * (size_t)xc_bytes;                             // 2 raw images
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sXr + 2 * (size_t)xr_bytes);
+    uint64_t* a_full = bars;                    // [TW_SLOTS] tx
+    uint64_t* a_empty = bars + TW_SLOTS;        // [TW_SLOTS] commit
+    uint64_t* xr_full = bars + 2 * TW_SLOTS;    // [2] tx
+    uint64_t* xr_empty = xr_full + 2;           // [2] TW_TR
+    uint64_t* xc_full = xr_full + 4;            // [2] TW_TR
+    uint64_t* xc_empty = xr_full + 6;           // [2] commit
+    uint64_t* acc_full = xr_full + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xr_full + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int nimg = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;       // images blockIdx.x + n*gridDim.x
+
+    // Xcol buffers: rows 0-8 are rewritten per image, row 9 = 1 for real pixels (0 in the K padding), rows 10-15 = 0
+    for (uint32_t e = tid; e < 2 * xc_bytes / 16; e += TW_THREADS) {
+        const uint32_t off = (e * 16) % xc_bytes;
+        const int chunk = off >> 11, row = (off >> 7) & 15, q8 = ((off >> 4) & 7) ^ (row & 7);    // logical 16-byte chunk
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row == 9) {
+            const int m0 = chunk * 32 + q8 * 4;
+            v = make_float4(m0 < p.npx ? 1.f : 0.f, m0 + 1 < p.npx ? 1.f : 0.f, m0 + 2 < p.npx ? 1.f : 0.f, m0 + 3 < p.npx ? 1.f : 0.f);
+        }
+        reinterpret_cast<float4*>(sXc)[e] = v;
+    }
+    // the slack behind the ring is read (rows 32-63 of the last slot when F == 32): keep it finite
+    for (uint32_t e = tid; e < 4096 / 16; e += TW_THREADS)
+        reinterpret_cast<float4*>(sA + (size_t)TW_SLOTS * slot_bytes)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) {
+        tma_prefetch_desc(&tmD);
+        for (int s = 0; s < TW_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&xr_full[s], 1); mbar_init(&xr_empty[s], TW_TR);
+            mbar_init(&xc_full[s], TW_TR); mbar_init(&xc_empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 32);
+        tmem_relinquish();
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: the raw image, then its dY chunks =====================
+        if (elect_one()) {
+            int it = 0;
+            for (int n = 0; n < nimg; ++n) {
+                const int b = (int)blockIdx.x + n * (int)gridDim.x, buf = n & 1;
+                if (n >= 2) mbar_wait(&xr_empty[buf], ((n >> 1) - 1) & 1);
+                mbar_arrive_expect_tx(&xr_full[buf], (uint32_t)p.H * p.W * 4);
+                bulk_load_1d(sXr + (size_t)buf * xr_bytes, p.x + (size_t)b * p.H * p.W, (uint32_t)p.H * p.W * 4, &xr_full[buf]);
+                for (int c = 0; c < p.nchunks; ++c, ++it) {
+                    const int s = it % TW_SLOTS;
+                    if (it >= TW_SLOTS) mbar_wait(&a_empty[s], ((it / TW_SLOTS) - 1) & 1);
+                    mbar_arrive_expect_tx(&a_full[s], slot_bytes);
+                    tma_load_3d(sA + (size_t)s * slot_bytes, &tmD, c * 32, 0, b, &a_full[s]);   // pixels past npx arrive as zeros
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issue =====================
+        const uint32_t idesc = make_idesc_tf32(64, 16, 0, 0);
+        int it = 0;
+        for (int n = 0; n < nimg; ++n) {
+            const int buf = n & 1;
+            mbar_wait(&xc_full[buf], (n >> 1) & 1);
+            tc_fence_after();
+            const uint64_t b0 = make_smem_desc(smem_u32(sXc + (size_t)buf * xc_bytes), 16, 1024);
+            for (int c = 0; c < p.nchunks; ++c, ++it) {
+                const int s = it % TW_SLOTS;
+                mbar_wait(&a_full[s], (it / TW_SLOTS) & 1);
+                tc_fence_after();
+                const uint64_t a = make_smem_desc(smem_u32(sA + (size_t)s * slot_bytes), 16, 1024);
+                const uint64_t bq = b0 + (uint64_t)((uint32_t)c * (2048 >> 4));
+                if (elect_one()) {
+                    mma_tf32(tmem_base, a, bq, idesc, it > 0 ? 1u : 0u);
+                    mma_tf32_acc(tmem_base, a + 2, bq + 2, idesc);
+                    mma_tf32_acc(tmem_base, a + 4, bq + 4, idesc);
+                    mma_tf32_acc(tmem_base, a + 6, bq + 6, idesc);
+                    mma_commit(&a_empty[s]);
+                    if (c == p.nchunks - 1) mma_commit(&xc_empty[buf]);
+                }
+                __syncwarp();
+            }
+        }
+        if (elect_one()) mma_commit(acc_full);
+        __syncwarp();
+    } else {
+        // ===================== im2col transposers: raw image -> nine shifted rows of Xcol =====================
+        const int ttid = tid - 64;
+        constexpr int LT = TW_TR * 32;
+        const int nquad = (p.npx + 3) >> 2;
+        const int tasks = 9 * nquad;
+        int t_src[TW_TB][4];
+        uint32_t t_dst[TW_TB];
+#pragma unroll
+        for (int r = 0; r < TW_TB; ++r) {
+            const int t = ttid + r * LT;
+            t_dst[r] = 0xffffffffu;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) t_src[r][e] = -1;
+            if (t < tasks) {
+                const int tap = t / nquad, q = t - tap * nquad;
+                const int i = tap / 3, j = tap - i * 3;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int m = 4 * q + e;
+                    if (m < p.npx) {
+                        const int oy = m / p.OW, ox = m - oy * p.OW;
+                        const int iy = oy + i - p.pt, ix = ox + j - p.pl;
+                        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) t_src[r][e] = (iy * p.W + ix) * 4;
+                    }
+                }
+                const int m0 = 4 * q;
+                t_dst[r] = (uint32_t)(m0 >> 5) * 2048 + (uint32_t)tap * 128 + (((((m0 & 31) >> 2) ^ (tap & 7)) & 7) << 4);
+            }
+        }
+        for (int n = 0; n < nimg; ++n) {
+            const int buf = n & 1;
+            mbar_wait(&xr_full[buf], (n >> 1) & 1);
+            if (n >= 2) mbar_wait(&xc_empty[buf], ((n >> 1) - 1) & 1);
+            const uint32_t raw_s = smem_u32(sXr + (size_t)buf * xr_bytes), xc_s = smem_u32(sXc + (size_t)buf * xc_bytes);
+#pragma unroll
+            for (int r = 0; r < TW_TB; ++r) {
+                if (t_dst[r] != 0xffffffffu) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        v[e] = 0.f;
+                        if (t_src[r][e] >= 0) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[e]) : "r"(raw_s + (uint32_t)t_src[r][e]) : "memory");
+                    }
+                    sts128(xc_s + t_dst[r], make_float4(v[0], v[1], v[2], v[3]));
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&xc_full[buf]); mbar_arrive(&xr_empty[buf]); }
+        }
+        // ---- epilogue: D[f][tap] -> gW, D[f][9] -> gb (M=64: row r lives in TMEM lane (r/16)*32 + r%16) ----
+        if (warp < 6 && nimg > 0) {
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            const int q = warp & 3;
+            uint32_t v[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(tmem_base + ((uint32_t)(q * 32) << 16)) : "memory");
+            tmem_ld_wait();
+            const int f = q * 16 + lane;
+            if (lane < 16 && f < p.F) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) atomicAdd(p.gw + (size_t)f * 9 + k, __uint_as_float(v[k]) * p.inv_m);
+                if (p.gb) atomicAdd(p.gb + f, __uint_as_float(v[9]) * p.inv_m);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 32);
+}
+
+static size_t tw_smem(const dnb_win_t* g) {
+    const size_t npx = (size_t)g->OH * g->OW, nchunks = (npx + 31) / 32;
+    return (size_t)TW_SLOTS * g->F * 128 + 4096 + 2 * nchunks * 2048 + 2 * (((size_t)g->H * g->W * 4 + 127) & ~(size_t)127) +
+           (2 * TW_SLOTS + 12) * 8 + 1024;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+bool tc_thin_wgrad_supported(const dnb_win_t* g) {
+    if (!get_encode_tiled() || getenv("DNB_NO_TC_THIN")) return false;
+    if (g->C != 1 || g->kh != 3 || g->kw != 3 || g->sy != 1 || g->sx != 1) return false;
+    if (g->F != 32 && g->F != 64) return false;
+    const long npx = (long)g->OH * g->OW;
+    if (npx % 4 || (g->H * g->W) % 4 || g->B < 1) return false;               // TMA row pitch / bulk copy granularity
+    if (9 * ((npx + 3) / 4) > (long)TW_TB * TW_TR * 32) return false;          // im2col task table
+    return tw_smem(g) <= 225 * 1024;
+}
+
+int tc_thin_wgrad(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, cudaStream_t st) {
+    if (!tc_thin_wgrad_supported(g)) return set_err(DNB_ERR_UNSUPPORTED, "conv2d_bwd_weight(thin tc): unsupported shape");
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15))
+        return set_err(DNB_ERR_UNSUPPORTED, "conv2d_bwd_weight(thin tc): tensors must be 16-byte aligned");
+    ThinWgParams p{x, gw, gb, g->B, g->H, g->W, g->F, g->OH, g->OW, g->pt, g->pl, g->OH * g->OW, (g->OH * g->OW + 31) / 32, inv_m};
+    CUtensorMap td;
+    uint64_t dd[3] = {(uint64_t)p.npx, (uint64_t)g->F, (uint64_t)g->B};
+    uint64_t ds[2] = {(uint64_t)p.npx * 4, (uint64_t)p.npx * g->F * 4};
+    uint32_t dbx[3] = {32, (uint32_t)g->F, 1};
+    if (!make_tmap_f32(&td, dy, 3, dd, ds, dbx, 0)) return set_err(DNB_ERR_CUDA, "conv2d_bwd_weight(thin tc): cuTensorMapEncodeTiled failed");
+    const size_t smem = tw_smem(g);
+    cudaFuncSetAttribute(tc_thin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_thin_wgrad_kernel<<<std::min(g->B, kNumSMs), TW_THREADS, smem, st>>>(td, p);
+    DNB_LAUNCH_CHECK("tc_thin_conv2d_bwd_weight");
+    return DNB_OK;
+}
+
+}  // namespace dnb
