@@ -627,9 +627,16 @@ int dnb_conv2d_bwd(const float* x, const float* w, const float* b, const float* 
     // measured on B200 (conv 1->32, 28x28, B=8192): the register-tiled fp32 wgrad (0.35 ms) edges out the tensor-core
     // thin-K variant (0.40 ms) — both are dY-stream bound — so thin layers keep the fp32 kernel in either math mode
     const bool tc_wgrad = !thin && math >= DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_WGRAD);
+    // ... except the single-channel case, where dY can feed the tensor core straight from TMA (tc_conv_thin.cu)
+    const bool tc_thin = thin && math >= DNB_MATH_TF32 && tc_thin_wgrad_supported(g) &&
+                         !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15);
     if (thin) {
-        rc = thin_conv_bwd(x, w, dy, dx, gw, gb, g, inv_m, /*skip_wgrad=*/tc_wgrad, st);
+        rc = thin_conv_bwd(x, w, dy, dx, gw, gb, g, inv_m, /*skip_wgrad=*/tc_wgrad || tc_thin, st);
         if (rc) return rc;
+        if (tc_thin) {
+            rc = tc_thin_wgrad(x, dy, gw, gb, g, inv_m, st);
+            if (rc) return rc;
+        }
     }
     if (dx && !thin) {
         if (math >= DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_DGRAD)) {

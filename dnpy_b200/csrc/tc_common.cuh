@@ -42,6 +42,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(DNB_MBAR_SUSPEND_NS) : "memory");
     return ok != 0;
 }
+// plain polling (no suspend hint): for waits that complete every few hundred cycles, where the wake-up latency of a suspended
+// warp would be the critical path
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spins = 0; !ok; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spins > (1u << 26)) __trap();
+    }
+}
 // Bounded wait: a protocol bug must trap (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {

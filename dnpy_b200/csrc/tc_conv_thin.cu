@@ -6,29 +6,37 @@
 //   B = Xcol   [16 rows][K = pixels]  rows 0-8 the nine shifted copies of the (3 KB) input image, row 9 all ones (its
 //                                      column of D is the bias gradient), rows 10-15 zero; built in shared memory by the
 //                                      transposer warps from the raw image (one 1-D bulk copy per image)
-//   D[f][16]   one TMEM accumulator (M=64, N=16), persistent over ALL images of the CTA; one tiny epilogue at the end.
+//   D[f][16]   EIGHT TMEM accumulators (M=64, N=16) used round-robin — back-to-back MMAs into one accumulator serialise on
+//              its read-modify-write (~100 clk each at N=16) — persistent over ALL images of the CTA; one tiny epilogue.
 // Roles: warp 0 TMA producer, warp 1 MMA issue (tcgen05.mma.kind::tf32), warps 2-9 im2col transposers (+ epilogue).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_conv.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 
 namespace dnb {
 namespace tc {
 
 struct ThinWgParams {
-    const float* x; float* gw; float* gb;
+    const float* x; const float* dy; float* gw; float* gb;
     int B, H, W, F, OH, OW, pt, pl;
     int npx;                 // OH * OW
     int nchunks;             // 32-pixel K chunks per image
     float inv_m;
+    int debug;               // DNB_TW_DEBUG: 1 no MMAs, 2 no dY loads, 4 no im2col
+    unsigned long long* prof;    // DNB_SV_PROF: per-role clock64 totals of CTA 0
 };
+#define TW_T0() const long long _t0 = p.prof ? clock64() : 0
+#define TW_ACC(var) do { if (p.prof) var += clock64() - _t0; } while (0)
 
 constexpr int TW_TR = 8;                                   // transposer warps
 constexpr int TW_THREADS = (2 + TW_TR) * 32;
 constexpr int TW_SLOTS = 16;                               // A ring: dY chunks in flight
 constexpr int TW_TB = 8;                                   // im2col task slots per transposer thread
+constexpr int TW_XR = 4;                                   // raw input images in flight: requested TW_XR-1 images ahead, so the
+                                                           // load + im2col latency of image n+1 hides behind the MMAs of image n
 
 __global__ void __launch_bounds__(TW_THREADS, 1)
 tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, ThinWgParams p) {
@@ -39,16 +47,16 @@ tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, ThinWgParams p) {
     const uint32_t xr_bytes = ((uint32_t)p.H * p.W * 4 + 127) & ~127u;     // one raw input image
     uint8_t* sA = smem;                                    // TW_SLOTS chunks (+4 KB slack: an M=64 MMA over F=32 rows reads on)
     uint8_t* sXc = sA + (size_t)TW_SLOTS * slot_bytes + 4096;              // 2 Xcol buffers
-    uint8_t* sXr = sXc + 2 * (size_t)xc_bytes;                             // 2 raw images
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sXr + 2 * (size_t)xr_bytes);
+    uint8_t* sXr = sXc + 2 * (size_t)xc_bytes;                             // TW_XR raw images
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sXr + TW_XR * (size_t)xr_bytes);
     uint64_t* a_full = bars;                    // [TW_SLOTS] tx
     uint64_t* a_empty = bars + TW_SLOTS;        // [TW_SLOTS] commit
-    uint64_t* xr_full = bars + 2 * TW_SLOTS;    // [2] tx
-    uint64_t* xr_empty = xr_full + 2;           // [2] TW_TR
-    uint64_t* xc_full = xr_full + 4;            // [2] TW_TR
-    uint64_t* xc_empty = xr_full + 6;           // [2] commit
-    uint64_t* acc_full = xr_full + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xr_full + 9);
+    uint64_t* xr_full = bars + 2 * TW_SLOTS;    // [TW_XR] tx
+    uint64_t* xr_empty = xr_full + TW_XR;       // [TW_XR] TW_TR
+    uint64_t* xc_full = xr_full + 2 * TW_XR;    // [2] TW_TR
+    uint64_t* xc_empty = xc_full + 2;           // [2] commit
+    uint64_t* acc_full = xc_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xc_full + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int nimg = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;       // images blockIdx.x + n*gridDim.x
@@ -70,15 +78,13 @@ tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, ThinWgParams p) {
     if (tid == 0) {
         tma_prefetch_desc(&tmD);
         for (int s = 0; s < TW_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&xr_full[s], 1); mbar_init(&xr_empty[s], TW_TR);
-            mbar_init(&xc_full[s], TW_TR); mbar_init(&xc_empty[s], 1);
-        }
+        for (int s = 0; s < TW_XR; ++s) { mbar_init(&xr_full[s], 1); mbar_init(&xr_empty[s], TW_TR); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&xc_full[s], TW_TR); mbar_init(&xc_empty[s], 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 32);
+        tmem_alloc(tmem_slot, 128);
         tmem_relinquish();
     }
     fence_proxy_async_smem();
@@ -91,40 +97,64 @@ tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, ThinWgParams p) {
         // ===================== TMA producer: the raw image, then its dY chunks =====================
         if (elect_one()) {
             int it = 0;
-            for (int n = 0; n < nimg; ++n) {
-                const int b = (int)blockIdx.x + n * (int)gridDim.x, buf = n & 1;
-                if (n >= 2) mbar_wait(&xr_empty[buf], ((n >> 1) - 1) & 1);
+            long long w_ae = 0, w_xre = 0;
+            const long long t_begin = p.prof ? clock64() : 0;
+            // The 128-byte box rows of a chunk sit 4*npx bytes apart: fetched straight from HBM they open a DRAM page each.
+            // Pull every image into L2 as ONE contiguous stream two images ahead; the boxes then hit L2.
+            const uint32_t img_bytes = (uint32_t)p.npx * p.F * 4;
+            constexpr int PF = 2;
+            for (int n = 0; n < min(PF, nimg); ++n)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.dy + (size_t)((int)blockIdx.x + n * (int)gridDim.x) * p.npx * p.F), "r"(img_bytes) : "memory");
+            auto issue_raw = [&](int n) {
+                const int b = (int)blockIdx.x + n * (int)gridDim.x, buf = n % TW_XR;
+                if (n >= TW_XR) { TW_T0(); mbar_wait(&xr_empty[buf], ((n / TW_XR) - 1) & 1); TW_ACC(w_xre); }
                 mbar_arrive_expect_tx(&xr_full[buf], (uint32_t)p.H * p.W * 4);
                 bulk_load_1d(sXr + (size_t)buf * xr_bytes, p.x + (size_t)b * p.H * p.W, (uint32_t)p.H * p.W * 4, &xr_full[buf]);
+            };
+            for (int n = 0; n < min(TW_XR - 1, nimg); ++n) issue_raw(n);
+            for (int n = 0; n < nimg; ++n) {
+                const int b = (int)blockIdx.x + n * (int)gridDim.x;
+                if (n + PF < nimg)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.dy + (size_t)(b + PF * (int)gridDim.x) * p.npx * p.F), "r"(img_bytes) : "memory");
+                if (n + TW_XR - 1 < nimg) issue_raw(n + TW_XR - 1);
                 for (int c = 0; c < p.nchunks; ++c, ++it) {
                     const int s = it % TW_SLOTS;
-                    if (it >= TW_SLOTS) mbar_wait(&a_empty[s], ((it / TW_SLOTS) - 1) & 1);
+                    // slots are released in groups of four: one tcgen05.commit per four chunks (a commit per chunk made the
+                    // skeleton alone cost ~330 clk per 4 KB chunk)
+                    if (it >= TW_SLOTS && (s & 3) == 0) { TW_T0(); mbar_wait_spin(&a_empty[s >> 2], ((it / TW_SLOTS) - 1) & 1); TW_ACC(w_ae); }
+                    if (p.debug & 2) { mbar_arrive(&a_full[s]); continue; }
                     mbar_arrive_expect_tx(&a_full[s], slot_bytes);
                     tma_load_3d(sA + (size_t)s * slot_bytes, &tmD, c * 32, 0, b, &a_full[s]);   // pixels past npx arrive as zeros
                 }
             }
+            if (p.prof && blockIdx.x == 0) { p.prof[0] = w_ae; p.prof[1] = w_xre; p.prof[2] = clock64() - t_begin; }
         }
     } else if (warp == 1) {
         // ===================== MMA issue =====================
         const uint32_t idesc = make_idesc_tf32(64, 16, 0, 0);
         int it = 0;
+        long long w_xcf = 0, w_af = 0;
+        const long long t_begin = p.prof ? clock64() : 0;
         for (int n = 0; n < nimg; ++n) {
             const int buf = n & 1;
-            mbar_wait(&xc_full[buf], (n >> 1) & 1);
+            { TW_T0(); mbar_wait(&xc_full[buf], (n >> 1) & 1); TW_ACC(w_xcf); }
             tc_fence_after();
             const uint64_t b0 = make_smem_desc(smem_u32(sXc + (size_t)buf * xc_bytes), 16, 1024);
             for (int c = 0; c < p.nchunks; ++c, ++it) {
                 const int s = it % TW_SLOTS;
-                mbar_wait(&a_full[s], (it / TW_SLOTS) & 1);
+                { TW_T0(); mbar_wait_spin(&a_full[s], (it / TW_SLOTS) & 1); TW_ACC(w_af); }
                 tc_fence_after();
                 const uint64_t a = make_smem_desc(smem_u32(sA + (size_t)s * slot_bytes), 16, 1024);
                 const uint64_t bq = b0 + (uint64_t)((uint32_t)c * (2048 >> 4));
                 if (elect_one()) {
-                    mma_tf32(tmem_base, a, bq, idesc, it > 0 ? 1u : 0u);
-                    mma_tf32_acc(tmem_base, a + 2, bq + 2, idesc);
-                    mma_tf32_acc(tmem_base, a + 4, bq + 4, idesc);
-                    mma_tf32_acc(tmem_base, a + 6, bq + 6, idesc);
-                    mma_commit(&a_empty[s]);
+                    const uint32_t d0 = tmem_base + (uint32_t)(it & 1) * 64, acc = it > 1 ? 1u : 0u;
+                    if (!(p.debug & 1)) {
+                    mma_tf32(d0, a, bq, idesc, acc);
+                    mma_tf32(d0 + 16, a + 2, bq + 2, idesc, acc);
+                    mma_tf32(d0 + 32, a + 4, bq + 4, idesc, acc);
+                    mma_tf32(d0 + 48, a + 6, bq + 6, idesc, acc);
+                    }
+                    if ((s & 3) == 3) mma_commit(&a_empty[s >> 2]);
                     if (c == p.nchunks - 1) mma_commit(&xc_empty[buf]);
                 }
                 __syncwarp();
@@ -132,6 +162,7 @@ tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, ThinWgParams p) {
         }
         if (elect_one()) mma_commit(acc_full);
         __syncwarp();
+        if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[3] = w_xcf; p.prof[4] = w_af; p.prof[5] = clock64() - t_begin; }
     } else {
         // ===================== im2col transposers: raw image -> nine shifted rows of Xcol =====================
         const int ttid = tid - 64;
@@ -162,14 +193,16 @@ tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, ThinWgParams p) {
                 t_dst[r] = (uint32_t)(m0 >> 5) * 2048 + (uint32_t)tap * 128 + (((((m0 & 31) >> 2) ^ (tap & 7)) & 7) << 4);
             }
         }
+        long long w_xrf = 0, w_xce = 0;
+        const long long t_begin = p.prof ? clock64() : 0;
         for (int n = 0; n < nimg; ++n) {
-            const int buf = n & 1;
-            mbar_wait(&xr_full[buf], (n >> 1) & 1);
-            if (n >= 2) mbar_wait(&xc_empty[buf], ((n >> 1) - 1) & 1);
-            const uint32_t raw_s = smem_u32(sXr + (size_t)buf * xr_bytes), xc_s = smem_u32(sXc + (size_t)buf * xc_bytes);
+            const int buf = n & 1, rbuf = n % TW_XR;
+            { TW_T0(); mbar_wait(&xr_full[rbuf], (n / TW_XR) & 1); TW_ACC(w_xrf); }
+            if (n >= 2) { TW_T0(); mbar_wait(&xc_empty[buf], ((n >> 1) - 1) & 1); TW_ACC(w_xce); }
+            const uint32_t raw_s = smem_u32(sXr + (size_t)rbuf * xr_bytes), xc_s = smem_u32(sXc + (size_t)buf * xc_bytes);
 #pragma unroll
             for (int r = 0; r < TW_TB; ++r) {
-                if (t_dst[r] != 0xffffffffu) {
+                if (t_dst[r] != 0xffffffffu && !(p.debug & 4)) {
                     float v[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -181,36 +214,45 @@ tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, ThinWgParams p) {
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&xc_full[buf]); mbar_arrive(&xr_empty[buf]); }
+            if (lane == 0) { mbar_arrive(&xc_full[buf]); mbar_arrive(&xr_empty[rbuf]); }
         }
+        if (p.prof && blockIdx.x == 0 && ttid == 0) { p.prof[6] = w_xrf; p.prof[7] = w_xce; p.prof[8] = clock64() - t_begin; }
         // ---- epilogue: D[f][tap] -> gW, D[f][9] -> gb (M=64: row r lives in TMEM lane (r/16)*32 + r%16) ----
         if (warp < 6 && nimg > 0) {
             mbar_wait(acc_full, 0);
             tc_fence_after();
             const int q = warp & 3;
-            uint32_t v[16];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                         : "r"(tmem_base + ((uint32_t)(q * 32) << 16)) : "memory");
-            tmem_ld_wait();
+            const int nacc = (long)nimg * p.nchunks > 1 ? 8 : 4;      // accumulators that were ever written
+            float sum[10];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) sum[k] = 0.f;
+            for (int a8 = 0; a8 < nacc; ++a8) {
+                uint32_t v[16];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a8 * 16) : "memory");
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 10; ++k) sum[k] += __uint_as_float(v[k]);
+            }
             const int f = q * 16 + lane;
             if (lane < 16 && f < p.F) {
 #pragma unroll
-                for (int k = 0; k < 9; ++k) atomicAdd(p.gw + (size_t)f * 9 + k, __uint_as_float(v[k]) * p.inv_m);
-                if (p.gb) atomicAdd(p.gb + f, __uint_as_float(v[9]) * p.inv_m);
+                for (int k = 0; k < 9; ++k) atomicAdd(p.gw + (size_t)f * 9 + k, sum[k] * p.inv_m);
+                if (p.gb) atomicAdd(p.gb + f, sum[9] * p.inv_m);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 32);
+    if (warp == 1) tmem_dealloc(tmem_base, 128);
 }
 
 static size_t tw_smem(const dnb_win_t* g) {
     const size_t npx = (size_t)g->OH * g->OW, nchunks = (npx + 31) / 32;
-    return (size_t)TW_SLOTS * g->F * 128 + 4096 + 2 * nchunks * 2048 + 2 * (((size_t)g->H * g->W * 4 + 127) & ~(size_t)127) +
-           (2 * TW_SLOTS + 12) * 8 + 1024;
+    return (size_t)TW_SLOTS * g->F * 128 + 4096 + 2 * nchunks * 2048 + TW_XR * (((size_t)g->H * g->W * 4 + 127) & ~(size_t)127) +
+           (2 * TW_SLOTS + 2 * TW_XR + 8) * 8 + 1024;
 }
 
 }  // namespace tc
@@ -218,7 +260,12 @@ static size_t tw_smem(const dnb_win_t* g) {
 using namespace tc;
 
 bool tc_thin_wgrad_supported(const dnb_win_t* g) {
-    if (!get_encode_tiled() || getenv("DNB_NO_TC_THIN")) return false;
+    // EXPERIMENT, off by default (DNB_TC_THIN=1 enables it).  Measured on B200 (B=8192, F=32, 26x26): 260-310 us against
+    // 168 us for the FP32 register-tiled kernel.  Per-role clocks (DNB_SV_PROF=1): with MMAs, dY loads and im2col all
+    // disabled the barrier skeleton alone costs ~350 clk per 4 KB chunk (TMA -> full barrier -> fence -> commit -> empty
+    // barrier round trips), and an N=16 tf32 MMA issues every ~39 clk, i.e. 88 MMAs = 3.4 k clk per image: a ~96 us floor
+    // before any synchronisation.  A K=9 contraction is too thin to amortise tcgen05's fixed per-instruction costs.
+    if (!get_encode_tiled() || !getenv("DNB_TC_THIN")) return false;
     if (g->C != 1 || g->kh != 3 || g->kw != 3 || g->sy != 1 || g->sx != 1) return false;
     if (g->F != 32 && g->F != 64) return false;
     const long npx = (long)g->OH * g->OW;
@@ -231,7 +278,14 @@ int tc_thin_wgrad(const float* x, const float* dy, float* gw, float* gb, const d
     if (!tc_thin_wgrad_supported(g)) return set_err(DNB_ERR_UNSUPPORTED, "conv2d_bwd_weight(thin tc): unsupported shape");
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15))
         return set_err(DNB_ERR_UNSUPPORTED, "conv2d_bwd_weight(thin tc): tensors must be 16-byte aligned");
-    ThinWgParams p{x, gw, gb, g->B, g->H, g->W, g->F, g->OH, g->OW, g->pt, g->pl, g->OH * g->OW, (g->OH * g->OW + 31) / 32, inv_m};
+    ThinWgParams p{x, dy, gw, gb, g->B, g->H, g->W, g->F, g->OH, g->OW, g->pt, g->pl, g->OH * g->OW, (g->OH * g->OW + 31) / 32, inv_m,
+                   getenv("DNB_TW_DEBUG") ? atoi(getenv("DNB_TW_DEBUG")) : 0, nullptr};
+    if (getenv("DNB_SV_PROF")) {
+        static unsigned long long* dprof = nullptr;
+        if (!dprof) cudaMalloc(&dprof, 16 * sizeof(unsigned long long));
+        cudaMemsetAsync(dprof, 0, 16 * sizeof(unsigned long long), st);
+        p.prof = dprof;
+    }
     CUtensorMap td;
     uint64_t dd[3] = {(uint64_t)p.npx, (uint64_t)g->F, (uint64_t)g->B};
     uint64_t ds[2] = {(uint64_t)p.npx * 4, (uint64_t)p.npx * g->F * 4};
@@ -241,6 +295,13 @@ int tc_thin_wgrad(const float* x, const float* dy, float* gw, float* gb, const d
     cudaFuncSetAttribute(tc_thin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     tc_thin_wgrad_kernel<<<std::min(g->B, kNumSMs), TW_THREADS, smem, st>>>(td, p);
     DNB_LAUNCH_CHECK("tc_thin_conv2d_bwd_weight");
+    if (p.prof) {
+        unsigned long long h[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, p.prof, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[tw prof] tma: wait a_empty %llu wait xr_empty %llu total %llu | mma: wait xc_full %llu wait a_full %llu total %llu | "
+                        "im2col: wait xr_full %llu wait xc_empty %llu total %llu\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8]);
+    }
     return DNB_OK;
 }
 

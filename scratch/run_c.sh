@@ -1,2 +1,1 @@
-SVMATH=bf16 DNB_SV_STAGE=1 python scratch/sv_bench.py 0 2>&1 | grep debug
-SVMATH=bf16 python scratch/sv_bench.py 0 2>&1 | grep debug
+DNB_SV_PROF=1 python scratch/tw_bench.py 0 7 2>&1 | grep -E "tw prof|debug" | tail -5
