@@ -93,6 +93,57 @@ __global__ void rnn_fwd_kernel(const float* __restrict__ x, const float* __restr
     }
 }
 
+// Warp-per-sample forward for H <= 32, D <= 32: lane j keeps rows j of Waa and Wax in registers, h_{t-1} and x_t are read
+// from a per-warp shared scratch with broadcast LDS.128; one __syncwarp pair per time step instead of three block barriers.
+constexpr int RF_WARPS = 8;
+__global__ void __launch_bounds__(RF_WARPS * 32)
+rnn_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ waa, const float* __restrict__ wax,
+                    const float* __restrict__ ba, float* __restrict__ states, float* __restrict__ y, int B, int T, int D, int H) {
+    __shared__ __align__(16) float scratch[RF_WARPS][2][32];    // per warp: h_{t-1} | x_t
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * RF_WARPS + warp;
+    if (b >= B) return;
+    float wrow[32], xrow[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        wrow[k] = (lane < H && k < H) ? __ldg(waa + lane * H + k) : 0.f;
+        xrow[k] = (lane < H && k < D) ? __ldg(wax + lane * D + k) : 0.f;
+    }
+    const float bj = lane < H ? __ldg(ba + lane) : 0.f;
+    float* sh = scratch[warp][0];
+    float* sx = scratch[warp][1];
+    sh[lane] = 0.f;
+    const float* xs = x + (size_t)b * T * D;
+    float xn = lane < D ? __ldg(xs + lane) : 0.f;
+    for (int t = 0; t < T; ++t) {
+        sx[lane] = xn;
+        __syncwarp();
+        if (t + 1 < T) xn = lane < D ? __ldg(xs + (size_t)(t + 1) * D + lane) : 0.f;     // next step's input, off the critical path
+        float a0 = bj, a1 = 0.f, a2 = 0.f, a3 = 0.f;            // four independent chains: the sum is on the critical path
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 h4 = *reinterpret_cast<const float4*>(sh + 4 * q4);
+            a0 = fmaf(h4.x, wrow[4 * q4], a0); a1 = fmaf(h4.y, wrow[4 * q4 + 1], a1);
+            a2 = fmaf(h4.z, wrow[4 * q4 + 2], a2); a3 = fmaf(h4.w, wrow[4 * q4 + 3], a3);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+            if (4 * q4 < D) {
+                const float4 x4 = *reinterpret_cast<const float4*>(sx + 4 * q4);
+                a0 = fmaf(x4.x, xrow[4 * q4], a0); a1 = fmaf(x4.y, xrow[4 * q4 + 1], a1);
+                a2 = fmaf(x4.z, xrow[4 * q4 + 2], a2); a3 = fmaf(x4.w, xrow[4 * q4 + 3], a3);
+            }
+        }
+        const float hn = lane < H ? tanhf((a0 + a1) + (a2 + a3)) : 0.f;
+        __syncwarp();
+        sh[lane] = hn;
+        if (lane < H) {
+            states[((size_t)b * T + t) * H + lane] = hn;
+            if (t == T - 1) y[(size_t)b * H + lane] = hn;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // SimpleRNN backward (literal truncated BPTT)
 // ------------------------------------------------------------------------------------------
@@ -225,14 +276,14 @@ rnn_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ state
     float* sx = scratch[warp][2];
     // sum_q v[q] * col[q] with v read from shared memory (all lanes read the same addresses: broadcast)
     auto dot32 = [&](const float* v, const float (&col)[32]) {
-        float acc = 0.f;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;           // four independent chains: the result is on the critical path
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
             const float4 t = *reinterpret_cast<const float4*>(v + 4 * q4);
-            acc = fmaf(t.x, col[4 * q4], acc); acc = fmaf(t.y, col[4 * q4 + 1], acc);
-            acc = fmaf(t.z, col[4 * q4 + 2], acc); acc = fmaf(t.w, col[4 * q4 + 3], acc);
+            c0 = fmaf(t.x, col[4 * q4], c0); c1 = fmaf(t.y, col[4 * q4 + 1], c1);
+            c2 = fmaf(t.z, col[4 * q4 + 2], c2); c3 = fmaf(t.w, col[4 * q4 + 3], c3);
         }
-        return acc;
+        return (c0 + c1) + (c2 + c3);
     };
     float dh = 0.f;
     if (act) {
@@ -244,9 +295,14 @@ rnn_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ state
             const float pre = (d0 + dh) * (1.f - h * h);
             float S = pre;
             const int k_lo = max(0, t - trunc);
+            float hp_n = (t > 0 && lane < H) ? __ldg(hs + (size_t)(t - 1) * H + lane) : 0.f;
+            float xk_n = lane < D ? __ldg(xs + (size_t)t * D + lane) : 0.f;
             for (int k = t; k >= k_lo; --k) {
-                const float hp = (k > 0 && lane < H) ? __ldg(hs + (size_t)(k - 1) * H + lane) : 0.f;
-                const float xk = lane < D ? __ldg(xs + (size_t)k * D + lane) : 0.f;
+                const float hp = hp_n, xk = xk_n;
+                if (k > k_lo) {                                    // the next lag's operands, one lag ahead of their use
+                    hp_n = (k > 1 && lane < H) ? __ldg(hs + (size_t)(k - 2) * H + lane) : 0.f;
+                    xk_n = lane < D ? __ldg(xs + (size_t)(k - 1) * D + lane) : 0.f;
+                }
                 __syncwarp();
                 su[lane] = S * (1.f - hp * hp);
                 sh[lane] = hp;
@@ -348,6 +404,11 @@ int dnb_rnn_fwd(const float* x, const float* waa, const float* wax, const float*
     DNB_CHECK_ARG(x && waa && wax && ba && states && y, "rnn_fwd: null pointer");
     if (H > 256) return set_err(DNB_ERR_UNSUPPORTED, "rnn_fwd: hidden_dim %d > 256 not supported", H);
     int SB, threads;
+    if (H <= 32 && D <= 32 && !getenv("DNB_RNN_TILE_FWD")) {
+        rnn_fwd_warp_kernel<<<(B + RF_WARPS - 1) / RF_WARPS, RF_WARPS * 32, 0, S(stream)>>>(x, waa, wax, ba, states, y, B, T, D, H);
+        DNB_LAUNCH_CHECK("rnn_fwd");
+        return DNB_OK;
+    }
     rnn_tile(H, &SB, &threads);
     size_t smem = ((size_t)H * H + (size_t)D * H + (size_t)SB * H + (size_t)SB * D) * sizeof(float);
     if (smem > 200 * 1024) return set_err(DNB_ERR_UNSUPPORTED, "rnn_fwd: H=%d D=%d exceed shared memory", H, D);
