@@ -478,11 +478,16 @@ __global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(Thi
         return;
     }
     // ===== consumers =====
-    float acc[FT][K + 1];
+    // accumulators as float2 pairs (k, k+1): the hot loop issues packed FFMA2 (__ffma2_rn, sm_100: two IEEE fp32 FMAs per
+    // instruction, bit-identical to scalar FMAs) — this kernel is bound by FP32 issue, and FFMA2 sustains ~1.55x the scalar
+    // FMA rate on B200 (scratch/ffma2.cu).  Slot K is the bias gradient: its "window value" is the constant 1.
+    constexpr int P2 = (K + 2) / 2;
+    float2 acc2[FT][P2];
+#define WG_ACC(f, k) (((k) & 1) ? acc2[f][(k) >> 1].y : acc2[f][(k) >> 1].x)
 #pragma unroll
     for (int f = 0; f < FT; ++f)
 #pragma unroll
-        for (int k = 0; k <= K; ++k) acc[f][k] = 0.f;
+        for (int p2 = 0; p2 < P2; ++p2) acc2[f][p2] = make_float2(0.f, 0.f);
     // ONEQ geometry of this thread's quad (image independent)
     int xo[4] = {0, 0, 0, 0};
     uint32_t vm[4] = {0u, 0u, 0u, 0u};
@@ -512,9 +517,12 @@ __global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(Thi
             if (tid < qpi) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    float xin[2][K];
+                    float2 xin[2][P2];
+#define WG_XIN(e, k) (((k) & 1) ? xin[e][(k) >> 1].y : xin[e][(k) >> 1].x)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
+                        WG_XIN(e, K) = 1.f;
+                        if (2 * P2 > K + 1) WG_XIN(e, 2 * P2 - 1) = 0.f;
                         const float* xe = sx + xo[2 * h + e];
 #pragma unroll
                         for (int c = 0; c < C; ++c)
@@ -522,17 +530,17 @@ __global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(Thi
                             for (int i = 0; i < 3; ++i)
 #pragma unroll
                                 for (int j = 0; j < 3; ++j) {
-                                    if (NOPAD) xin[e][(c * 3 + i) * 3 + j] = xe[c * hw + i * a.W + j];
-                                    else xin[e][(c * 3 + i) * 3 + j] = ((vm[2 * h + e] >> (i * 3 + j)) & 1u) ? xe[c * hw + i * a.W + j] : 0.f;
+                                    if (NOPAD) WG_XIN(e, (c * 3 + i) * 3 + j) = xe[c * hw + i * a.W + j];
+                                    else WG_XIN(e, (c * 3 + i) * 3 + j) = ((vm[2 * h + e] >> (i * 3 + j)) & 1u) ? xe[c * hw + i * a.W + j] : 0.f;
                                 }
                     }
 #pragma unroll
                     for (int f = 0; f < FT; ++f) {
                         if (f < nf) {
                             const float2 d = *reinterpret_cast<const float2*>(sd + f * plane + 4 * tid + 2 * h);
-                            acc[f][K] += d.x + d.y;
+                            const float2 d0 = make_float2(d.x, d.x), d1 = make_float2(d.y, d.y);
 #pragma unroll
-                            for (int k = 0; k < K; ++k) acc[f][k] = fmaf(d.y, xin[1][k], fmaf(d.x, xin[0][k], acc[f][k]));
+                            for (int p2 = 0; p2 < P2; ++p2) acc2[f][p2] = __ffma2_rn(d1, xin[1][p2], __ffma2_rn(d0, xin[0][p2], acc2[f][p2]));
                         }
                     }
                 }
@@ -561,13 +569,13 @@ __global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(Thi
             for (int f = 0; f < FT; ++f) {
                 if (f < nf) {
                     const float4 d = *reinterpret_cast<const float4*>(sd + f * plane + 4 * q);
-                    acc[f][K] += (d.x + d.y) + (d.z + d.w);
+                    WG_ACC(f, K) += (d.x + d.y) + (d.z + d.w);
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        float t = acc[f][k];
+                        float t = WG_ACC(f, k);
                         t = fmaf(d.x, xin[0][k], t); t = fmaf(d.y, xin[1][k], t);
                         t = fmaf(d.z, xin[2][k], t); t = fmaf(d.w, xin[3][k], t);
-                        acc[f][k] = t;
+                        WG_ACC(f, k) = t;
                     }
                 }
             }
@@ -581,7 +589,7 @@ __global__ void __launch_bounds__(FLAT_WG_THREADS, 2) thin_wgrad_flat_kernel(Thi
     for (int f = 0; f < FT; ++f)
 #pragma unroll
         for (int k = 0; k <= K; ++k) {
-            const float v = warp_sum(acc[f][k]);
+            const float v = warp_sum(WG_ACC(f, k));
             if (lane == 0) red[wid][f * (K + 1) + k] = v;
         }
     // consumers only: named barrier 1 (the producer warp has returned)

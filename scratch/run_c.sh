@@ -1,8 +1,9 @@
-timeout 900 python -m pytest tests/test_gpu_layers.py tests/test_gpu_nets.py -m gpu -x -q -k "rnn or RNN" 2>&1 | tail -4
-timeout 300 python bench.py --no-cpu --workload rnn_sentiment > gpurun_out/bench_rnn_sentiment_bf16.json 2> gpurun_out/bench_rnn_sentiment_bf16.err; echo "rc $?"
+timeout 900 python -m pytest tests/test_gpu_layers.py -m gpu -x -q -k "conv" 2>&1 | tail -3
+timeout 300 python bench.py --no-cpu > gpurun_out/bench_c.json 2>gpurun_out/bench_c.err; echo rc $?
 python - <<PY
 import json
-d=json.load(open('gpurun_out/bench_rnn_sentiment_bf16.json'))
-print(round(d['value']), d['unit'], d['ms_per_step'], 'loss', d['final_loss'])
-for t in d['top_kernels'][:6]: print(f"   {t['ms_per_step']*1e3:8.1f} us {t['share']*100:5.1f}% {t['frac']} {t['kernel']}")
+d=json.load(open('gpurun_out/bench_c.json'))
+print(d['ms_per_step'], d['e2e']['ms_per_step'], d['value'], d['final_loss'])
+for t in d['top_kernels'][:8]:
+    print(f"{t['ms_per_step']*1e3:8.1f} us {t['share']*100:5.1f}% {t['frac']} {t['kernel']}")
 PY
