@@ -235,6 +235,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the informational run with the other MaxPool routing")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -438,6 +439,24 @@ def main():
             r = roofline_of(t, k, e)
             top5.append(dict(kernel=f"{t}/{k}", ms_per_step=e["ms"] / prof_steps, share=e["ms"] / total_ms,
                              bound=r["bound"] if r else None, frac=round(r["frac"], 4) if r else None))
+    # ---------------------------------------------------------------- the other MaxPool routing (N=1 only, informational)
+    # LITERAL (default) is dnpy/layers/pooling.py:95 as written (every sample's delta lands in sample 0); PER_SAMPLE is the
+    # intended scatter-add, the variant whose arithmetic is meaningful.  Same protocol, K timed steps.
+    alt = None
+    if world == 1 and name == "mnist_cnn" and not args.no_alt:
+        import dnpy_b200
+        other = "per_sample" if args.route == "literal" else "literal"
+        net_main = net
+        try:
+            net = build_net(args.workload, args.math, other)
+            for i in range(3 * n_mb + 8):
+                step_resident(i)
+            torch.cuda.synchronize()
+            ms_alt, _ = timed(step_resident, args.steps)
+            alt = dict(maxpool_route=other, value=batch * args.steps / (ms_alt * 1e-3), unit=unit, ms_per_step=ms_alt / args.steps)
+        finally:
+            net = net_main
+            dnpy_b200.set_maxpool_route(args.route)
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -453,7 +472,8 @@ def main():
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
                              ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, top_kernels=top5, final_loss=loss)
+                    gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, top_kernels=top5, final_loss=loss,
+                    other_maxpool_route=alt)
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
     if world > 1:

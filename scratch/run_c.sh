@@ -1,9 +1,7 @@
-timeout 900 python -m pytest tests/test_gpu_layers.py -m gpu -x -q -k "conv" 2>&1 | tail -3
-timeout 300 python bench.py --no-cpu > gpurun_out/bench_c.json 2>gpurun_out/bench_c.err; echo rc $?
+timeout 600 python bench.py > gpurun_out/bench_r01_default.json 2> gpurun_out/bench_r01_default.err; echo bench rc $?
 python - <<PY
 import json
-d=json.load(open('gpurun_out/bench_c.json'))
-print(d['ms_per_step'], d['e2e']['ms_per_step'], d['value'], d['final_loss'])
-for t in d['top_kernels'][:8]:
-    print(f"{t['ms_per_step']*1e3:8.1f} us {t['share']*100:5.1f}% {t['frac']} {t['kernel']}")
+d=json.load(open('gpurun_out/bench_r01_default.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['cpu_baseline']['value'], d['other_maxpool_route'], d['roofline']['kernel'], d['roofline']['frac'])
 PY
+tail -3 gpurun_out/bench_r01_default.err
