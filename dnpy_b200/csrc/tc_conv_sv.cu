@@ -370,8 +370,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++it) {
             const int b = p.nbands == 1 ? u : u / p.nbands, band = p.nbands == 1 ? 0 : u - b * p.nbands;
             float* so = reinterpret_cast<float*>(sO + (size_t)(it & 1) * out_bytes);
-            // staging buffer (it & 1) is free once the issuing thread has seen the bulk store of unit it-2 finish reading it
-            if (staged) asm volatile("bar.sync 2, %0;" ::"n"(SV_EPI * 32) : "memory");
+            // staging buffer (it & 1) was copied out by every epilogue thread before it reached the barrier of unit it-1
             for (int t = 0; t < p.tiles; ++t, ++tcount) {
                 const int as = tcount & 1;
                 // M=128 tile: D row r = TMEM lane r; M=64 tile: row r = lane (r/16)*32 + r%16 (16 rows per quadrant)
@@ -451,18 +450,18 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 if (lane == 0) mbar_arrive(&acc_empty[as]);
             }
             if (staged) {
-                fence_proxy_async_smem();
+                // the image [Cd][Hd*Wd] is contiguous in shared AND in global memory: a straight, fully coalesced copy
+                // (16 bytes per lane, 512 contiguous bytes per warp instruction) instead of 4-byte stores scattered over
+                // the channel planes.  (A bulk store of the same buffer is slower: its read of shared memory completes late.)
                 asm volatile("bar.sync 2, %0;" ::"n"(SV_EPI * 32) : "memory");
-                if (warp == SV_W_EPI0 && lane == 0) {
-                    if (!(p.debug & 1))
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                     ::"l"(p.dst + (size_t)b * p.Cd * plane_d), "r"(smem_u32(so)), "r"((uint32_t)(p.Cd * plane_d * 4)) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                if (!(p.debug & 1)) {
+                    const int n4 = (int)(p.Cd * plane_d) >> 2;
+                    float4* g4 = reinterpret_cast<float4*>(p.dst + (size_t)b * p.Cd * plane_d);
+                    const float4* s4 = reinterpret_cast<const float4*>(so);
+                    for (int e = tid - SV_W_EPI0 * 32; e < n4; e += SV_EPI * 32) g4[e] = s4[e];
                 }
             }
         }
-        if (staged && warp == SV_W_EPI0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (p.prof && blockIdx.x == 0 && lane == 0 && warp == SV_W_EPI0) { p.prof[10] = e_ld; p.prof[11] = e_sh; p.prof[12] = e_st; }
         if (p.prof && blockIdx.x == 0 && lane == 0 && warp == SV_W_EPI0) { p.prof[7] = w_af; p.prof[8] = clock64() - t_begin; p.prof[9] = tcount; }
     }
@@ -520,8 +519,9 @@ static bool sv_plan(SvParams& p, int bn) {
     shape(p, best_th);
     // staged output (bulk store per image): single-band units whose image is a whole number of 16-byte quads, if two
     // staging buffers fit next to at least two raw stages
-    // (measured on B200: SLOWER than the direct stores — conv2 forward 149 -> 212 us — the store engine finishes reading a
-    // 37 KB image too late for two buffers to hide it; kept as an experiment switch, off by default)
+    // EXPERIMENT, off by default (DNB_SV_STAGE=1).  Measured on B200, conv2 of the CNN (bf16): direct 4-byte stores 113 us
+    // forward / 110 us dgrad; staged + coalesced 16-byte copy-out by the epilogue warps 147 / 132 us; staged + cp.async.bulk
+    // store 130 / 123 us.  The per-image barrier among the epilogue warps costs more than the scattered stores.
     if (p.nbands == 1 && ((long)p.Cd * p.Hd * p.Wd) % 4 == 0 && getenv("DNB_SV_STAGE")) {
         p.nout = 2;
         if (sv_smem_bytes(p, bn) > budget) p.nout = 0;
