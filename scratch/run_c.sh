@@ -1,1 +1,1 @@
-SVMATH=bf16 python scratch/sv_bench.py 0 1 2 8 3 2>&1 | grep debug
+timeout 900 python -m pytest tests/test_gpu_layers.py -m gpu -x -q -k "depthwise or rnn" 2>&1 | tail -6

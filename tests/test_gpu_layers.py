@@ -140,6 +140,10 @@ BIG_CASES = [
     dict(name="big_conv_c3", kind="Conv2D", in_shape=(3, 32, 32), batch=16,
          kw=dict(filters=32, kernel_size=(3, 3), strides=(1, 1), padding="same")),
     dict(name="big_pointwise", kind="PointwiseConv2D", in_shape=(32, 16, 16), batch=16, kw=dict(filters=32)),
+    dict(name="ring_depthwise_nonsquare", kind="DepthwiseConv2D", in_shape=(3, 9, 12), batch=5,      # ring kernels: odd H, row tails
+         kw=dict(kernel_size=(3, 3), strides=(1, 1), padding="same")),
+    dict(name="ring_depthwise_w8_many", kind="DepthwiseConv2D", in_shape=(5, 8, 8), batch=70,         # several planes per CTA
+         kw=dict(kernel_size=(3, 3), strides=(1, 1), padding="same")),
     dict(name="big_depthwise", kind="DepthwiseConv2D", in_shape=(32, 16, 16), batch=16,
          kw=dict(kernel_size=(3, 3), strides=(1, 1), padding="same")),
     dict(name="big_maxpool", kind="MaxPool2D", in_shape=(32, 26, 26), batch=130,
@@ -169,6 +173,7 @@ BIG_CASES = [
     # pscale 0.1: with 0.5*randn recurrent weights (spectral radius ~2.8) the recurrence is chaotic and
     # amplifies fp32-vs-fp64 round-off exponentially in T — a property of the test weights, not the kernel
     dict(name="big_rnn", kind="SimpleRNN", in_shape=(40, 8), batch=19, pscale=0.1, kw=dict(hidden_dim=32, bptt_truncate=4)),
+    dict(name="warp_rnn_odd_dims", kind="SimpleRNN", in_shape=(7, 3), batch=11, pscale=0.1, kw=dict(hidden_dim=7, bptt_truncate=2)),
     dict(name="big_rnn_full_bptt", kind="SimpleRNN", in_shape=(12, 5), batch=9, pscale=0.1, kw=dict(hidden_dim=16)),
     dict(name="big_dropout", kind="Dropout", in_shape=(1000,), batch=16, kw=dict(rate=0.25), training=True, seed=3),
 ]
