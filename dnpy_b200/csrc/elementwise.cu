@@ -144,9 +144,18 @@ __global__ void __launch_bounds__(EW_BLOCK) prelu_bwd_kernel(const float* __rest
 
 // ---- Add over n inputs (merge.py:13-16) --------------------------------------------------
 struct PtrPack { const float* p[8]; };
-__global__ void __launch_bounds__(EW_BLOCK) add_n_kernel(PtrPack xs, int n_in, float* __restrict__ y, size_t n) {
+__global__ void __launch_bounds__(EW_BLOCK) add_n_kernel(PtrPack xs, int n_in, float* __restrict__ y, size_t n, bool vec) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = tid; i < n; i += stride) {
+    const size_t n4 = vec ? n / 4 : 0;                       // 128-bit body, scalar tail
+    for (size_t i = tid; i < n4; i += stride) {
+        float4 acc = __ldg(reinterpret_cast<const float4*>(xs.p[0]) + i);
+        for (int k = 1; k < n_in; ++k) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(xs.p[k]) + i);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        reinterpret_cast<float4*>(y)[i] = acc;
+    }
+    for (size_t i = n4 * 4 + tid; i < n; i += stride) {
         float acc = xs.p[0][i];
         for (int k = 1; k < n_in; ++k) acc += xs.p[k][i];
         y[i] = acc;
@@ -342,7 +351,9 @@ int dnb_add_n(const float* const* xs, int n_in, float* y, size_t n, dnb_stream_t
     PtrPack pk;
     for (int i = 0; i < 8; ++i) pk.p[i] = (i < n_in) ? xs[i] : nullptr;
     for (int i = 0; i < n_in; ++i) DNB_CHECK_ARG(xs[i], "add_n: null input %d", i);
-    add_n_kernel<<<ew_grid(n, EW_BLOCK), EW_BLOCK, 0, S(stream)>>>(pk, n_in, y, n);
+    bool vec = aligned16(y);
+    for (int i = 0; i < n_in; ++i) vec = vec && aligned16(xs[i]);
+    add_n_kernel<<<ew_grid(vec ? n / 4 + 1 : n, EW_BLOCK), EW_BLOCK, 0, S(stream)>>>(pk, n_in, y, n, vec);
     DNB_LAUNCH_CHECK("add_n");
     return DNB_OK;
 }

@@ -165,6 +165,7 @@ BIG_CASES = [
     dict(name="big_avgpool", kind="AvgPool2D", in_shape=(16, 16, 16), batch=32,
          kw=dict(pool_size=(2, 2), strides=(2, 2), padding="none")),
     dict(name="big_batchnorm", kind="BatchNorm", in_shape=(8, 9, 9), batch=257, kw=dict(), training=True),
+    dict(name="vec_batchnorm", kind="BatchNorm", in_shape=(16, 8, 12), batch=37, kw=dict(), training=True),     # 128-bit column path, odd row tail
     dict(name="big_relu", kind="Relu", in_shape=(32, 12, 12), batch=67, kw=dict()),
     dict(name="big_softmax", kind="Softmax", in_shape=(10,), batch=1000, kw=dict()),
     dict(name="big_softmax_wide", kind="Softmax", in_shape=(100,), batch=33, kw=dict()),
