@@ -573,7 +573,49 @@ using namespace tc;
 static size_t ws_fwd_floats(const dnb_win_t* g) { return (size_t)round_up(g->F, 128) * round_up(round_up(g->C, 4) * g->kh * g->kw, CBK); }
 static size_t ws_dgrad_floats(const dnb_win_t* g) { return (size_t)round_up(g->C, 128) * round_up(round_up(g->F, 4) * g->kh * g->kw, CBK); }
 
-size_t tc_conv_ws_bytes(const dnb_win_t* g) { return (ws_fwd_floats(g) + ws_dgrad_floats(g)) * sizeof(float) + 256; }
+// Data gradient of a STRIDED convolution through the stride-1 shifted-view kernel: dY is scattered into a zero-interleaved
+// ("dilated") buffer dYu[s*oy][s*ox] = dY[oy][ox] and dX = corr(dYu, flip(W)) is the data gradient of a fictitious stride-1
+// convolution with the same top/left pads.  One extra streaming pass (read dY, write s^2 x as much) instead of the gather
+// kernel's predicated taps (3/4 of the MMA work of a stride-2 layer multiplies zeros there: 0.07 of HBM peak on B200).
+static bool dgrad_dilate_geom(const dnb_win_t* g, dnb_win_t* g1) {
+    if ((g->sy == 1 && g->sx == 1) || getenv("DNB_NO_DILATE")) return false;
+    *g1 = *g;
+    g1->sy = 1; g1->sx = 1;
+    g1->OH = std::max((g->OH - 1) * g->sy + 1, g->H + g->pt - g->kh + 1);
+    g1->OW = (std::max((g->OW - 1) * g->sx + 1, g->W + g->pl - g->kw + 1) + 3) & ~3;     // source rows in whole 16-byte quads
+    g1->pb = g1->OH - 1 + g->kh - g->H - g->pt;
+    g1->pr = g1->OW - 1 + g->kw - g->W - g->pl;
+    if (g1->pb < 0 || g1->pr < 0) return false;
+    return tc_conv_sv_supported(g1, true);
+}
+static size_t ws_weights_bytes(const dnb_win_t* g) { return ((ws_fwd_floats(g) + ws_dgrad_floats(g)) * sizeof(float) + 256 + 255) & ~(size_t)255; }
+
+size_t tc_conv_ws_bytes(const dnb_win_t* g) {
+    dnb_win_t g1;
+    size_t n = ws_weights_bytes(g);
+    if (dgrad_dilate_geom(g, &g1)) n += (size_t)g->B * g->F * g1.OH * g1.OW * sizeof(float);
+    return n;
+}
+
+// dYu[b,f,y,x] = (y % sy == 0 && x % sx == 0 && inside) ? dY[b,f,y/sy,x/sx] : 0; one thread per 4 consecutive x (OW1 % 4 == 0)
+__global__ void __launch_bounds__(256) dilate_dy_kernel(const float* __restrict__ dy, float* __restrict__ du, long planes,
+                                                        int OH, int OW, int OH1, int OW1, int sy, int sx) {
+    const long total = planes * OH1 * (OW1 >> 2);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int xq = (int)(i % (OW1 >> 2)); long t = i / (OW1 >> 2);
+        const int y = (int)(t % OH1); const long pl = t / OH1;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (y % sy == 0 && y / sy < OH) {
+            const float* row = dy + (pl * OH + y / sy) * OW;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int x = 4 * xq + e;
+                if (x % sx == 0 && x / sx < OW) v[e] = __ldg(row + x / sx);
+            }
+        }
+        reinterpret_cast<float4*>(du)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
 
 bool tc_conv_supported(const dnb_win_t* g, int kind) {
     if (!get_encode_tiled()) return false;
@@ -606,6 +648,18 @@ int tc_conv_dgrad(const float* dy, const float* w, float* dx, const dnb_win_t* g
     if (!ws) return set_err(DNB_ERR_INVALID, "conv2d_bwd(tf32): workspace required");
     const int cp = round_up(g->F, 4), Kp = round_up(cp * g->kh * g->kw, CBK), n_pad = round_up(g->C, 128);
     float* wp = static_cast<float*>(ws) + ws_fwd_floats(g);
+    dnb_win_t g1;
+    if (!getenv("DNB_NO_SV") && dgrad_dilate_geom(g, &g1)) {
+        float* du = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + ws_weights_bytes(g));
+        const long planes = (long)g->B * g->F;
+        const long quads = planes * g1.OH * (g1.OW >> 2);
+        dilate_dy_kernel<<<(unsigned)std::min<long>((quads + 255) / 256, 148L * 16), 256, 0, st>>>(dy, du, planes, g->OH, g->OW, g1.OH, g1.OW, g->sy, g->sx);
+        DNB_LAUNCH_CHECK("conv2d_dilate_dy");
+        const bool bf1 = bf16 && tc_conv_sv_bf16_supported(&g1, true);
+        prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, cp, 1, bf1);
+        DNB_LAUNCH_CHECK("conv2d_prep_weights_t");
+        return tc_conv_sv_run("tc_conv2d_bwd_data_sv", du, wp, n_pad, Kp, nullptr, 0.f, dx, &g1, true, bf1, st);
+    }
     const bool sv = !getenv("DNB_NO_SV") && tc_conv_sv_supported(g, true);
     const bool bf = bf16 && sv && tc_conv_sv_bf16_supported(g, true);
     prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, cp, 1, bf);

@@ -1,8 +1,8 @@
-timeout 900 python -m pytest tests/test_gpu_layers.py tests/test_gpu_nets.py -m gpu -x -q -k "atchnorm or BatchNorm or res_conv or iris or Add or add" 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_layers.py tests/test_gpu_nets.py tests/test_abi.py -m gpu -x -q -k "conv or res_conv or abi" 2>&1 | tail -4
 timeout 300 python bench.py --no-cpu --workload res_conv > gpurun_out/bench_res_conv_bf16.json 2> gpurun_out/bench_res_conv_bf16.err; echo "rc $?"
 python - <<PY
 import json
 d=json.load(open('gpurun_out/bench_res_conv_bf16.json'))
 print(round(d['value']), d['unit'], d['ms_per_step'], 'loss', d['final_loss'])
-for t in d['top_kernels'][:14]: print(f"   {t['ms_per_step']*1e3:8.1f} us {t['share']*100:5.1f}% {t['frac']} {t['kernel']}")
+for t in d['top_kernels'][:10]: print(f"   {t['ms_per_step']*1e3:8.1f} us {t['share']*100:5.1f}% {t['frac']} {t['kernel']}")
 PY
