@@ -691,6 +691,8 @@ int tc_conv_wgrad(const float* x, const float* dy, float* gw, float* gb, const d
                   bool bf16, cudaStream_t st) {
     (void)ws;
     if (tc_conv_wgrad_sv_supported(g)) return tc_conv_wgrad_sv(x, dy, gw, gb, g, inv_m, bf16, st);
+    if (tc_pointwise_wgrad_supported(g) && !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15))
+        return tc_pointwise_wgrad(x, dy, gw, gb, g, inv_m, st);
     const int K = g->C * g->kh * g->kw;
     const int npx = g->OH * g->OW;
     const int mt = (K + 1 + CBM - 1) / CBM;

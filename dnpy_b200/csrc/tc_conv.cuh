@@ -26,6 +26,8 @@ bool tc_conv_wgrad_sv_supported(const dnb_win_t* g);
 int tc_conv_wgrad_sv(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, bool bf16, cudaStream_t st);
 
 // tc_conv_thin.cu: tensor-core weight gradient of the single-channel 3x3 stride-1 convolution (dY straight from TMA)
+bool tc_pointwise_wgrad_supported(const dnb_win_t* g);
+int tc_pointwise_wgrad(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, cudaStream_t st);
 bool tc_thin_wgrad_supported(const dnb_win_t* g);
 int tc_thin_wgrad(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, cudaStream_t st);
 

@@ -306,3 +306,176 @@ int tc_thin_wgrad(const float* x, const float* dy, float* gw, float* gb, const d
 }
 
 }  // namespace dnb
+
+// =====================================================================================================
+// Pointwise (1x1) convolution weight gradient: gW[f][c] = (1/m) sum_{b,px} dY[b,f,px] * X[b,c,px], gb[f] = (1/m) sum dY.
+// Both operands are K-major (pixels contiguous) exactly as they lie in NCHW memory: A = dY[b] (F rows) and B = X[b] (C rows)
+// arrive as TMA boxes {32 px, rows} with the 128B swizzle — no transposer, no register ever holds an operand.  A constant
+// all-ones B tile yields the bias gradient from the same A tiles.  Two TMEM accumulators (gW: N = C columns, gb: N = 16)
+// persist over all (image, 64-pixel slot) units of the CTA; one small epilogue of atomics at the end.
+//   warp 0: TMA producer (64-pixel slots: two boxes per operand, one barrier)   warp 1: MMA issue   warps 2-5: epilogue
+// =====================================================================================================
+namespace dnb {
+namespace tc {
+
+struct PwWgParams {
+    float* gw; float* gb;
+    int B, C, F, npx;
+    int slots_per_img;           // ceil(npx / 64)
+    long units;                  // B * slots_per_img
+    float inv_m;
+};
+constexpr int PW_THREADS = 6 * 32;
+constexpr int PW_SLOTS = 6;
+
+template <int M>
+__global__ void __launch_bounds__(PW_THREADS, 1)
+tc_pointwise_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, PwWgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t a_blk = (uint32_t)p.F * 128, b_blk = (uint32_t)p.C * 128;       // one 32-pixel block of dY / X
+    const uint32_t a_pitch = a_blk > (uint32_t)M * 128 ? a_blk : (uint32_t)M * 128; // an M-row MMA reads M rows: keep them in the slot
+    const uint32_t slot_bytes = 2 * a_pitch + 2 * b_blk;
+    uint8_t* sOnes = smem;                                  // [16 rows x 32 px] of 1.0f (swizzle invariant)
+    uint8_t* sS = smem + 2048;                              // PW_SLOTS slots: A block 0, A block 1, B block 0, B block 1
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sS + (size_t)PW_SLOTS * slot_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + PW_SLOTS;
+    uint64_t* acc_full = bars + 2 * PW_SLOTS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PW_SLOTS + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const long mine = (p.units - (long)blockIdx.x + (long)gridDim.x - 1) / (long)gridDim.x;
+    const uint32_t ncols = (uint32_t)p.C + 16;              // gW columns, then 16 for the bias gradient
+    const uint32_t tmem_cols = ncols <= 32 ? 32 : (ncols <= 64 ? 64 : (ncols <= 128 ? 128 : 256));
+
+    for (int e = tid; e < 2048 / 4; e += PW_THREADS) reinterpret_cast<float*>(sOnes)[e] = 1.f;
+    // rows F..M-1 of an A block are never written by TMA when F < M: zero them once (they only feed unused D rows)
+    for (uint32_t e = tid; e < PW_SLOTS * slot_bytes / 16; e += PW_THREADS) reinterpret_cast<float4*>(sS)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) {
+        tma_prefetch_desc(&tmD); tma_prefetch_desc(&tmX);
+        for (int s = 0; s < PW_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (long n = 0; n < mine; ++n) {
+                const int s = (int)(n % PW_SLOTS);
+                if (n >= PW_SLOTS) mbar_wait_spin(&empty[s], (uint32_t)((n / PW_SLOTS) - 1) & 1);
+                const long u = (long)blockIdx.x + n * gridDim.x;
+                const int b = (int)(u / p.slots_per_img), px0 = (int)(u % p.slots_per_img) * 64;
+                uint8_t* st = sS + (size_t)s * slot_bytes;
+                mbar_arrive_expect_tx(&full[s], 2 * (a_blk + b_blk));
+                tma_load_3d(st, &tmD, px0, 0, b, &full[s]);                       // pixels past npx arrive as zeros
+                tma_load_3d(st + a_pitch, &tmD, px0 + 32, 0, b, &full[s]);
+                tma_load_3d(st + 2 * a_pitch, &tmX, px0, 0, b, &full[s]);
+                tma_load_3d(st + 2 * a_pitch + b_blk, &tmX, px0 + 32, 0, b, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc_w = make_idesc_tf32(M, p.C, 0, 0), idesc_b = make_idesc_tf32(M, 16, 0, 0);
+        const uint64_t ones = make_smem_desc(smem_u32(sOnes), 16, 1024);
+        for (long n = 0; n < mine; ++n) {
+            const int s = (int)(n % PW_SLOTS);
+            mbar_wait_spin(&full[s], (uint32_t)(n / PW_SLOTS) & 1);
+            tc_fence_after();
+            const uint32_t st = smem_u32(sS + (size_t)s * slot_bytes);
+            if (elect_one()) {
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    const uint64_t a = make_smem_desc(st + blk * a_pitch, 16, 1024);
+                    const uint64_t bx = make_smem_desc(st + 2 * a_pitch + blk * b_blk, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t acc = (n > 0 || blk > 0 || k > 0) ? 1u : 0u;
+                        mma_tf32(tmem_base, a + 2 * k, bx + 2 * k, idesc_w, acc);
+                        mma_tf32(tmem_base + (uint32_t)p.C, a + 2 * k, ones + 2 * k, idesc_b, acc);
+                    }
+                }
+                mma_commit(&empty[s]);
+                if (n == mine - 1) mma_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else if (mine > 0) {
+        // ---- epilogue: D[f][c] -> gW[f][c], D[f][C] -> gb[f] ----
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int f = M == 64 ? (lane < 16 ? q * 16 + lane : p.F) : q * 32 + lane;
+        for (int c0 = 0; c0 < (int)ncols; c0 += 16) {
+            uint32_t v[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0) : "memory");
+            tmem_ld_wait();
+            if (f < p.F) {
+                if (c0 < p.C) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) atomicAdd(p.gw + (size_t)f * p.C + c0 + j, __uint_as_float(v[j]) * p.inv_m);
+                } else if (p.gb) {
+                    atomicAdd(p.gb + f, __uint_as_float(v[0]) * p.inv_m);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static size_t pw_smem(const dnb_win_t* g, int M) {
+    const size_t a_pitch = std::max<size_t>((size_t)g->F * 128, (size_t)M * 128);
+    return 2048 + (size_t)PW_SLOTS * (2 * a_pitch + 2 * (size_t)g->C * 128) + (2 * PW_SLOTS + 4) * 8 + 1024;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+bool tc_pointwise_wgrad_supported(const dnb_win_t* g) {
+    if (!get_encode_tiled() || getenv("DNB_NO_TC_PW")) return false;
+    if (g->kh != 1 || g->kw != 1 || g->sy != 1 || g->sx != 1 || g->pt || g->pb || g->pl || g->pr) return false;
+    if (g->F != 32 && g->F != 64 && g->F != 128) return false;
+    if (g->C % 16 || g->C < 16 || g->C > 128) return false;
+    const long npx = (long)g->H * g->W;
+    if (npx % 4 || npx < 64) return false;
+    return pw_smem(g, g->F <= 64 ? 64 : 128) <= 225 * 1024;
+}
+
+int tc_pointwise_wgrad(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, cudaStream_t st) {
+    if (!tc_pointwise_wgrad_supported(g)) return set_err(DNB_ERR_UNSUPPORTED, "conv2d_bwd_weight(pointwise tc): unsupported shape");
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15))
+        return set_err(DNB_ERR_UNSUPPORTED, "conv2d_bwd_weight(pointwise tc): tensors must be 16-byte aligned");
+    const int npx = g->H * g->W;
+    PwWgParams p{gw, gb, g->B, g->C, g->F, npx, (npx + 63) / 64, (long)g->B * ((npx + 63) / 64), inv_m};
+    CUtensorMap td, tx;
+    uint64_t dd[3] = {(uint64_t)npx, (uint64_t)g->F, (uint64_t)g->B}, ds[2] = {(uint64_t)npx * 4, (uint64_t)npx * g->F * 4};
+    uint32_t dbx[3] = {32, (uint32_t)g->F, 1};
+    uint64_t xd[3] = {(uint64_t)npx, (uint64_t)g->C, (uint64_t)g->B}, xs[2] = {(uint64_t)npx * 4, (uint64_t)npx * g->C * 4};
+    uint32_t xbx[3] = {32, (uint32_t)g->C, 1};
+    if (!make_tmap_f32(&td, dy, 3, dd, ds, dbx, 0) || !make_tmap_f32(&tx, x, 3, xd, xs, xbx, 0))
+        return set_err(DNB_ERR_CUDA, "conv2d_bwd_weight(pointwise tc): cuTensorMapEncodeTiled failed");
+    const int grid = (int)std::min<long>(p.units, kNumSMs);
+    if (g->F <= 64) {
+        const size_t smem = pw_smem(g, 64);
+        cudaFuncSetAttribute(tc_pointwise_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc_pointwise_wgrad_kernel<64><<<grid, PW_THREADS, smem, st>>>(td, tx, p);
+    } else {
+        const size_t smem = pw_smem(g, 128);
+        cudaFuncSetAttribute(tc_pointwise_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc_pointwise_wgrad_kernel<128><<<grid, PW_THREADS, smem, st>>>(td, tx, p);
+    }
+    DNB_LAUNCH_CHECK("tc_pointwise_bwd_weight");
+    return DNB_OK;
+}
+
+}  // namespace dnb

@@ -1,4 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_layers.py tests/test_gpu_nets.py tests/test_abi.py -m gpu -x -q -k "conv or res_conv or abi" 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_layers.py tests/test_gpu_nets.py -m gpu -x -q -k "ointwise or res_conv" 2>&1 | tail -4
 timeout 300 python bench.py --no-cpu --workload res_conv > gpurun_out/bench_res_conv_bf16.json 2> gpurun_out/bench_res_conv_bf16.err; echo "rc $?"
 python - <<PY
 import json
