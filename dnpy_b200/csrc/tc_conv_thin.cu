@@ -33,7 +33,8 @@ struct ThinWgParams {
 
 constexpr int TW_TR = 8;                                   // transposer warps
 constexpr int TW_THREADS = (2 + TW_TR) * 32;
-constexpr int TW_SLOTS = 16;                               // A ring: dY chunks in flight
+constexpr int TW_SLOTS = 6;                                // A ring: dY slots in flight
+constexpr int TW_CPS = 4;                                  // 32-pixel chunks (TMA boxes) per slot: one barrier round trip per 128 px
 constexpr int TW_TB = 8;                                   // im2col task slots per transposer thread
 constexpr int TW_XR = 4;                                   // raw input images in flight: requested TW_XR-1 images ahead, so the
                                                            // load + im2col latency of image n+1 hides behind the MMAs of image n
@@ -42,7 +43,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
 tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, ThinWgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t slot_bytes = (uint32_t)p.F * 128;                       // one dY chunk: F rows x 32 px
+    const uint32_t box_bytes = (uint32_t)p.F * 128;                        // one dY chunk: F rows x 32 px
+    const uint32_t slot_bytes = TW_CPS * box_bytes;
     const uint32_t xc_bytes = (uint32_t)p.nchunks * 2048;                  // one Xcol buffer: 16 rows x 32 px per chunk
     const uint32_t xr_bytes = ((uint32_t)p.H * p.W * 4 + 127) & ~127u;     // one raw input image
     uint8_t* sA = smem;                                    // TW_SLOTS chunks (+4 KB slack: an M=64 MMA over F=32 rows reads on)
@@ -117,14 +119,14 @@ tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, ThinWgParams p) {
                 if (n + PF < nimg)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.dy + (size_t)(b + PF * (int)gridDim.x) * p.npx * p.F), "r"(img_bytes) : "memory");
                 if (n + TW_XR - 1 < nimg) issue_raw(n + TW_XR - 1);
-                for (int c = 0; c < p.nchunks; ++c, ++it) {
+                for (int c = 0; c < p.nchunks; c += TW_CPS, ++it) {
                     const int s = it % TW_SLOTS;
-                    // slots are released in groups of four: one tcgen05.commit per four chunks (a commit per chunk made the
-                    // skeleton alone cost ~330 clk per 4 KB chunk)
-                    if (it >= TW_SLOTS && (s & 3) == 0) { TW_T0(); mbar_wait_spin(&a_empty[s >> 2], ((it / TW_SLOTS) - 1) & 1); TW_ACC(w_ae); }
+                    if (it >= TW_SLOTS) { TW_T0(); mbar_wait_spin(&a_empty[s], ((it / TW_SLOTS) - 1) & 1); TW_ACC(w_ae); }
                     if (p.debug & 2) { mbar_arrive(&a_full[s]); continue; }
                     mbar_arrive_expect_tx(&a_full[s], slot_bytes);
-                    tma_load_3d(sA + (size_t)s * slot_bytes, &tmD, c * 32, 0, b, &a_full[s]);   // pixels past npx arrive as zeros
+#pragma unroll
+                    for (int k = 0; k < TW_CPS; ++k)          // chunks past npx arrive as zeros (and still count their bytes)
+                        tma_load_3d(sA + (size_t)s * slot_bytes + k * box_bytes, &tmD, (c + k) * 32, 0, b, &a_full[s]);
                 }
             }
             if (p.prof && blockIdx.x == 0) { p.prof[0] = w_ae; p.prof[1] = w_xre; p.prof[2] = clock64() - t_begin; }
@@ -140,22 +142,26 @@ tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, ThinWgParams p) {
             { TW_T0(); mbar_wait(&xc_full[buf], (n >> 1) & 1); TW_ACC(w_xcf); }
             tc_fence_after();
             const uint64_t b0 = make_smem_desc(smem_u32(sXc + (size_t)buf * xc_bytes), 16, 1024);
-            for (int c = 0; c < p.nchunks; ++c, ++it) {
+            for (int c = 0; c < p.nchunks; c += TW_CPS, ++it) {
                 const int s = it % TW_SLOTS;
                 { TW_T0(); mbar_wait_spin(&a_full[s], (it / TW_SLOTS) & 1); TW_ACC(w_af); }
                 tc_fence_after();
-                const uint64_t a = make_smem_desc(smem_u32(sA + (size_t)s * slot_bytes), 16, 1024);
-                const uint64_t bq = b0 + (uint64_t)((uint32_t)c * (2048 >> 4));
+                const uint64_t a0 = make_smem_desc(smem_u32(sA + (size_t)s * slot_bytes), 16, 1024);
                 if (elect_one()) {
-                    const uint32_t d0 = tmem_base + (uint32_t)(it & 1) * 64, acc = it > 1 ? 1u : 0u;
                     if (!(p.debug & 1)) {
-                    mma_tf32(d0, a, bq, idesc, acc);
-                    mma_tf32(d0 + 16, a + 2, bq + 2, idesc, acc);
-                    mma_tf32(d0 + 32, a + 4, bq + 4, idesc, acc);
-                    mma_tf32(d0 + 48, a + 6, bq + 6, idesc, acc);
+#pragma unroll
+                        for (int k = 0; k < TW_CPS; ++k) {
+                            const uint64_t a = a0 + (uint64_t)(k * (box_bytes >> 4));
+                            const uint64_t bq = b0 + (uint64_t)((uint32_t)(c + k) * (2048 >> 4));
+                            const uint32_t d0 = tmem_base + (uint32_t)(k & 1) * 64, acc = (it > 0 || k > 1) ? 1u : 0u;
+                            mma_tf32(d0, a, bq, idesc, acc);
+                            mma_tf32(d0 + 16, a + 2, bq + 2, idesc, acc);
+                            mma_tf32(d0 + 32, a + 4, bq + 4, idesc, acc);
+                            mma_tf32(d0 + 48, a + 6, bq + 6, idesc, acc);
+                        }
                     }
-                    if ((s & 3) == 3) mma_commit(&a_empty[s >> 2]);
-                    if (c == p.nchunks - 1) mma_commit(&xc_empty[buf]);
+                    mma_commit(&a_empty[s]);
+                    if (c + TW_CPS >= p.nchunks) mma_commit(&xc_empty[buf]);
                 }
                 __syncwarp();
             }
@@ -222,7 +228,7 @@ tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, ThinWgParams p) {
             mbar_wait(acc_full, 0);
             tc_fence_after();
             const int q = warp & 3;
-            const int nacc = (long)nimg * p.nchunks > 1 ? 8 : 4;      // accumulators that were ever written
+            const int nacc = 8;                                       // every slot writes all eight (TW_CPS = 4 chunks)
             float sum[10];
 #pragma unroll
             for (int k = 0; k < 10; ++k) sum[k] = 0.f;
@@ -250,8 +256,8 @@ tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmD, ThinWgParams p) {
 }
 
 static size_t tw_smem(const dnb_win_t* g) {
-    const size_t npx = (size_t)g->OH * g->OW, nchunks = (npx + 31) / 32;
-    return (size_t)TW_SLOTS * g->F * 128 + 4096 + 2 * nchunks * 2048 + TW_XR * (((size_t)g->H * g->W * 4 + 127) & ~(size_t)127) +
+    const size_t npx = (size_t)g->OH * g->OW, nchunks = ((npx + 31) / 32 + TW_CPS - 1) / TW_CPS * TW_CPS;
+    return (size_t)TW_SLOTS * TW_CPS * g->F * 128 + 4096 + 2 * nchunks * 2048 + TW_XR * (((size_t)g->H * g->W * 4 + 127) & ~(size_t)127) +
            (2 * TW_SLOTS + 2 * TW_XR + 8) * 8 + 1024;
 }
 
@@ -260,11 +266,11 @@ static size_t tw_smem(const dnb_win_t* g) {
 using namespace tc;
 
 bool tc_thin_wgrad_supported(const dnb_win_t* g) {
-    // EXPERIMENT, off by default (DNB_TC_THIN=1 enables it).  Measured on B200 (B=8192, F=32, 26x26): 260-310 us against
-    // 168 us for the FP32 register-tiled kernel.  Per-role clocks (DNB_SV_PROF=1): with MMAs, dY loads and im2col all
-    // disabled the barrier skeleton alone costs ~350 clk per 4 KB chunk (TMA -> full barrier -> fence -> commit -> empty
-    // barrier round trips), and an N=16 tf32 MMA issues every ~39 clk, i.e. 88 MMAs = 3.4 k clk per image: a ~96 us floor
-    // before any synchronisation.  A K=9 contraction is too thin to amortise tcgen05's fixed per-instruction costs.
+    // EXPERIMENT, off by default (DNB_TC_THIN=1 enables it).  Measured on B200 (B=8192, F=32, 26x26): 168 us — the same as
+    // the FP32 register-tiled kernel (with one barrier round trip per 4 KB chunk it was 260-310 us: ~350 clk of TMA -> full
+    // barrier -> fence -> commit -> empty barrier latency per chunk; 128-pixel slots fixed that).  Debug switches: no MMAs
+    // 117 us, bare skeleton 98 us — the 96 M=64/N=16/K=8 MMAs per image cost ~60 clk each and are the bound.  A K=9
+    // contraction with 32 filters uses 1/8 of an MMA's rows x columns: too thin to beat FP32 FMAs.
     if (!get_encode_tiled() || !getenv("DNB_TC_THIN")) return false;
     if (g->C != 1 || g->kh != 3 || g->kw != 3 || g->sy != 1 || g->sx != 1) return false;
     if (g->F != 32 && g->F != 64) return false;
@@ -278,7 +284,9 @@ int tc_thin_wgrad(const float* x, const float* dy, float* gw, float* gb, const d
     if (!tc_thin_wgrad_supported(g)) return set_err(DNB_ERR_UNSUPPORTED, "conv2d_bwd_weight(thin tc): unsupported shape");
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15))
         return set_err(DNB_ERR_UNSUPPORTED, "conv2d_bwd_weight(thin tc): tensors must be 16-byte aligned");
-    ThinWgParams p{x, dy, gw, gb, g->B, g->H, g->W, g->F, g->OH, g->OW, g->pt, g->pl, g->OH * g->OW, (g->OH * g->OW + 31) / 32, inv_m,
+    // chunks per image rounded up to whole slots: the extra chunks are all-zero K padding on both operands
+    ThinWgParams p{x, dy, gw, gb, g->B, g->H, g->W, g->F, g->OH, g->OW, g->pt, g->pl, g->OH * g->OW,
+                   ((g->OH * g->OW + 31) / 32 + TW_CPS - 1) / TW_CPS * TW_CPS, inv_m,
                    getenv("DNB_TW_DEBUG") ? atoi(getenv("DNB_TW_DEBUG")) : 0, nullptr};
     if (getenv("DNB_SV_PROF")) {
         static unsigned long long* dprof = nullptr;

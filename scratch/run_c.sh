@@ -1,8 +1,3 @@
-timeout 900 python -m pytest tests/test_gpu_layers.py tests/test_gpu_nets.py -m gpu -x -q -k "ointwise or res_conv" 2>&1 | tail -4
-timeout 300 python bench.py --no-cpu --workload res_conv > gpurun_out/bench_res_conv_bf16.json 2> gpurun_out/bench_res_conv_bf16.err; echo "rc $?"
-python - <<PY
-import json
-d=json.load(open('gpurun_out/bench_res_conv_bf16.json'))
-print(round(d['value']), d['unit'], d['ms_per_step'], 'loss', d['final_loss'])
-for t in d['top_kernels'][:10]: print(f"   {t['ms_per_step']*1e3:8.1f} us {t['share']*100:5.1f}% {t['frac']} {t['kernel']}")
-PY
+export DNB_TC_THIN=1
+python scratch/tw_bench.py 0 1 7 2>&1 | grep debug
+timeout 600 python -m pytest tests/test_gpu_layers.py -m gpu -x -q -k "big_conv1" 2>&1 | tail -3
