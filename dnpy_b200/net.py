@@ -547,6 +547,8 @@ class Net:
         if self.mode != "test":
             print("[WARNING] Setting net mode to 'test'")
             self.set_mode('test')
+        if self._can_evaluate_in_chunks(batch_size):
+            return self._evaluate_chunked(x_test, y_test, batch_size, num_batches)
         losses, metrics = [], []
         for b in range(num_batches):
             x_mb, y_mb = [], []
@@ -565,6 +567,43 @@ class Net:
         metrics = [np.mean(me, axis=0) for me in metrics]
         assert len(losses) == len(self.losses)
         assert len(metrics) == len(self.losses)
+        return losses, metrics
+
+    # Net.fit evaluates the whole training and test set with batch_size=1 after every printed epoch (net.py:197-210):
+    # one forward per SAMPLE.  In test mode every layer is independent per sample (BatchNorm uses its moving statistics,
+    # Dropout scales), and MSE / BCE / CE / MAE and the accuracies are plain means over samples, so the mean of the
+    # per-batch values over the first num_batches*batch_size samples equals the sample-weighted mean over ANY partition
+    # of them: evaluate in chunks of up to EVAL_CHUNK samples.  Anything else (RMSE: a square root of a
+    # mean) keeps the literal per-batch loop.  DNPY_B200_EVAL_LITERAL=1 forces the literal loop.
+    EVAL_CHUNK = 4096
+    _ADDITIVE = ("MSE", "MAE", "BinaryCrossEntropy", "CrossEntropy", "BinaryAccuracy", "CategoricalAccuracy")
+
+    def _can_evaluate_in_chunks(self, batch_size):
+        import os
+        if os.environ.get("DNPY_B200_EVAL_LITERAL") or batch_size >= self.EVAL_CHUNK or self.mode != "test":
+            return False
+        names = [type(lo).__name__ for lo in self.losses] + [type(me).__name__ for row in self.metrics for me in row]
+        return all(n in self._ADDITIVE for n in names)
+
+    def _evaluate_chunked(self, x_test, y_test, batch_size, num_batches):
+        total = num_batches * batch_size
+        chunk = max(1, self.EVAL_CHUNK // batch_size) * batch_size
+        acc_l = np.zeros(len(self.losses))
+        acc_m = [np.zeros(len(row)) for row in self.metrics]
+        for lo_i in range(0, total, chunk):
+            n = min(chunk, total - lo_i)
+            x_mb = [x_test[j][lo_i:lo_i + n] for j in range(len(self.l_in))]
+            y_mb = [y_test[j][lo_i:lo_i + n] for j in range(len(self.l_in))]
+            self.feed_input(x_mb)
+            self.forward()
+            for i in range(len(self.losses)):
+                loss = self.losses[i].compute_loss(self.l_out[i].output, y_mb[i])
+                self._raise_on_flags(loss, self.losses[i], self.l_out[i].output, y_mb[i], flags=0)
+                acc_l[i] += float(loss) * n
+            for i, row in enumerate(self.compute_metrics(y_target=y_mb)):
+                acc_m[i] += np.asarray(row, dtype=np.float64) * n
+        losses = acc_l / float(total)
+        metrics = [m / float(total) for m in acc_m]
         return losses, metrics
 
     # ------------------------------------------------------------------ summary / params / checkpoint

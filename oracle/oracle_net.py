@@ -248,6 +248,13 @@ class OracleNet:
                 else:
                     O.sgd_apply(n.params[k], n.grads[k], st['V'], o["lr"], o["momentum"], o["nesterov"])
 
+    def forward_loss(self, x_mb, y_mb):
+        """feed_input + forward + losses only (what Net.evaluate does per batch, net.py:237-253)."""
+        for j, n in enumerate(self.l_in):
+            n.output = np.asarray(x_mb[j]) if self.l_in[j].src.__class__.__name__ == "Input" else x_mb[j]
+        self.forward()
+        return self.compute_losses(y_mb)[0]
+
     def step(self, x_mb, y_mb, apply=True):
         """One iteration of net.py:176-195; returns the list of losses."""
         for j, n in enumerate(self.l_in):

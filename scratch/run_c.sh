@@ -1,3 +1,1 @@
-export DNB_TC_THIN=1
-python scratch/tw_bench.py 0 1 7 2>&1 | grep debug
-timeout 600 python -m pytest tests/test_gpu_layers.py -m gpu -x -q -k "big_conv1" 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_nets.py -m gpu -x -q -k "evaluate or fit or save_load" 2>&1 | tail -6

@@ -230,6 +230,32 @@ def test_fit_evaluate_api(ns, capsys):
     net.fit([x], [y], batch_size=8, epochs=3, evaluate_epoch=True, print_rate=2, x_test=[x], y_test=[y])
 
 
+def test_evaluate_in_chunks_equals_the_literal_per_batch_loop(ns, monkeypatch):
+    """Net.evaluate(batch_size=1) as Net.fit calls it (net.py:197-210): the chunked test-mode evaluation must
+    return what the literal one-forward-per-batch loop returns, and what the float64 oracle computes per sample."""
+    np.random.seed(7)
+    net = topologies.mnist_cnn(ns, f1=2, f2=4)
+    onet = OracleNet.mirror(net)
+    rs = np.random.RandomState(3)
+    x, y = topologies.make_data("mnist_cnn", 37, rs)
+    net.set_mode("test"); onet.set_mode("test")
+    monkeypatch.setattr(type(net), "EVAL_CHUNK", 16)            # several chunks, the last one ragged
+    lo_c, me_c = net.evaluate([x], [y], batch_size=1)
+    monkeypatch.setenv("DNPY_B200_EVAL_LITERAL", "1")
+    lo_l, me_l = net.evaluate([x], [y], batch_size=1)
+    assert abs(lo_c[0] - lo_l[0]) <= 1e-6 * max(1.0, abs(lo_l[0]))
+    assert abs(float(me_c[0][0]) - float(me_l[0][0])) <= 1e-9
+    # batch_size that does not divide the set: the reference drops the remainder
+    monkeypatch.delenv("DNPY_B200_EVAL_LITERAL")
+    lo_c5, _ = net.evaluate([x], [y], batch_size=5)
+    monkeypatch.setenv("DNPY_B200_EVAL_LITERAL", "1")
+    lo_l5, _ = net.evaluate([x], [y], batch_size=5)
+    assert abs(lo_c5[0] - lo_l5[0]) <= 1e-6 * max(1.0, abs(lo_l5[0]))
+    # float64 oracle, one sample at a time
+    want = np.mean([onet.forward_loss([x[i:i + 1]], [y[i:i + 1]])[0] for i in range(len(x))])
+    assert abs(lo_c[0] - want) <= 1e-5 * max(1.0, abs(want))
+
+
 def test_save_load_roundtrip_device(tmp_path, ns):
     np.random.seed(1)
     net = topologies.mnist_cnn(ns, f1=2, f2=4)
