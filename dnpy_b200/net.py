@@ -31,6 +31,26 @@ from .runtime import config
 _ALIGN = 32     # floats: every arena slot starts on a 128-byte boundary (TMA / float4 friendly)
 
 
+class _ResidentSlice:
+    """A row block of a dataset that Net.fit uploaded once: a CUDA tensor view.  `_stage_in` copies it
+    device-to-device into the step's persistent input buffer, so buffer addresses (and the captured step graph) do not
+    depend on the minibatch index."""
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t
+
+    def __len__(self):
+        return int(self.t.shape[0])
+
+    def __getitem__(self, key):
+        return _ResidentSlice(self.t[key])
+
+    @property
+    def shape(self):
+        return tuple(self.t.shape)
+
+
 def check_datasets(x_train, y_train, x_test, y_test):
     """net.py:10-35."""
     if x_train and y_train and x_test and y_test:
@@ -199,13 +219,13 @@ class Net:
             for k in l.grads.keys():
                 l.grads[k].fill(0.0)
 
-    def feed_input(self, x):
+    def feed_input(self, x, key="x"):
         """net.py:304-307.  On a CUDA device this is the H2D boundary: each input minibatch is copied
         (asynchronously when the source is pinned) into a persistent device buffer, so its address
         is stable across steps."""
         ready = self._device_ready()
         for j in range(len(self.l_in)):
-            self.l_in[j].output = self._stage_in(("x", j), x[j], self._input_is_int(j)) if ready else x[j]
+            self.l_in[j].output = self._stage_in((key, j), x[j], self._input_is_int(j)) if ready else x[j]
 
     def _input_is_int(self, j):
         from .layers import Embedding
@@ -220,7 +240,10 @@ class Net:
         if isinstance(a, DArray):
             return a
         t = torch()
-        if t.is_tensor(a):
+        resident = isinstance(a, _ResidentSlice)
+        if resident:
+            src = a.t
+        elif t.is_tensor(a):
             src = a
             if src.is_cuda:
                 return DArray.device(src, is_int=is_int)
@@ -245,7 +268,9 @@ class Net:
         if k > 0:
             st["free"][prev].record(cur)          # everything queued so far (the previous step) has read slot `prev`
         buf = st["bufs"][slot]
-        if src.is_pinned():
+        if resident:
+            buf.copy_(src, non_blocking=True)       # device-to-device, stream ordered behind the previous step
+        elif src.is_pinned():
             if self._copy_stream is None:
                 self._copy_stream = t.cuda.Stream()
             cs = self._copy_stream
@@ -484,6 +509,10 @@ class Net:
         num_samples = len(x_train[0])
         num_batches = int(num_samples / batch_size)
         verbose = config.rank == 0
+        # dataset residency: upload the sets once (fp32 / int32) and slice minibatches on the device
+        x_train, y_train = self._make_resident(x_train, y_train)
+        if x_test is not None and y_test is not None:
+            x_test, y_test = self._make_resident(x_test, y_test)
 
         for i in range(epochs):
             printing = (i % print_rate) == 0
@@ -495,6 +524,7 @@ class Net:
                 x_mb, y_mb = self.get_minibatch(x_train, y_train, b, batch_size)
                 if printing:
                     # reference order: forward, losses (+guards), metrics, print, then the update
+                    y_mb = [DArray.device(v.t) if isinstance(v, _ResidentSlice) else v for v in y_mb]
                     self.feed_input(x_mb)
                     self.forward()
                     b_losses, b_deltas = self.compute_losses(y_target=y_mb)
@@ -527,6 +557,29 @@ class Net:
                     if verbose:
                         print(f"\t - Validation losses[{', '.join(str_eval[0])}]; Validation metrics[{'; '.join(str_eval[1])}];")
 
+    RESIDENT_BYTES = 16 << 30
+
+    def _make_resident(self, xs, ys):
+        """Upload a dataset once if it fits RESIDENT_BYTES (and a device is present); else leave it on the host."""
+        import os
+        if not self._device_ready() or os.environ.get("DNPY_B200_NO_RESIDENT"):
+            return xs, ys
+        if any(isinstance(a, (_ResidentSlice, DArray)) for a in list(xs) + list(ys)):
+            return xs, ys
+        t = torch()
+        total = sum(int(np.prod(np.shape(a))) * 4 for a in list(xs) + list(ys))
+        if total > self.RESIDENT_BYTES:
+            return xs, ys
+
+        def up(a, is_int):
+            if t.is_tensor(a):
+                src = a
+            else:
+                src = t.from_numpy(np.ascontiguousarray(np.asarray(a), dtype=np.int32 if is_int else np.float32))
+            return _ResidentSlice(src.to("cuda", dtype=t.int32 if is_int else t.float32).contiguous())
+
+        return ([up(a, self._input_is_int(j)) for j, a in enumerate(xs)], [up(a, False) for a in ys])
+
     def _check_pending(self):
         """Deferred NaN/Inf guard for the non-printing steps (one sync per 64 steps, not per step)."""
         pend, self._pending_flags = self._pending_flags, []
@@ -556,7 +609,8 @@ class Net:
             for j in range(len(self.l_in)):
                 x_mb += [x_test[j][lo_i:lo_i + batch_size]]
                 y_mb += [y_test[j][lo_i:lo_i + batch_size]]
-            self.feed_input(x_mb)
+            y_mb = [DArray.device(v.t) if isinstance(v, _ResidentSlice) else v for v in y_mb]
+            self.feed_input(x_mb, key="x_eval")      # own staging buffers: the training step graph keeps its addresses
             self.forward()
             lo, de = self.compute_losses(y_target=y_mb)
             losses.append(lo)
@@ -594,7 +648,8 @@ class Net:
             n = min(chunk, total - lo_i)
             x_mb = [x_test[j][lo_i:lo_i + n] for j in range(len(self.l_in))]
             y_mb = [y_test[j][lo_i:lo_i + n] for j in range(len(self.l_in))]
-            self.feed_input(x_mb)
+            y_mb = [DArray.device(v.t) if isinstance(v, _ResidentSlice) else v for v in y_mb]
+            self.feed_input(x_mb, key="x_eval")      # own staging buffers: the training step graph keeps its addresses
             self.forward()
             for i in range(len(self.losses)):
                 loss = self.losses[i].compute_loss(self.l_out[i].output, y_mb[i])

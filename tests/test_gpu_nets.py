@@ -256,6 +256,25 @@ def test_evaluate_in_chunks_equals_the_literal_per_batch_loop(ns, monkeypatch):
     assert abs(lo_c[0] - want) <= 1e-5 * max(1.0, abs(want))
 
 
+def test_fit_with_resident_dataset_equals_host_minibatches(ns, monkeypatch, capsys):
+    """Net.fit uploads the dataset once and slices minibatches on the device: same parameters, same printed
+    losses as feeding host minibatches step by step (also covers the last ragged evaluate chunk and a non-printing epoch)."""
+    rs = np.random.RandomState(5)
+    x, y = topologies.make_data("mnist_cnn", 40, rs)
+    runs = []
+    for no_res in ("", "1"):
+        if no_res:
+            monkeypatch.setenv("DNPY_B200_NO_RESIDENT", "1")
+        np.random.seed(11)
+        net = topologies.mnist_cnn(ns, f1=2, f2=4)
+        net.fit([x], [y], batch_size=8, epochs=3, evaluate_epoch=True, print_rate=2, x_test=[x[:16]], y_test=[y[:16]])
+        runs.append(([dict((k, np.asarray(v).copy()) for k, v in l.params.items()) for l in net.fts_layers], capsys.readouterr().out))
+    for pa, pb in zip(runs[0][0], runs[1][0]):
+        for k in pa:
+            assert np.array_equal(pa[k], pb[k]), k
+    assert runs[0][1] == runs[1][1]
+
+
 def test_save_load_roundtrip_device(tmp_path, ns):
     np.random.seed(1)
     net = topologies.mnist_cnn(ns, f1=2, f2=4)
