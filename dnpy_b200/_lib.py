@@ -63,6 +63,7 @@ SIGNATURES = {
     "dnb_mul": (_i, [_p, _p, _p, _z, _p]),
     "dnb_scale": (_i, [_p, _p, _z, _f, _p]),
     "dnb_add_n": (_i, [C.POINTER(_p), _i, _p, _z, _p]),
+    "dnb_merge_n": (_i, [C.POINTER(_p), _i, _p, _z, _i, _f, _p]),
     "dnb_batchnorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _z, _f, _f, _i, _p]),
     "dnb_batchnorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _z, _p]),
     "dnb_embedding_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),

@@ -162,6 +162,27 @@ __global__ void __launch_bounds__(EW_BLOCK) add_n_kernel(PtrPack xs, int n_in, f
     }
 }
 
+// ---- point-wise merges over n inputs (merge.py:13-16,29-62): out = x0 op x1 op x2 ... (left fold, the reference's order) ----
+__device__ __forceinline__ float merge_op(int op, float a, float b) {
+    switch (op) {
+        case DNB_MERGE_SUB: return a - b;
+        case DNB_MERGE_MUL: return a * b;
+        case DNB_MERGE_DIV: return a / b;
+        case DNB_MERGE_POW: return powf(a, b);
+        case DNB_MERGE_MAX: return (a != a || b != b) ? (a + b) : fmaxf(a, b);      // np.maximum propagates NaN
+        case DNB_MERGE_MIN: return (a != a || b != b) ? (a + b) : fminf(a, b);
+        default: return a + b;
+    }
+}
+__global__ void __launch_bounds__(EW_BLOCK) merge_n_kernel(PtrPack xs, int n_in, float* __restrict__ y, size_t n, int op, float post) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < n; i += stride) {
+        float acc = xs.p[0][i];
+        for (int k = 1; k < n_in; ++k) acc = merge_op(op, acc, xs.p[k][i]);
+        y[i] = acc * post;
+    }
+}
+
 // ---- optimizers (dnpy/optimizers.py) -----------------------------------------------------
 // Adam, literal: no bias correction, epsilon under the sqrt (Q13).  28 B/param of HBM traffic.
 __global__ void __launch_bounds__(EW_BLOCK) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -355,6 +376,18 @@ int dnb_add_n(const float* const* xs, int n_in, float* y, size_t n, dnb_stream_t
     for (int i = 0; i < n_in; ++i) vec = vec && aligned16(xs[i]);
     add_n_kernel<<<ew_grid(vec ? n / 4 + 1 : n, EW_BLOCK), EW_BLOCK, 0, S(stream)>>>(pk, n_in, y, n, vec);
     DNB_LAUNCH_CHECK("add_n");
+    return DNB_OK;
+}
+
+int dnb_merge_n(const float* const* xs, int n_in, float* y, size_t n, int op, float post_scale, dnb_stream_t stream) {
+    DNB_CHECK_ARG(n_in >= 1 && n_in <= 8, "merge_n: between 1 and 8 inputs supported, got %d", n_in);
+    DNB_CHECK_ARG(op >= DNB_MERGE_ADD && op <= DNB_MERGE_MIN, "merge_n: unknown operator %d", op);
+    if (n == 0) return DNB_OK;
+    PtrPack pk;
+    for (int i = 0; i < 8; ++i) pk.p[i] = (i < n_in) ? xs[i] : nullptr;
+    for (int i = 0; i < n_in; ++i) DNB_CHECK_ARG(xs[i], "merge_n: null input %d", i);
+    merge_n_kernel<<<ew_grid(n, EW_BLOCK), EW_BLOCK, 0, S(stream)>>>(pk, n_in, y, n, op, post_scale);
+    DNB_LAUNCH_CHECK("merge_n");
     return DNB_OK;
 }
 

@@ -144,6 +144,17 @@ int dnb_mul(const float* a, const float* b, float* y, size_t n, dnb_stream_t str
 int dnb_scale(const float* x, float* y, size_t n, float s, dnb_stream_t stream);
 /* y = sum of n_in inputs (merge.py:13-16 with np.add) */
 int dnb_add_n(const float* const* xs, int n_in, float* y, size_t n, dnb_stream_t stream);
+/* MPWLayer.forward for the other point-wise merges (merge.py:13-16, 29-62): y = ((x0 op x1) op x2) ... * post_scale.
+ * Average.forward (merge.py:71-75) = DNB_MERGE_ADD with post_scale = 1/n_in.  Backward is a delta hand-over
+ * (merge.py:18-20; Average: dnb_scale by 1/n_in per parent, merge.py:77-79). */
+#define DNB_MERGE_ADD 0
+#define DNB_MERGE_SUB 1
+#define DNB_MERGE_MUL 2
+#define DNB_MERGE_DIV 3
+#define DNB_MERGE_POW 4
+#define DNB_MERGE_MAX 5
+#define DNB_MERGE_MIN 6
+int dnb_merge_n(const float* const* xs, int n_in, float* y, size_t n, int op, float post_scale, dnb_stream_t stream);
 /* BatchNorm over axis 0 of x[B, n_feat] (regularization.py:94-136).  training: computes
  * mu/var (biased) into save_mu/save_std (std = sqrt(var+eps)) and updates moving_* in place
  * with `momentum`; test: uses moving_*.  stat_sync, when non-NULL, is unused here (reserved

@@ -13,6 +13,10 @@ import numpy as np
 from . import dnpy_oracle as O
 
 
+_MERGE_OPS = {"Add": np.add, "Subtract": np.subtract, "Multiply": np.multiply, "Divide": np.divide, "Power": np.power,
+              "Maximum": np.maximum, "Minimum": np.minimum}
+
+
 def _reg(r):
     """(l1, l2) of a dnpy regularizer object (regularizers.py:16-53)."""
     if r is None:
@@ -131,11 +135,13 @@ class OracleNet:
                 raise NotImplementedError("BatchNorm(bias_correction=True) is out of scope")
             n.output, n.cache['bn'], P['moving_mu'], P['moving_var'] = O.batchnorm_forward(
                 x, P['gamma'], P['beta'], P['moving_mu'], P['moving_var'], s.momentum, n.training)
-        elif k == "Add":
-            out = np.array(n.parents[0].output)
+        elif k in _MERGE_OPS:                   # merge.py:13-16: left fold with the layer's NumPy operator
+            out = np.array(n.parents[0].output, dtype=np.float64)
             for p in n.parents[1:]:
-                out = out + p.output
+                out = _MERGE_OPS[k](out, p.output)
             n.output = out
+        elif k == "Average":                    # merge.py:71-75
+            n.output = np.sum([p.output for p in n.parents], axis=0) / len(n.parents)
         elif k == "Embedding":
             n.output = O.embedding_forward(np.asarray(x).astype(np.int64), P['w1'])
         elif k == "SimpleRNN":
@@ -199,9 +205,12 @@ class OracleNet:
             par.delta, gg, gb = O.batchnorm_backward(d, P['gamma'], n.cache['bn'])
             G['gamma'] += gg.reshape(G['gamma'].shape)
             G['beta'] += gb.reshape(G['beta'].shape)
-        elif k == "Add":
+        elif k in _MERGE_OPS:
             for p in n.parents:          # merge.py:18-20: same delta to every parent (Q10)
                 p.delta = d
+        elif k == "Average":             # merge.py:77-79
+            for p in n.parents:
+                p.delta = d / len(n.parents)
         elif k == "Embedding":
             O.embedding_backward_inplace(G['w1'], np.asarray(x).astype(np.int64), d)
         elif k == "SimpleRNN":

@@ -58,6 +58,13 @@ LAYER_CASES = [
     dict(name="batchnorm_train_3d", kind="BatchNorm", in_shape=(2, 3, 3), batch=4, kw=dict(momentum=0.9), training=True),
     dict(name="batchnorm_test", kind="BatchNorm", in_shape=(5,), batch=3, kw=dict(), training=False),
     dict(name="add3", kind="Add", in_shape=(4,), n_inputs=3, batch=3, kw=dict()),
+    dict(name="subtract3", kind="Subtract", in_shape=(5,), n_inputs=3, batch=4, kw=dict()),
+    dict(name="multiply3", kind="Multiply", in_shape=(2, 3), n_inputs=3, batch=3, kw=dict()),
+    dict(name="divide2", kind="Divide", in_shape=(6,), n_inputs=2, batch=3, kw=dict()),
+    dict(name="power2", kind="Power", in_shape=(6,), n_inputs=2, batch=3, positive=True, kw=dict()),
+    dict(name="maximum3", kind="Maximum", in_shape=(7,), n_inputs=3, batch=4, quantize=True, kw=dict()),
+    dict(name="minimum2", kind="Minimum", in_shape=(7,), n_inputs=2, batch=4, kw=dict()),
+    dict(name="average3", kind="Average", in_shape=(3, 2), n_inputs=3, batch=5, kw=dict()),
     dict(name="embedding_dups", kind="Embedding", in_shape=(5,), batch=4, int_input=7,
          kw=dict(input_dim=7, output_dim=3, input_length=5)),
     dict(name="rnn_trunc2", kind="SimpleRNN", in_shape=(6, 3), batch=3, kw=dict(hidden_dim=4, bptt_truncate=2)),
@@ -104,6 +111,8 @@ def case_inputs(case):
             x = rs.randn(case["batch"], *case["in_shape"])
             if case.get("negative"):
                 x = -np.abs(x) - 0.1
+            if case.get("positive"):
+                x = np.abs(x) + 0.25             # np.power on negative bases is NaN: keep the case meaningful
             if case.get("quantize"):
                 x = np.round(x * 2) / 2      # many exact ties -> first-max-wins matters
             xs.append(x)
