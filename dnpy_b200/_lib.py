@@ -75,6 +75,10 @@ SIGNATURES = {
     "dnb_loss_ce": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _p, _p]),
     "dnb_loss_bce": (_i, [_p, _p, _p, _p, _i, _i, _f, _p, _p]),
     "dnb_loss_mse": (_i, [_p, _p, _p, _p, _i, _i, _f, _p, _p]),
+    "dnb_loss_rmse": (_i, [_p, _p, _p, _p, _i, _i, _f, _p, _p]),
+    "dnb_loss_mae": (_i, [_p, _p, _p, _p, _i, _i, _f, _p, _p]),
+    "dnb_loss_nll": (_i, [_p, _p, _p, _p, _i, _i, _f, _p, _p]),
+    "dnb_loss_hinge": (_i, [_p, _p, _p, _p, _i, _i, _f, _p, _p]),
     "dnb_metric_categorical": (_i, [_p, _p, _p, _i, _i, _p]),
     "dnb_metric_binary": (_i, [_p, _p, _p, _i, _i, _f, _p]),
     "dnb_opt_adam": (_i, [_p, _p, _p, _p, _z, _f, _f, _f, _f, _p]),

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
     for (int j = lane; j < n; j += 32) dx[(size_t)row * n + j] = yr[j] * (dr[j] - s);
 }
 
-enum { LOSS_CE = 0, LOSS_CE_SM = 1, LOSS_BCE = 2, LOSS_MSE = 3 };
+enum { LOSS_CE = 0, LOSS_CE_SM = 1, LOSS_BCE = 2, LOSS_MSE = 3, LOSS_RMSE = 4, LOSS_MAE = 5, LOSS_NLL = 6, LOSS_HINGE = 7 };
 
 __device__ __forceinline__ int bad_bits(float v) { return (v != v ? 4 : 0) | (isinf(v) ? 8 : 0); }
 
@@ -64,6 +64,20 @@ __global__ void __launch_bounds__(256) loss_rows_kernel(const float* __restrict_
         } else if (KIND == LOSS_BCE) {
             v = tv * logf(pv + kEps) + (1.0f - tv) * logf(1.0f - pv + kEps);
             d = -1.0f * (tv * 1.0f / (pv + kEps) + (1.0f - tv) * 1.0f / (1.0f - pv + kEps) * -1.0f);
+        } else if (KIND == LOSS_RMSE) {                       // losses.py:34-43: sqrt of the mean; delta = e / sqrt(e^2 + eps)
+            float e = pv - tv;
+            v = e * e;
+            d = e / sqrtf(e * e + kEps);
+        } else if (KIND == LOSS_MAE) {                        // losses.py:50-58
+            float e = pv - tv;
+            v = fabsf(e);
+            d = (e > 0.f) ? 1.f : ((e < 0.f) ? -1.f : (e != e ? e : 0.f));
+        } else if (KIND == LOSS_NLL) {                        // losses.py:105-114: inputs are log-probabilities
+            v = tv * pv;
+            d = expf(pv) - tv;
+        } else if (KIND == LOSS_HINGE) {                      // losses.py:121-133
+            v = fmaxf(0.f, 1.0f - tv * pv);
+            d = (tv * pv > 1.0f) ? 0.f * (-1.0f * tv) : -1.0f * tv;
         } else {
             float e = pv - tv;
             v = e * e;
@@ -83,13 +97,14 @@ __global__ void __launch_bounds__(256) loss_rows_kernel(const float* __restrict_
 }
 
 __global__ void __launch_bounds__(1024) loss_finish_kernel(const float* __restrict__ rows, const int* __restrict__ flags,
-                                                           float* __restrict__ out, int B, float scale) {
+                                                           float* __restrict__ out, int B, float scale, int root) {
     __shared__ float red[32];
     float acc = 0.f;
     for (int i = threadIdx.x; i < B; i += 1024) acc += rows[i];
     float s = block_sum<1024>(acc, red);
     if (threadIdx.x == 0) {
         float loss = s * scale;
+        if (root) loss = sqrtf(loss);                       // RMSE
         int f = *flags | (loss != loss ? 1 : 0) | (isinf(loss) ? 2 : 0);
         out[0] = loss;
         out[1] = (float)f;
@@ -107,7 +122,7 @@ static int run_loss(const char* name, const float* p, const float* t, float* del
     if (e != cudaSuccess) return set_err(DNB_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e));
     loss_rows_kernel<KIND><<<(B + 7) / 8, 256, 0, st>>>(p, t, delta, rows, flags, B, n);
     DNB_LAUNCH_CHECK(name);
-    loss_finish_kernel<<<1, 1024, 0, st>>>(rows, flags, out, B, scale);
+    loss_finish_kernel<<<1, 1024, 0, st>>>(rows, flags, out, B, scale, KIND == LOSS_RMSE ? 1 : 0);
     DNB_LAUNCH_CHECK(name);
     return DNB_OK;
 }
@@ -191,6 +206,26 @@ int dnb_loss_mse(const float* p, const float* t, float* delta, float* out, int B
     return run_loss<LOSS_MSE>("loss_mse", p, t, delta, out, B, n, loss_scale, ws, S(stream));
 }
 
+int dnb_loss_rmse(const float* p, const float* t, float* delta, float* out, int B, int n,
+                  float loss_scale, void* ws, dnb_stream_t stream) {
+    DNB_CHECK_ARG(n == 1, "loss_rmse: the reference's float(sqrt(mean(axis=0))) only accepts one output column (got %d)", n);
+    return run_loss<LOSS_RMSE>("loss_rmse", p, t, delta, out, B, n, loss_scale, ws, S(stream));
+}
+int dnb_loss_mae(const float* p, const float* t, float* delta, float* out, int B, int n,
+                 float loss_scale, void* ws, dnb_stream_t stream) {
+    DNB_CHECK_ARG(n == 1, "loss_mae: the reference's float(mean(axis=0)) only accepts one output column (got %d)", n);
+    return run_loss<LOSS_MAE>("loss_mae", p, t, delta, out, B, n, loss_scale, ws, S(stream));
+}
+int dnb_loss_nll(const float* p, const float* t, float* delta, float* out, int B, int n,
+                 float loss_scale, void* ws, dnb_stream_t stream) {
+    // loss = -mean_b sum_k t * p   (p = log-probabilities)
+    return run_loss<LOSS_NLL>("loss_nll", p, t, delta, out, B, n, -loss_scale, ws, S(stream));
+}
+int dnb_loss_hinge(const float* p, const float* t, float* delta, float* out, int B, int n,
+                   float loss_scale, void* ws, dnb_stream_t stream) {
+    DNB_CHECK_ARG(n == 1, "loss_hinge: the reference's float(mean(axis=0)) only accepts one output column (got %d)", n);
+    return run_loss<LOSS_HINGE>("loss_hinge", p, t, delta, out, B, n, loss_scale, ws, S(stream));
+}
 int dnb_metric_categorical(const float* p, const float* t, float* out, int B, int n, dnb_stream_t stream) {
     DNB_CHECK_ARG(B > 0 && n > 0 && p && t && out, "metric_categorical: bad arguments");
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float), S(stream));

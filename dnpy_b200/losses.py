@@ -3,7 +3,7 @@ produces the scalar loss, the delta tensor and the NaN/Inf flags Net.compute_los
 (net.py:342-350).  ``compute_loss`` and ``compute_delta`` keep the reference's two-call protocol:
 the first call on a (y_pred, y_target) pair runs the kernel, the second reuses its result.
 
-RMSE / MAE / NLL / Hinge have no config and no kernel."""
+RMSE / MAE / NLL / Hinge (no BASELINE config) run through the same kernel family."""
 import numpy as np
 
 from . import _lib
@@ -96,20 +96,32 @@ class CrossEntropy(Loss):
 
 
 class RMSE(Loss):
+    """losses.py:29-43."""
+    _kernel = "dnb_loss_rmse"
+
     def __init__(self, name="RMSE"):
         super().__init__(name=name)
 
 
 class MAE(Loss):
+    """losses.py:45-57."""
+    _kernel = "dnb_loss_mae"
+
     def __init__(self, name="MAE"):
         super().__init__(name=name)
 
 
 class NLL(Loss):
+    """losses.py:97-114 (predictions are log-probabilities, e.g. a LogSoftmax output)."""
+    _kernel = "dnb_loss_nll"
+
     def __init__(self, name="NLL"):
         super().__init__(name=name)
 
 
 class Hinge(Loss):
+    """losses.py:116-133."""
+    _kernel = "dnb_loss_hinge"
+
     def __init__(self, name="Hinge"):
         super().__init__(name=name)

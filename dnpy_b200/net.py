@@ -630,7 +630,7 @@ class Net:
     # of them: evaluate in chunks of up to EVAL_CHUNK samples.  Anything else (RMSE: a square root of a
     # mean) keeps the literal per-batch loop.  DNPY_B200_EVAL_LITERAL=1 forces the literal loop.
     EVAL_CHUNK = 4096
-    _ADDITIVE = ("MSE", "MAE", "BinaryCrossEntropy", "CrossEntropy", "BinaryAccuracy", "CategoricalAccuracy")
+    _ADDITIVE = ("MSE", "MAE", "NLL", "Hinge", "BinaryCrossEntropy", "CrossEntropy", "BinaryAccuracy", "CategoricalAccuracy")
 
     def _can_evaluate_in_chunks(self, batch_size):
         import os

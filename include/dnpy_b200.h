@@ -196,7 +196,17 @@ int dnb_loss_ce(const float* p, const float* t, float* delta, float* out, int B,
 int dnb_loss_bce(const float* p, const float* t, float* delta, float* out, int B, int n,
                  float loss_scale, void* ws, dnb_stream_t stream);                        /* :65-73 */
 int dnb_loss_mse(const float* p, const float* t, float* delta, float* out, int B, int n,
-                 float loss_scale, void* ws, dnb_stream_t stream);                        /* :22-26 */
+                 float loss_scale, void* ws, dnb_stream_t stream);
+/* RMSE / MAE / NLL / Hinge (losses.py:29-57, 97-133), same protocol: out[0] = loss, out[1] = NaN/Inf flags, delta filled.
+ * RMSE, MAE and Hinge accept one output column (the reference takes float() of a per-column mean). */
+int dnb_loss_rmse(const float* p, const float* t, float* delta, float* out, int B, int n,
+                  float loss_scale, void* ws, dnb_stream_t stream);
+int dnb_loss_mae(const float* p, const float* t, float* delta, float* out, int B, int n,
+                 float loss_scale, void* ws, dnb_stream_t stream);
+int dnb_loss_nll(const float* p, const float* t, float* delta, float* out, int B, int n,
+                 float loss_scale, void* ws, dnb_stream_t stream);
+int dnb_loss_hinge(const float* p, const float* t, float* delta, float* out, int B, int n,
+                   float loss_scale, void* ws, dnb_stream_t stream);                        /* :22-26 */
 /* metrics.py:44-80: out[0] = number of correct rows (host divides) */
 int dnb_metric_categorical(const float* p, const float* t, float* out, int B, int n, dnb_stream_t stream);
 int dnb_metric_binary(const float* p, const float* t, float* out, int B, int n, float thr, dnb_stream_t stream);

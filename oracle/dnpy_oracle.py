@@ -507,6 +507,46 @@ def mse_delta(p, t):
     return 2 * (p - t)
 
 
+def rmse_loss(p, t):
+    """losses.py:34-37."""
+    return float(np.sqrt(np.mean((p - t) ** 2, axis=0, keepdims=True)).item())
+
+
+def rmse_delta(p, t):
+    """losses.py:39-42."""
+    return (p - t) / np.sqrt((p - t) ** 2 + EPS)
+
+
+def mae_loss(p, t):
+    """losses.py:50-53."""
+    return float(np.mean(np.abs(p - t), axis=0, keepdims=True).item())
+
+
+def mae_delta(p, t):
+    return np.sign(p - t)
+
+
+def nll_loss(p, t):
+    """losses.py:105-110 (p holds log-probabilities)."""
+    v = np.sum(t.astype(float) * p, axis=1, keepdims=True)
+    return -1.0 * float(np.mean(v, axis=0, keepdims=True).item())
+
+
+def nll_delta(p, t):
+    return np.exp(p) - t
+
+
+def hinge_loss(p, t):
+    """losses.py:121-127."""
+    return float(np.mean(np.maximum(0, (1 - t * p)), axis=0, keepdims=True).item())
+
+
+def hinge_delta(p, t):
+    """losses.py:129-133."""
+    gate = np.invert((t * p) > 1).astype(float)
+    return gate * (-1.0 * t)
+
+
 def bce_loss(p, t):
     """losses.py:65-68 (single output column)."""
     v = t * np.log(p + EPS) + (1.0 - t) * np.log(1.0 - p + EPS)

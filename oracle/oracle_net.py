@@ -237,6 +237,8 @@ class OracleNet:
                 losses.append(O.bce_loss(p, t)); deltas.append(O.bce_delta(p, t))
             elif kind == "MSE":
                 losses.append(O.mse_loss(p, t)); deltas.append(O.mse_delta(p, t))
+            elif kind in ("RMSE", "MAE", "NLL", "Hinge"):
+                losses.append(getattr(O, kind.lower() + "_loss")(p, t)); deltas.append(getattr(O, kind.lower() + "_delta")(p, t))
             else:
                 raise NotImplementedError(kind)
         return losses, deltas

@@ -76,6 +76,10 @@ LOSS_CASES = [
     dict(name="ce_softmax", kind="CrossEntropy", shape=(6, 4), softmax_output=True),
     dict(name="bce", kind="BinaryCrossEntropy", shape=(7, 1)),
     dict(name="mse", kind="MSE", shape=(5, 1)),
+    dict(name="rmse", kind="RMSE", shape=(6, 1)),
+    dict(name="mae", kind="MAE", shape=(6, 1)),
+    dict(name="nll", kind="NLL", shape=(5, 4)),
+    dict(name="hinge", kind="Hinge", shape=(9, 1)),
 ]
 
 OPT_CASES = [

@@ -107,6 +107,13 @@ def run_loss_case(ns, case):
     elif case["kind"] == "BinaryCrossEntropy":
         p = rs.rand(n, c) * 0.98 + 0.01
         t = rs.randint(0, 2, (n, c)).astype(float)
+    elif case["kind"] == "NLL":                  # log-probabilities against one-hot targets
+        z = rs.randn(n, c)
+        p = z - np.log(np.exp(z).sum(axis=1, keepdims=True))
+        t = np.eye(c)[rs.randint(0, c, n)]
+    elif case["kind"] == "Hinge":                # +-1 targets, scores on both sides of the margin
+        p = rs.randn(n, c) * 1.5
+        t = rs.randint(0, 2, (n, c)).astype(float) * 2.0 - 1.0
     else:
         p = rs.randn(n, c)
         t = rs.randn(n, c)

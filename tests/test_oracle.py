@@ -110,6 +110,9 @@ def test_loss_cases(case, golden):
         loss, delta = O.ce_loss(p, t), O.ce_delta(p, t, case.get("softmax_output", False))
     elif case["kind"] == "BinaryCrossEntropy":
         loss, delta = O.bce_loss(p, t), O.bce_delta(p, t)
+    elif case["kind"] in ("RMSE", "MAE", "NLL", "Hinge"):
+        k = case["kind"].lower()
+        loss, delta = getattr(O, k + "_loss")(p, t), getattr(O, k + "_delta")(p, t)
     else:
         loss, delta = O.mse_loss(p, t), O.mse_delta(p, t)
     assert abs(loss - float(g[f"{case['name']}/loss"])) <= 1e-12
