@@ -81,3 +81,19 @@ class Average(MLayer):
             dx = self._buf(f'dx{i}', d.shape)
             self._call("dnb_scale", d.ptr(), dx.ptr(), d.size, 1.0 / float(n))
             p.delta = dx
+
+
+class Concatenate(MLayer):
+    """merge.py:81-100, marked "Not tested" in the reference — and it is not usable there: the layer keeps the FIRST
+    parent's ``oshape`` although its output is wider, and ``backward`` raises ``TypeError`` (``np.take`` with a slice;
+    probed against the reference in this container).  Kept for API presence; scoped out with the reference's own failure."""
+
+    def __init__(self, l_in, axis=0, name="Concatenate"):
+        super().__init__(l_in, name=name)
+        self.axis = axis + 1
+
+    def forward(self):
+        raise NotImplementedError("Concatenate: the reference's own backward raises TypeError (merge.py:95-100); out of scope")
+
+    def backward(self):
+        raise TypeError("int() argument must be a string, a bytes-like object or a real number, not 'slice'")
