@@ -8,6 +8,7 @@
 // channel-transposed filter), the weight-gradient is a shared-memory micro-GEMM over gathered
 // pixel stages.  The TF32 tensor-core implicit-GEMM path is in tc_conv.cu.
 #include "common.cuh"
+#include <cstdlib>
 #include "tc_conv.cuh"
 #include "tc_common.cuh"
 #include <algorithm>
@@ -626,13 +627,21 @@ int dnb_conv2d_bwd(const float* x, const float* w, const float* b, const float* 
     const bool thin = thin_conv_supported(g);
     // measured on B200 (conv 1->32, 28x28, B=8192): the register-tiled fp32 wgrad (0.35 ms) edges out the tensor-core
     // thin-K variant (0.40 ms) — both are dY-stream bound — so thin layers keep the fp32 kernel in either math mode
-    const bool tc_wgrad = !thin && math >= DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_WGRAD);
+    // (C >= 3 on large planes is the exception: the thin-K tensor-core variant wins there — measured on the 3 x 64 x 64 stem
+    //  of the residual net, DNB_THIN_TC_WGRAD=0 restores the fp32 kernel)
+    const bool thin_tc = thin && g->C >= 3 && (long)g->OH * g->OW >= 1024 && !(getenv("DNB_THIN_TC_WGRAD") && atoi(getenv("DNB_THIN_TC_WGRAD")) == 0);
+    const bool tc_wgrad = (!thin || thin_tc) && math >= DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_WGRAD);
     // ... except the single-channel case, where dY can feed the tensor core straight from TMA (tc_conv_thin.cu)
     const bool tc_thin = thin && math >= DNB_MATH_TF32 && tc_thin_wgrad_supported(g) &&
                          !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15);
+    const bool thin_tc_dgrad = thin_tc && dx && math >= DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_DGRAD);
     if (thin) {
-        rc = thin_conv_bwd(x, w, dy, dx, gw, gb, g, inv_m, /*skip_wgrad=*/tc_wgrad || tc_thin, st);
+        rc = thin_conv_bwd(x, w, dy, thin_tc_dgrad ? nullptr : dx, gw, gb, g, inv_m, /*skip_wgrad=*/tc_wgrad || tc_thin, st);
         if (rc) return rc;
+        if (thin_tc_dgrad) {
+            rc = tc_conv_dgrad(dy, w, dx, g, ws, math == DNB_MATH_BF16, st);
+            if (rc) return rc;
+        }
         if (tc_thin) {
             rc = tc_thin_wgrad(x, dy, gw, gb, g, inv_m, st);
             if (rc) return rc;
