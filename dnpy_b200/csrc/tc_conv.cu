@@ -577,7 +577,23 @@ static size_t ws_dgrad_floats(const dnb_win_t* g) { return (size_t)round_up(g->C
 // ("dilated") buffer dYu[s*oy][s*ox] = dY[oy][ox] and dX = corr(dYu, flip(W)) is the data gradient of a fictitious stride-1
 // convolution with the same top/left pads.  One extra streaming pass (read dY, write s^2 x as much) instead of the gather
 // kernel's predicated taps (3/4 of the MMA work of a stride-2 layer multiplies zeros there: 0.07 of HBM peak on B200).
-static bool dgrad_dilate_geom(const dnb_win_t* g, dnb_win_t* g1) {
+// stride-2 specialisation (OW1 == 2*OW, OW % 4 == 0): one LDG.128 of dY feeds two STG.128 of the dilated row; odd rows are zero
+__global__ void __launch_bounds__(256) dilate2_dy_kernel(const float* __restrict__ dy, float* __restrict__ du, long planes,
+                                                         int OH, int OW, int OH1, int sy) {
+    const int q = OW >> 2;                                   // input quads per row
+    const long total = planes * OH1 * q;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int xq = (int)(i % q); long t = i / q;
+        const int y = (int)(t % OH1); const long pl = t / OH1;
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y % sy == 0 && y / sy < OH) d = __ldg(reinterpret_cast<const float4*>(dy + (pl * OH + y / sy) * OW) + xq);
+        float4* o = reinterpret_cast<float4*>(du + (pl * OH1 + y) * (long)(2 * OW)) + 2 * xq;
+        o[0] = make_float4(d.x, 0.f, d.y, 0.f);
+        o[1] = make_float4(d.z, 0.f, d.w, 0.f);
+    }
+}
+
+static bool dgrad_dilate_geom(const dnb_win_t* g, dnb_win_t* g1, bool bf16) {
     if ((g->sy == 1 && g->sx == 1) || getenv("DNB_NO_DILATE")) return false;
     *g1 = *g;
     g1->sy = 1; g1->sx = 1;
@@ -586,14 +602,14 @@ static bool dgrad_dilate_geom(const dnb_win_t* g, dnb_win_t* g1) {
     g1->pb = g1->OH - 1 + g->kh - g->H - g->pt;
     g1->pr = g1->OW - 1 + g->kw - g->W - g->pl;
     if (g1->pb < 0 || g1->pr < 0) return false;
-    return tc_conv_sv_supported(g1, true);
+    return tc_conv_sv_supported(g1, true) || (bf16 && tc_conv_sv_bf16_supported(g1, true));
 }
 static size_t ws_weights_bytes(const dnb_win_t* g) { return ((ws_fwd_floats(g) + ws_dgrad_floats(g)) * sizeof(float) + 256 + 255) & ~(size_t)255; }
 
 size_t tc_conv_ws_bytes(const dnb_win_t* g) {
     dnb_win_t g1;
     size_t n = ws_weights_bytes(g);
-    if (dgrad_dilate_geom(g, &g1)) n += (size_t)g->B * g->F * g1.OH * g1.OW * sizeof(float);
+    if (dgrad_dilate_geom(g, &g1, true)) n += (size_t)g->B * g->F * g1.OH * g1.OW * sizeof(float);
     return n;
 }
 
@@ -649,11 +665,14 @@ int tc_conv_dgrad(const float* dy, const float* w, float* dx, const dnb_win_t* g
     const int cp = round_up(g->F, 4), Kp = round_up(cp * g->kh * g->kw, CBK), n_pad = round_up(g->C, 128);
     float* wp = static_cast<float*>(ws) + ws_fwd_floats(g);
     dnb_win_t g1;
-    if (!getenv("DNB_NO_SV") && dgrad_dilate_geom(g, &g1)) {
+    if (!getenv("DNB_NO_SV") && dgrad_dilate_geom(g, &g1, bf16)) {
         float* du = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + ws_weights_bytes(g));
         const long planes = (long)g->B * g->F;
         const long quads = planes * g1.OH * (g1.OW >> 2);
-        dilate_dy_kernel<<<(unsigned)std::min<long>((quads + 255) / 256, 148L * 16), 256, 0, st>>>(dy, du, planes, g->OH, g->OW, g1.OH, g1.OW, g->sy, g->sx);
+        if (g->sx == 2 && g1.OW == 2 * g->OW && g->OW % 4 == 0 && !(reinterpret_cast<uintptr_t>(dy) & 15))
+            dilate2_dy_kernel<<<(unsigned)std::min<long>((quads / 2 + 255) / 256, 148L * 16), 256, 0, st>>>(dy, du, planes, g->OH, g->OW, g1.OH, g->sy);
+        else
+            dilate_dy_kernel<<<(unsigned)std::min<long>((quads + 255) / 256, 148L * 16), 256, 0, st>>>(dy, du, planes, g->OH, g->OW, g1.OH, g1.OW, g->sy, g->sx);
         DNB_LAUNCH_CHECK("conv2d_dilate_dy");
         const bool bf1 = bf16 && tc_conv_sv_bf16_supported(&g1, true);
         prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, cp, 1, bf1);

@@ -510,7 +510,7 @@ static bool sv_plan(SvParams& p, int bn) {
         SvParams q = p;
         shape(q, th);
         if (q.PH > 256 || p.Ws > 256) continue;                                            // TMA box limits
-        if ((long)(q.bulk ? p.Hs : q.PH) * p.Ws * 8 * (p.Cs / 32) > (long)SV_TB * SV_TR * 32) continue;      // transposer task table
+        if ((long)(q.bulk ? p.Hs : q.PH) * p.Ws * (p.bf ? 4 : 8) * (p.Cs / 32) > (long)SV_TB * SV_TR * 32) continue;      // transposer task table
         if (sv_smem_bytes(q, bn) > budget) continue;
         const long cost = (long)q.nbands * (2 * q.tiles - q.last64);                       // in units of 64 MMA rows
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_th = th; }
@@ -578,16 +578,24 @@ static SvParams sv_make(const dnb_win_t* g, bool dgrad) {
     return p;
 }
 
+static bool sv_geom_ok(const dnb_win_t* g, bool dgrad, SvParams& p);
+
+// BF16 staging halves the transposer task count and the staged bytes: some geometries (wide, 64-channel bands) fit ONLY this way
 bool tc_conv_sv_bf16_supported(const dnb_win_t* g, bool dgrad) {
-    if (getenv("DNB_SV_NOBF16") || !tc_conv_sv_supported(g, dgrad)) return false;
-    SvParams p = sv_make(g, dgrad);
+    SvParams p;
+    if (getenv("DNB_SV_NOBF16") || !sv_geom_ok(g, dgrad, p)) return false;
     p.bf = 1;
     return p.kh == 3 && p.kw == 3 && (p.Cs == 32 || p.Cs == 64) && sv_plan(p, pick_bn_sv(p.Cd));
 }
 
 bool tc_conv_sv_supported(const dnb_win_t* g, bool dgrad) {
+    SvParams p;
+    return sv_geom_ok(g, dgrad, p) && sv_plan(p, pick_bn_sv(p.Cd));
+}
+
+static bool sv_geom_ok(const dnb_win_t* g, bool dgrad, SvParams& p) {
     if (g->sy != 1 || g->sx != 1) return false;
-    SvParams p = sv_make(g, dgrad);
+    p = sv_make(g, dgrad);
     if (p.Cs % 32 || p.Cd > 128 || p.off_y < 0 || p.off_x < 0) return false;
     if (p.Ws % 4) return false;                                   // TMA box rows must be a multiple of 16 bytes
     // the produced extent must equal (gathered + pads - k + 1): true for forward by construction; for dgrad it
@@ -595,7 +603,7 @@ bool tc_conv_sv_supported(const dnb_win_t* g, bool dgrad) {
     if (dgrad && ((g->OH - 1) + g->kh != g->H + g->pt + g->pb || (g->OW - 1) + g->kw != g->W + g->pl + g->pr)) return false;
     // every source column must land inside the padded row (the ring is zeroed once and never rewritten)
     if (p.off_x + p.Ws > p.Wd + p.kw - 1) return false;
-    return sv_plan(p, pick_bn_sv(p.Cd));
+    return true;
 }
 
 int tc_conv_sv_run(const char* name, const float* src, const void* wprep, int n_pad, int Kp, const float* bias, float bias_k,
