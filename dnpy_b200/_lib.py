@@ -47,6 +47,8 @@ SIGNATURES = {
     "dnb_maxpool2d_fwd": (_i, [_p, _p, _p, _W, _p]),
     "dnb_maxpool2d_bwd_ws_bytes": (_z, [_W, _i]),
     "dnb_maxpool2d_bwd": (_i, [_p, _p, _p, _W, _i, _p, _p]),
+    "dnb_maxpool2d_bwd_prepare": (_i, [_p, _W, _p, _p]),
+    "dnb_maxpool2d_bwd_apply": (_i, [_p, _p, _W, _p, _p]),
     "dnb_avgpool2d_fwd": (_i, [_p, _p, _W, _p]),
     "dnb_avgpool2d_bwd": (_i, [_p, _p, _W, _p]),
     "dnb_leakyrelu_fwd": (_i, [_p, _p, _z, _f, _p]),

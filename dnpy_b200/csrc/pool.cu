@@ -564,6 +564,7 @@ size_t dnb_maxpool2d_bwd_ws_bytes(const dnb_win_t* g, int route) {
 
 int dnb_maxpool2d_bwd(const float* dy, const int32_t* idx, float* dx, const dnb_win_t* g,
                       int route, void* ws, dnb_stream_t stream) {
+    DNB_CHECK_ARG(route == DNB_ROUTE_PER_SAMPLE || (g && g->B == 1) || ws, "maxpool2d_bwd: the literal route needs a workspace");
     int rc = check_pool("maxpool2d_bwd", g);
     if (rc) return rc;
     long n = (long)g->B * g->C * g->H * g->W;
@@ -592,7 +593,21 @@ int dnb_maxpool2d_bwd(const float* dy, const int32_t* idx, float* dx, const dnb_
         return DNB_OK;
     }
     DNB_CHECK_ARG(route == DNB_ROUTE_LITERAL, "maxpool2d_bwd: unknown route %d", route);
-    DNB_CHECK_ARG(ws, "maxpool2d_bwd: the literal route needs a workspace");
+    rc = dnb_maxpool2d_bwd_prepare(idx, g, ws, stream);
+    if (rc) return rc;
+    return dnb_maxpool2d_bwd_apply(dy, dx, g, ws, stream);
+}
+
+// The LITERAL route in two halves, so a host can run the first (it depends on the forward's argmax offsets only) on a side
+// stream as soon as the forward has finished — latency-bound kernels hidden behind the rest of the step:
+//   prepare: ws <- last[c,oy,ox,p] = the newest sample whose window (c,oy,ox) has its maximum at offset p
+//   apply  : dx[0] <- gather of dY through `last`, dx[1..B-1] <- 0
+int dnb_maxpool2d_bwd_prepare(const int32_t* idx, const dnb_win_t* g, void* ws, dnb_stream_t stream) {
+    int rc = check_pool("maxpool2d_bwd", g);
+    if (rc) return rc;
+    if ((long)g->B * g->C * g->H * g->W == 0) return DNB_OK;
+    DNB_CHECK_ARG(idx && ws, "maxpool2d_bwd: the literal route needs the argmax offsets and a workspace");
+    cudaStream_t st = S(stream);
     const long npos = (long)g->C * g->OH * g->OW;
     const int P = g->kh * g->kw;
     int32_t* last = static_cast<int32_t*>(ws);
@@ -608,9 +623,20 @@ int dnb_maxpool2d_bwd(const float* dy, const int32_t* idx, float* dx, const dnb_
         maxpool_last_kernel<<<grid, 256, 0, st>>>(idx, last, done, *g, bchunk, g->B - top);
         DNB_LAUNCH_CHECK("maxpool2d_bwd_last");
     }
+    return DNB_OK;
+}
+
+int dnb_maxpool2d_bwd_apply(const float* dy, float* dx, const dnb_win_t* g, const void* ws, dnb_stream_t stream) {
+    int rc = check_pool("maxpool2d_bwd", g);
+    if (rc) return rc;
+    const long n = (long)g->B * g->C * g->H * g->W;
+    if (n == 0) return DNB_OK;
+    DNB_CHECK_ARG(dy && dx && ws, "maxpool2d_bwd: null pointer");
+    cudaStream_t st = S(stream);
+    const int32_t* last = static_cast<const int32_t*>(ws);
     const long n0 = (long)g->C * g->H * g->W;
     if (g->B > 1) {
-        e = cudaMemsetAsync(dx + n0, 0, (size_t)(n - n0) * sizeof(float), st);               // samples 1..B-1 get no delta
+        cudaError_t e = cudaMemsetAsync(dx + n0, 0, (size_t)(n - n0) * sizeof(float), st);   // samples 1..B-1 get no delta
         if (e != cudaSuccess) return set_err(DNB_ERR_CUDA, "maxpool2d_bwd: %s", cudaGetErrorString(e));
     }
     maxpool_bwd_literal_kernel<<<ew_grid(n0, 256), 256, 0, st>>>(dy, last, dx, *g);
