@@ -22,7 +22,7 @@ namespace dnb {
 constexpr int HD_MAXOUT = 16;
 constexpr int HF_CH = 512;                        // forward: features per W chunk
 constexpr int HX_ROWS = 32;                       // dX: rows per thread
-constexpr int HW_ROWS = 256;                      // dW: rows per CTA
+constexpr int HW_ROWS = 512;                      // dW: rows per CTA
 
 __device__ __forceinline__ void hd_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
