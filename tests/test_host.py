@@ -150,3 +150,34 @@ def test_two_rank_gloo_gradient_exchange(tmp_path):
                        capture_output=True, text=True, env=env, timeout=170)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_evaluate_chunking_policy_and_resident_slices(ns, monkeypatch):
+    """Host logic of SURVEY 8f-1/2 that needs no device: which (loss, metric) sets may be evaluated in chunks, the
+    resident-slice view protocol, and that without a device the datasets are left on the host."""
+    import torch
+    from dnpy_b200.net import _ResidentSlice
+    from tests import topologies
+    np.random.seed(0)
+    net = topologies.mnist_mlp(ns, h1=8, h2=4)
+    net.set_mode("test")
+    assert net._can_evaluate_in_chunks(1) and net._can_evaluate_in_chunks(128)
+    assert not net._can_evaluate_in_chunks(net.EVAL_CHUNK)          # nothing to gain: already one forward per chunk
+    monkeypatch.setenv("DNPY_B200_EVAL_LITERAL", "1")
+    assert not net._can_evaluate_in_chunks(1)
+    monkeypatch.delenv("DNPY_B200_EVAL_LITERAL")
+    net.metrics = [[ns.metrics.RMSE()]]                             # sqrt(mean): not a mean over samples
+    assert not net._can_evaluate_in_chunks(1)
+    net.metrics = [[ns.metrics.CategoricalAccuracy(), ns.metrics.MAE()]]
+    assert net._can_evaluate_in_chunks(1)
+    net.set_mode("train")
+    assert not net._can_evaluate_in_chunks(1)
+
+    s = _ResidentSlice(torch.arange(24, dtype=torch.float32).reshape(6, 4))
+    assert len(s) == 6 and s.shape == (6, 4)
+    sub = s[2:5]
+    assert isinstance(sub, _ResidentSlice) and sub.shape == (3, 4) and float(sub.t[0, 0]) == 8.0
+    if not torch.cuda.is_available():
+        x, y = [np.zeros((4, 784))], [np.zeros((4, 10))]
+        rx, ry = net._make_resident(x, y)
+        assert rx is x and ry is y
