@@ -45,6 +45,7 @@ SIGNATURES = {
     "dnb_dwconv2d_fwd": (_i, [_p, _p, _p, _p, _W, _p]),
     "dnb_dwconv2d_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _W, _f, _R, _f, _p]),
     "dnb_maxpool2d_fwd": (_i, [_p, _p, _p, _W, _p]),
+    "dnb_maxpool2d_fwd_act": (_i, [_p, _p, _p, _p, _f, _W, _p]),
     "dnb_maxpool2d_bwd_ws_bytes": (_z, [_W, _i]),
     "dnb_maxpool2d_bwd": (_i, [_p, _p, _p, _W, _i, _p, _p]),
     "dnb_maxpool2d_bwd_prepare": (_i, [_p, _W, _p, _p]),

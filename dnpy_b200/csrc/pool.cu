@@ -101,7 +101,8 @@ __device__ __forceinline__ void mp_bulk_s2g(void* dst, const void* src, uint32_t
 template <int K, int S, bool VEC2>
 __global__ void __launch_bounds__(MPR_THREADS, 2) maxpool_fwd_ring_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                            int32_t* __restrict__ idx, int nchunks, int G,
-                                                                           int H, int W, int OH, int OW) {
+                                                                           int H, int W, int OH, int OW,
+                                                                           float* __restrict__ yact, float alpha) {
     extern __shared__ __align__(128) uint8_t smraw[];
     const int plane = H * W, oplane = OH * OW;
     const int n_in = G * plane, n_out = G * oplane;
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(MPR_THREADS, 2) maxpool_fwd_ring_kernel(const 
     float* sin = reinterpret_cast<float*>(smraw + 128);                 // [ST][n_in]
     float* sy = sin + (size_t)MPR_ST * n_in;                            // [2][n_out]
     int32_t* si = reinterpret_cast<int32_t*>(sy + 2 * n_out);           // [2][n_out]
+    float* sa = reinterpret_cast<float*>(si + 2 * n_out);               // [2][n_out]  LeakyRelu(y) of a fused consumer (yact != nullptr)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < MPR_ST; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], MPR_CONS / 32); }
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(MPR_THREADS, 2) maxpool_fwd_ring_kernel(const 
                 }
                 oy_[e] = best;
                 oi_[e] = bi;
+                if (yact) sa[ob * n_out + e] = best > 0.f ? best : alpha * best;       // activations.py:17-19
             }
         }
         __syncwarp();
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(MPR_THREADS, 2) maxpool_fwd_ring_kernel(const 
             const long c = (long)blockIdx.x + (long)n * gridDim.x;
             mp_bulk_s2g(y + c * n_out, oy_, (uint32_t)n_out * 4u);
             mp_bulk_s2g(idx + c * n_out, oi_, (uint32_t)n_out * 4u);
+            if (yact) mp_bulk_s2g(yact + c * n_out, sa + ob * n_out, (uint32_t)n_out * 4u);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
@@ -195,31 +199,33 @@ __global__ void __launch_bounds__(MPR_THREADS, 2) maxpool_fwd_ring_kernel(const 
 }
 
 // planes per chunk for the ring kernel (0: shape not eligible)
-static int mpr_chunk_planes(long planes, int H, int W, int OH, int OW) {
+static int mpr_chunk_planes(long planes, int H, int W, int OH, int OW, long stage_budget = 24 * 1024) {
     const long plane = (long)H * W, oplane = (long)OH * OW;
     if (plane % 4) return 0;
-    const long gmax = std::min<long>({planes, (24 * 1024) / (plane * 4), (long)(MPR_MAXR * MPR_CONS) / oplane});
+    const long gmax = std::min<long>({planes, stage_budget / (plane * 4), (long)(MPR_MAXR * MPR_CONS) / oplane});
     for (long G = gmax; G >= 1; --G)
         if (planes % G == 0 && (G * oplane) % 4 == 0) return (int)G;
     return 0;
 }
 template <int K, int S>
-static bool maxpool_fwd_ring(const float* x, float* y, int32_t* idx, const dnb_win_t* g, cudaStream_t st) {
+static bool maxpool_fwd_ring(const float* x, float* y, int32_t* idx, const dnb_win_t* g, cudaStream_t st,
+                             float* yact = nullptr, float alpha = 0.f) {
     const long planes = (long)g->B * g->C;
-    const int G = mpr_chunk_planes(planes, g->H, g->W, g->OH, g->OW);
+    // the fused variant stages a third output: smaller chunks keep two CTAs per SM
+    const int G = mpr_chunk_planes(planes, g->H, g->W, g->OH, g->OW, yact ? 20 * 1024 : 24 * 1024);
     if (!G || getenv("DNB_NO_POOL_RING")) return false;
     const long nchunks = planes / G;
     if (nchunks > 0x7fffffffL) return false;
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(idx)) & 15) return false;
-    const size_t smem = 128 + ((size_t)MPR_ST * G * g->H * g->W + 4ull * G * g->OH * g->OW) * 4;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(yact)) & 15) return false;
+    const size_t smem = 128 + ((size_t)MPR_ST * G * g->H * g->W + (yact ? 6ull : 4ull) * G * g->OH * g->OW) * 4;
     const int grid = (int)std::min<long>(nchunks, 2L * kNumSMs);
     const bool v2 = (S == 2) && (g->W % 2 == 0);
     if (v2) {
         cudaFuncSetAttribute(maxpool_fwd_ring_kernel<K, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        maxpool_fwd_ring_kernel<K, S, true><<<grid, MPR_THREADS, smem, st>>>(x, y, idx, (int)nchunks, G, g->H, g->W, g->OH, g->OW);
+        maxpool_fwd_ring_kernel<K, S, true><<<grid, MPR_THREADS, smem, st>>>(x, y, idx, (int)nchunks, G, g->H, g->W, g->OH, g->OW, yact, alpha);
     } else {
         cudaFuncSetAttribute(maxpool_fwd_ring_kernel<K, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        maxpool_fwd_ring_kernel<K, S, false><<<grid, MPR_THREADS, smem, st>>>(x, y, idx, (int)nchunks, G, g->H, g->W, g->OH, g->OW);
+        maxpool_fwd_ring_kernel<K, S, false><<<grid, MPR_THREADS, smem, st>>>(x, y, idx, (int)nchunks, G, g->H, g->W, g->OH, g->OW, yact, alpha);
     }
     return true;
 }
@@ -560,6 +566,28 @@ int dnb_maxpool2d_fwd(const float* x, float* y, int32_t* idx, const dnb_win_t* g
 size_t dnb_maxpool2d_bwd_ws_bytes(const dnb_win_t* g, int route) {
     if (!g || route != DNB_ROUTE_LITERAL) return 0;
     return (size_t)g->C * g->OH * g->OW * (g->kh * g->kw + 1) * sizeof(int32_t);      // last[npos][P] + done[npos]
+}
+
+// MaxPool2D.forward fused with a LeakyRelu / Relu consumer (activations.py:17-19): the pooled values, the argmax offsets AND
+// the consumer's output leave the ring kernel together — the activation's own pass over the pooled tensor (one read + one
+// write) disappears.  Only for the shapes the ring kernel takes; DNB_ERR_UNSUPPORTED otherwise (the host then runs the two
+// layers separately).
+int dnb_maxpool2d_fwd_act(const float* x, float* y, int32_t* idx, float* yact, float alpha, const dnb_win_t* g, dnb_stream_t stream) {
+    int rc = check_pool("maxpool2d_fwd_act", g);
+    if (rc) return rc;
+    if ((long)g->B * g->C * g->OH * g->OW == 0) return DNB_OK;
+    DNB_CHECK_ARG(x && y && idx && yact, "maxpool2d_fwd_act: null pointer");
+    bool done = false;
+    if (!(g->pt | g->pb | g->pl | g->pr) && g->kh == g->kw && g->sy == g->sx &&
+        (g->OH - 1) * g->sy + g->kh <= g->H && (g->OW - 1) * g->sx + g->kw <= g->W) {
+        if (g->kh == 3 && g->sy == 2) done = maxpool_fwd_ring<3, 2>(x, y, idx, g, S(stream), yact, alpha);
+        else if (g->kh == 2 && g->sy == 2) done = maxpool_fwd_ring<2, 2>(x, y, idx, g, S(stream), yact, alpha);
+        else if (g->kh == 3 && g->sy == 1) done = maxpool_fwd_ring<3, 1>(x, y, idx, g, S(stream), yact, alpha);
+        else if (g->kh == 2 && g->sy == 1) done = maxpool_fwd_ring<2, 1>(x, y, idx, g, S(stream), yact, alpha);
+    }
+    if (!done) return set_err(DNB_ERR_UNSUPPORTED, "maxpool2d_fwd_act: shape not taken by the ring kernel");
+    DNB_LAUNCH_CHECK("maxpool2d_fwd");
+    return DNB_OK;
 }
 
 int dnb_maxpool2d_bwd(const float* dy, const int32_t* idx, float* dx, const dnb_win_t* g,

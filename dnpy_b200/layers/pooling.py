@@ -51,7 +51,19 @@ class MaxPool2D(Pool):
         b = x.shape[0]
         out = self._buf('out', (b, *self.oshape))
         idx = self._buf('idx', (b, *self.oshape), is_int=True)
-        self._call("dnb_maxpool2d_fwd", x.ptr(), out.ptr(), idx.ptr(), self._win(b))
+        act = getattr(self, "_fused_act", None)          # set by Net.build: a LeakyRelu/Relu that is this layer's only consumer
+        fused = False
+        if act is not None and not getattr(self, "_fused_unsupported", False):
+            aout = act._buf('out', (b, *self.oshape))
+            try:
+                self._call("dnb_maxpool2d_fwd_act", x.ptr(), out.ptr(), idx.ptr(), aout.ptr(), float(act.alpha), self._win(b))
+                aout.written()
+                act._precomputed = (out, aout)           # valid for exactly this output object
+                fused = True
+            except NotImplementedError:
+                self._fused_unsupported = True          # shape outside the ring kernel: run the two layers separately
+        if not fused:
+            self._call("dnb_maxpool2d_fwd", x.ptr(), out.ptr(), idx.ptr(), self._win(b))
         self.output = out
         self.output_idxs = idx
 

@@ -122,6 +122,25 @@ class Net:
         self.initialize()
         self._arena = None
         self._graphs = {}
+        self._plan_fusions()
+
+    def _plan_fusions(self):
+        """MaxPool2D -> LeakyRelu/Relu where the activation is the pool's ONLY consumer: the pool's forward kernel also
+        writes the activation's output (dnb_maxpool2d_fwd_act); every layer still exposes its own output/delta buffers.
+        OPT-IN (DNPY_B200_FUSION=1): correct (the GPU suite passes with it), but measured slower on B200 — the third output
+        forces smaller ring chunks, the pool forward goes 171 -> 250 us to save the activation's 49 us (1.375 -> 1.404 ms/step)."""
+        import os
+        from .layers import MaxPool2D, LeakyRelu
+        consumers = {}
+        for l in self.fts_layers:
+            for p in l.parents:
+                consumers.setdefault(id(p), []).append(l)
+        for l in self.fts_layers:
+            l._fused_act = None
+            cons = consumers.get(id(l), [])
+            if (isinstance(l, MaxPool2D) and len(cons) == 1 and type(cons[0]).__name__ in ("LeakyRelu", "Relu")
+                    and isinstance(cons[0], LeakyRelu) and l not in self.l_out and os.environ.get("DNPY_B200_FUSION")):
+                l._fused_act = cons[0]
 
     def fts(self):
         self.fts_layers = list(self.bts_layers)

@@ -116,6 +116,9 @@ int dnb_dwconv2d_bwd(const float* x, const float* w, const float* b, const float
 /* ---- MaxPool2D / AvgPool2D (layers/pooling.py:43-99, 118-174) --------------- */
 /* idx[B,C,OH,OW] int32: first max of the zero-padded row-major window (bit-exact vs np.argmax) */
 int dnb_maxpool2d_fwd(const float* x, float* y, int32_t* idx, const dnb_win_t* g, dnb_stream_t stream);
+/* MaxPool2D.forward + the forward of a LeakyRelu/Relu that consumes it (activations.py:17-19), one kernel:
+ * yact = y > 0 ? y : alpha*y.  Returns DNB_ERR_UNSUPPORTED for shapes outside the bulk-copy ring kernel. */
+int dnb_maxpool2d_fwd_act(const float* x, float* y, int32_t* idx, float* yact, float alpha, const dnb_win_t* g, dnb_stream_t stream);
 size_t dnb_maxpool2d_bwd_ws_bytes(const dnb_win_t* g, int route);
 int dnb_maxpool2d_bwd(const float* dy, const int32_t* idx, float* dx, const dnb_win_t* g,
                       int route, void* ws, dnb_stream_t stream);
