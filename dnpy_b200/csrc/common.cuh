@@ -9,7 +9,9 @@
 
 namespace dnb {
 
-constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+// SM count of the current device (B200: 148 = 2 dies x 74), queried once per process; grids are sized in multiples of it
+int num_sms();
+#define kNumSMs (dnb::num_sms())
 
 // thread-local error string behind dnb_last_error()
 char* err_buf();

@@ -23,6 +23,15 @@ int set_err(int code, const char* fmt, ...) {
 
 thread_local cudaStream_t g_cur_stream = nullptr;
 
+int num_sms() {
+    static int cached = 0;          // one process drives one GPU (one rank per device)
+    if (cached > 0) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+        cached = n;
+    return cached > 0 ? cached : 148;
+}
+
 // ---- launch bookkeeping ---------------------------------------------------------------------
 static long long g_launches = 0;
 struct ProfState {

@@ -128,8 +128,8 @@ class DArray:
         if tuple(a.shape) != self.shape and self._pinned:
             raise ValueError(f"shape mismatch: slot {self.shape} vs {tuple(a.shape)}")
         self._set_host(a)
-        if self._pinned:
-            self.dev()
+        if self._pinned or self._dev is not None:
+            self.dev()          # same device storage, new values (dev() copies into the existing tensor)
         return self
 
     # -- host side ------------------------------------------------------------
@@ -236,12 +236,17 @@ class ParamDict(dict):
         cur = dict.get(self, key)
         if isinstance(value, DArray):
             dict.__setitem__(self, key, value)
-        elif cur is not None and cur._pinned and tuple(np.shape(value)) == cur.shape:
+        elif cur is not None and tuple(np.shape(value)) == cur.shape:
+            # in place, pinned (arena slot) or not (BatchNorm moving stats): captured step graphs hold the buffer's
+            # address, so Net.set_params / Net.load must never swap the device storage of an existing parameter
             cur.assign(value)
         else:
             if cur is not None and cur._pinned:
                 raise ValueError(f"params['{key}']: cannot change the shape of an arena-bound parameter "
                                  f"({cur.shape} -> {tuple(np.shape(value))})")
+            if cur is not None and cur._dev is not None:
+                from .layers.base import Layer        # a device buffer is being replaced: captured graphs are stale
+                Layer.buffer_generation += 1
             dict.__setitem__(self, key, DArray(host=value))
 
     def host_copy(self):

@@ -56,7 +56,7 @@ class Embedding(Layer):
         from .. import _lib
         ws = self._raw('ws', _lib.load().dnb_embedding_bwd_ws_bytes(l, v, d))
         self._call("dnb_embedding_bwd", idx.ptr(), dy.ptr(), self.grads['w1'].ptr(), b, l, v, d,
-                   1.0 / float(b), ws)
+                   self._inv_m(b), ws)
         self.grads['w1'].written()
 
 

@@ -6,7 +6,49 @@ from .. import initializers
 from ..darray import DArray, ParamDict
 
 
-class Dropout(Layer):
+def _global_draw(draw, shape):
+    """One host draw for the GLOBAL minibatch from NumPy's global stream.  Under data parallelism every rank holds the
+    same stream state (identical seeds), draws the full (B_local * world, ...) block exactly like a single process
+    would (regularization.py:19,41) and keeps its own contiguous row block."""
+    from ..runtime import config
+    shape = tuple(int(s) for s in shape)
+    if config.world == 1:
+        return draw(shape)
+    full = draw((shape[0] * config.world,) + shape[1:])
+    return full[config.rank * shape[0]:(config.rank + 1) * shape[0]]
+
+
+class _HostDrawLayer(Layer):
+    """Layers whose training forward consumes the host RNG (Dropout, GaussianNoise): the draw is made by ``prepare``
+    into a STATIC device buffer, so a captured step graph replays with fresh values.  Net calls ``prepare`` before it
+    captures / replays a step graph; an eager forward calls it itself."""
+
+    def _draw(self, shape):
+        raise NotImplementedError
+
+    def prepare(self, shape):
+        shape = tuple(int(s) for s in shape)
+        buf = self._bufs.get('draw')
+        if buf is None or buf.shape != shape:
+            from ..darray import dev_empty
+            buf = DArray.device(dev_empty(shape))
+            self._bufs['draw'] = buf
+            Layer.buffer_generation += 1
+        import torch
+        host = np.ascontiguousarray(_global_draw(self._draw, shape), dtype=np.float32)
+        buf.dev().copy_(torch.from_numpy(host))
+        buf.written()
+        self._prepared = True
+        return buf
+
+    def _drawn(self, shape):
+        if not getattr(self, "_prepared", False):
+            self.prepare(shape)
+        self._prepared = False
+        return self._bufs['draw']
+
+
+class Dropout(_HostDrawLayer):
     """regularization.py:7-25.  Non-inverted dropout (Q12).  The mask is drawn on the host from
     NumPy's GLOBAL stream — one ``np.random.random(shape)`` per training forward, exactly the
     reference's call — so masks are bit-identical for a shared seed; only the 0/1 gate is uploaded."""
@@ -18,30 +60,14 @@ class Dropout(Layer):
         self.rate = rate
         self.gate = None
 
-    def prepare(self, shape):
-        """Draw this step's mask from the global NumPy stream (the reference's one call per training forward,
-        regularization.py:19) and upload it into the layer's STATIC gate buffer.  Net calls this before it
-        replays a captured step graph; an eager forward calls it itself."""
-        gate = self._bufs.get('gate')
-        if gate is None or gate.shape != tuple(shape):
-            from ..darray import dev_empty
-            gate = DArray.device(dev_empty(tuple(shape)))
-            self._bufs['gate'] = gate
-            Layer.buffer_generation += 1
-        import torch
-        host = (np.random.random(shape) > self.rate).astype(np.float32)
-        gate.dev().copy_(torch.from_numpy(host))
-        gate.written()
-        self.gate = gate
-        self._prepared = True
+    def _draw(self, shape):
+        return (np.random.random(shape) > self.rate).astype(np.float32)
 
     def forward(self):
         x = self._in()
         out = self._buf('out', x.shape)
         if self.training:
-            if not getattr(self, "_prepared", False):
-                self.prepare(x.shape)
-            self._prepared = False
+            self.gate = self._drawn(x.shape)
             self._call("dnb_mul", x.ptr(), self.gate.ptr(), out.ptr(), x.size)
         else:
             self._call("dnb_scale", x.ptr(), out.ptr(), x.size, float(1 - self.rate))
@@ -56,8 +82,9 @@ class Dropout(Layer):
         self.parents[0].delta = dx
 
 
-class GaussianNoise(Layer):
-    """regularization.py:28-47: host-drawn noise (same global stream), added on the device."""
+class GaussianNoise(_HostDrawLayer):
+    """regularization.py:28-47: host-drawn noise (same global stream, one ``np.random.normal`` per training forward),
+    added on the device from a static buffer (graph-capturable, like Dropout's gate)."""
 
     def __init__(self, l_in, mean=0.0, stddev=1.0, name="GaussianNoise"):
         super().__init__(name=name)
@@ -66,13 +93,16 @@ class GaussianNoise(Layer):
         self.stddev = stddev
         self.oshape = self.parents[0].oshape
 
+    def _draw(self, shape):
+        return np.random.normal(loc=self.mean, scale=self.stddev, size=shape)
+
     def forward(self):
         x = self._in()
         if not self.training:
             self.output = x
             return
         import ctypes as C
-        noise = DArray(host=np.random.normal(loc=self.mean, scale=self.stddev, size=x.shape))
+        noise = self._drawn(x.shape)
         out = self._buf('out', x.shape)
         ptrs = (C.c_void_p * 2)(x.ptr(), noise.ptr())
         self._call("dnb_add_n", ptrs, 2, out.ptr(), x.size)

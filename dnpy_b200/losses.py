@@ -19,6 +19,7 @@ class Loss:
         self.name = name
         self.epsilon = 10e-8
         self._memo = None       # (id(y_pred), id(y_target), loss, delta, flags)
+        self._last_out = None
         self._bufs = {}
 
     def _extra(self):
@@ -52,6 +53,7 @@ class Loss:
         _lib.call(self._kernel, p.ptr(), t.ptr(), delta.ptr(), out.data_ptr(), b, n, *self._extra(), scale,
                   ws.data_ptr(), stream_ptr())
         delta.written()
+        self._last_out = out        # [loss, flags] of the most recent launch (Net.compute_losses reads the delta flags here)
         self._memo = (y_pred, y_target, out, delta, who)
         return self._memo
 

@@ -318,9 +318,24 @@ class Net:
             from . import parallel
             parallel.allreduce_grads(self)
 
+    @staticmethod
+    def _opt_hyper(o):
+        """Class + scalar hyper-parameters of an optimizer copy (state dicts excluded)."""
+        if o is None:
+            return None
+        return (type(o).__name__,) + tuple(sorted((k, v) for k, v in vars(o).items()
+                                                 if isinstance(v, (int, float, bool, str)) and k != "name"))
+
+    def _uniform_hyper(self):
+        """The hyper-parameters shared by EVERY layer's deep-copied optimizer (base.py:34), or None when they differ
+        (layer-wise lr, a user poking ``l.optimizer.lr``): only then is one launch over the whole arena legal."""
+        hs = {self._opt_hyper(l.optimizer) for l in self.bts_layers if any(k in l.grads for k in l.params.keys())}
+        return next(iter(hs)) if len(hs) == 1 else None
+
     def apply_grads(self):
         a = self._bind_arenas() if self._device_ready() else None
-        if a is not None and a["uniform"] and not any(l.frozen for l in self.bts_layers):
+        if a is not None and a["uniform"] and not any(l.frozen for l in self.bts_layers) \
+                and self._uniform_hyper() is not None:
             self._apply_fused(a)
             return
         for l in self.bts_layers:
@@ -330,7 +345,7 @@ class Net:
     def _apply_fused(self, a):
         """One optimizer launch over the whole arena: legal because every layer's optimizer copy
         carries identical hyper-parameters (base.py:34)."""
-        o = self.optimizer
+        o = a["slots"][0][0].optimizer          # the layers' copies carry the live hyper-parameters, like the reference
         p, g, n = a["P"].data_ptr(), a["G"].data_ptr(), a["total"]
         if isinstance(o, Adam):
             if o.bias_correction:
@@ -367,8 +382,10 @@ class Net:
         elif math.isinf(loss):
             raise ValueError("Inf in the loss function")
         if flags is None:
-            memo = loss_obj._memo
-            flags = int(memo[2][1].item()) if memo is not None else 0
+            # the fused loss kernel's [loss, flags] tensor of the launch that just produced loss and delta (the
+            # memo itself is consumed by the compute_loss / compute_delta pair)
+            out = getattr(loss_obj, "_last_out", None)
+            flags = int(out[1].item()) if out is not None else 0
         if flags & 4:
             raise ValueError("NaNs in the delta")
         elif flags & 8:
@@ -410,7 +427,7 @@ class Net:
         if not (self.use_graph and not self.debug and self._graph_ok_for_world()):
             return self._step_body(xs, ys)
         key = (tuple(x.ptr() for x in xs), tuple(y.ptr() for y in ys), tuple(x.shape for x in xs), self.mode,
-               config.math, config.maxpool_route, self._layer_generation())
+               config.math, config.maxpool_route, self._uniform_hyper(), self._layer_generation())
         ent = self._graphs.get(key)
         if ent is None:
             ent = self._graphs[key] = dict(calls=0, graph=None, outs=None)
@@ -560,7 +577,9 @@ class Net:
                     self.backward()
                     self.apply_grads()
                 else:
-                    self._pending_flags.append(self.train_step(x_mb, y_mb))
+                    # the step returns the losses' PERSISTENT [loss, flags] tensors: keep a copy per step, or only the
+                    # newest step would ever be checked
+                    self._pending_flags.append([o.clone() for o in self.train_step(x_mb, y_mb)])
                     if len(self._pending_flags) >= 64:
                         self._check_pending()
             self._check_pending()

@@ -410,6 +410,14 @@ def dropout_backward(delta, gate):
     return delta * gate
 
 
+def gaussian_noise_forward(x, mean, stddev, training, rng=np.random):
+    """regularization.py:39-44: one ``normal(mean, stddev, x.shape)`` draw from the global stream per TRAINING forward;
+    identity in test mode.  Backward is a pass-through copy (regularization.py:46-47)."""
+    if not training:
+        return x
+    return x + rng.normal(loc=mean, scale=stddev, size=np.shape(x))
+
+
 def batchnorm_forward(x, gamma, beta, moving_mu, moving_var, momentum, training):
     """regularization.py:94-136 with bias_correction=False.
 

@@ -130,6 +130,8 @@ class OracleNet:
             if n.training:
                 n.cache['gate'] = O.dropout_mask(x.shape, s.rate, self.rng)
             n.output = O.dropout_forward(x, s.rate, n.training, n.cache.get('gate'))
+        elif k == "GaussianNoise":              # regularization.py:39-47
+            n.output = O.gaussian_noise_forward(x, s.mean, s.stddev, n.training, self.rng)
         elif k == "BatchNorm":
             if getattr(s, "bias_correction", False):
                 raise NotImplementedError("BatchNorm(bias_correction=True) is out of scope")
@@ -201,6 +203,8 @@ class OracleNet:
             par.delta = d
         elif k == "Dropout":
             par.delta = O.dropout_backward(d, n.cache['gate'])
+        elif k == "GaussianNoise":
+            par.delta = np.array(d)
         elif k == "BatchNorm":
             par.delta, gg, gb = O.batchnorm_backward(d, P['gamma'], n.cache['bn'])
             G['gamma'] += gg.reshape(G['gamma'].shape)

@@ -44,6 +44,9 @@ LAYER_CASES = [
          kw=dict(pool_size=(2, 2), strides=(2, 2), padding="none")),
     dict(name="avgpool_2x2_same", kind="AvgPool2D", in_shape=(2, 5, 5), batch=2,
          kw=dict(pool_size=(2, 2), strides=(2, 2), padding="same")),
+    # pooling.py:177-181: the window is the whole map; the reference's backward only exists for 4-element windows
+    dict(name="globalavgpool_2x2", kind="GlobalAvgPool2D", in_shape=(3, 2, 2), batch=3, kw=dict()),
+    dict(name="globalavgpool_fwd", kind="GlobalAvgPool2D", in_shape=(2, 5, 4), batch=3, kw=dict(), backward=False),
     dict(name="leakyrelu", kind="LeakyRelu", in_shape=(4, 3), batch=5, kw=dict(alpha=0.3)),
     dict(name="relu", kind="Relu", in_shape=(11,), batch=4, kw=dict()),
     dict(name="prelu", kind="PRelu", in_shape=(6,), batch=5, kw=dict()),
@@ -54,6 +57,11 @@ LAYER_CASES = [
     dict(name="dropout_train", kind="Dropout", in_shape=(8,), batch=6, kw=dict(rate=0.3), training=True, seed=11),
     dict(name="dropout_test", kind="Dropout", in_shape=(8,), batch=6, kw=dict(rate=0.3), training=False,
          backward=False),
+    # regularization.py:39-47: one np.random.normal call per training forward, from the global stream
+    dict(name="gaussiannoise_train", kind="GaussianNoise", in_shape=(3, 4), batch=5, kw=dict(mean=0.1, stddev=0.5),
+         training=True, seed=13),
+    dict(name="gaussiannoise_test", kind="GaussianNoise", in_shape=(7,), batch=4, kw=dict(mean=0.1, stddev=0.5),
+         training=False),
     dict(name="batchnorm_train_1d", kind="BatchNorm", in_shape=(5,), batch=7, kw=dict(), training=True),
     dict(name="batchnorm_train_3d", kind="BatchNorm", in_shape=(2, 3, 3), batch=4, kw=dict(momentum=0.9), training=True),
     dict(name="batchnorm_test", kind="BatchNorm", in_shape=(5,), batch=3, kw=dict(), training=False),

@@ -194,12 +194,29 @@ def test_config_shapes_vs_oracle(case, ns):
             assert e <= TOL32, (k, e)
 
 
+# Persistent tensor-core kernels (grid = min(units, #SMs)): MANY units per CTA, so the multi-unit loop — smem ring reuse,
+# mbarrier phase wrap, TMEM accumulator double-buffer reuse, `it >= 1` — is compared with the oracle, not only it == 0.
+# B=600 -> ~4 images per CTA, B=2048 -> ~14; the 64x64 maps split into several row bands per image (cfg4's shapes).
+PERSISTENT_CASES = [
+    dict(name="sv_conv2_b600", kind="Conv2D", in_shape=(32, 12, 12), batch=600,
+         kw=dict(filters=64, kernel_size=(3, 3), strides=(1, 1), padding="same")),
+    dict(name="sv_conv2_b2048", kind="Conv2D", in_shape=(32, 12, 12), batch=2048,
+         kw=dict(filters=64, kernel_size=(3, 3), strides=(1, 1), padding="same")),
+    dict(name="sv_conv_s1_bands_b24", kind="Conv2D", in_shape=(32, 64, 64), batch=24,
+         kw=dict(filters=32, kernel_size=(3, 3), strides=(1, 1), padding="same")),
+    dict(name="sv_conv_s2_bands_b40", kind="Conv2D", in_shape=(32, 64, 64), batch=40,
+         kw=dict(filters=64, kernel_size=(3, 3), strides=(2, 2), padding="same")),
+    dict(name="sv_pointwise_b40", kind="PointwiseConv2D", in_shape=(32, 64, 64), batch=40, kw=dict(filters=32)),
+    dict(name="tc_dense_b4096", kind="Dense", in_shape=(784,), batch=4096, kw=dict(units=512)),
+]
+
 TC_KINDS = ("Dense", "Conv2D", "PointwiseConv2D")
 TOL_TF32 = 2e-2
 
 
 @pytest.mark.parametrize("math", ["tf32", "bf16"])
-@pytest.mark.parametrize("case", [c for c in cases.LAYER_CASES + BIG_CASES if c["kind"] in TC_KINDS], ids=lambda c: c["name"])
+@pytest.mark.parametrize("case", [c for c in cases.LAYER_CASES + BIG_CASES + PERSISTENT_CASES if c["kind"] in TC_KINDS],
+                         ids=lambda c: c["name"])
 def test_tensor_core_path_vs_oracle(case, math, ns):
     """math="tf32": tcgen05 kernels (TF32 operands, fp32 accumulation in TMEM) for Dense / Conv2D /
     PointwiseConv2D, tolerance rel 2e-2 (BASELINE north_star); shapes the tensor path does not take
@@ -216,6 +233,36 @@ def test_tensor_core_path_vs_oracle(case, math, ns):
         if k in got:
             e = rel_err(np.asarray(got[k]).reshape(np.shape(w)), w)
             assert e <= TOL_TF32, (k, e)
+
+
+_FULL = {}
+
+
+@pytest.mark.parametrize("math", ["tf32", "bf16"])
+def test_full_batch_conv2_vs_oracle(math, ns):
+    """The benchmarked launch itself: Conv2D 32x12x12 -> 64, 3x3 'same' at the BASELINE batch (B=8192: 55 images per
+    persistent CTA) on the tcgen05 shifted-view kernels, forward / data gradient / weight + bias gradient against the
+    float64 oracle on the SAME 8192 images (tolerance rel 2e-2, tensor-level metric of conftest.rel_err); a random
+    sample of images is additionally checked image by image so an error confined to a few units cannot hide."""
+    import dnpy_b200
+    case = dict(name="sv_conv2_b8192", kind="Conv2D", in_shape=(32, 12, 12), batch=8192,
+                kw=dict(filters=64, kernel_size=(3, 3), strides=(1, 1), padding="same"))
+    if "want" not in _FULL:
+        _FULL["want"] = drive.run_layer_case_oracle(ns, case)
+    want = _FULL["want"]
+    dnpy_b200.set_math(math)
+    try:
+        got = drive.run_layer_case(ns, case)
+    finally:
+        dnpy_b200.set_math("fp32")
+    for k in ("out", "dx0", "g_w1", "g_b1"):
+        e = rel_err(np.asarray(got[k]).reshape(np.shape(want[k])), want[k])
+        assert e <= TOL_TF32, (k, e)
+    pick = np.random.RandomState(0).choice(8192, 96, replace=False)
+    for k in ("out", "dx0"):
+        for b in pick:
+            e = rel_err(got[k][b], want[k][b])
+            assert e <= TOL_TF32, (k, int(b), e)
 
 
 def test_tc_gemm_all_operand_orientations():

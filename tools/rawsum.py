@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One line per kernel from an .ncu-rep (raw page): time, DRAM bytes, key utilisation, launch config.
-   python profiles/rawsum.py REPORT.ncu-rep"""
+   python tools/rawsum.py REPORT.ncu-rep"""
 import csv, subprocess, sys
 out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise `ncu --page source --csv` for one kernel launch: stall-reason totals and the hottest SASS lines.
-   python profiles/srcsum.py REPORT.ncu-rep LAUNCH_INDEX [TOP]"""
+   python tools/srcsum.py REPORT.ncu-rep LAUNCH_INDEX [TOP]"""
 import csv, subprocess, sys, collections
 rep, idx = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Turn ncu outputs brought back in gpurun_out/ into the small text summaries committed here.
 
-  python profiles/summarize.py launches gpurun_out/launches_X.csv  > profiles/r01_launches_X.txt
-  python profiles/summarize.py full     gpurun_out/prof_X.ncu-rep  > profiles/r01_full_X.txt
+  python tools/summarize.py launches gpurun_out/launches_X.csv  > profiles/r01_launches_X.txt
+  python tools/summarize.py full     gpurun_out/prof_X.ncu-rep  > profiles/r01_full_X.txt
 """
 import collections
 import csv
