@@ -39,6 +39,8 @@ SIGNATURES = {
     "dnb_fill_i32": (_i, [_p, _z, C.c_int32, _p]),
     "dnb_dense_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "dnb_dense_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _R, _R, _f, _i, _p]),
+    "dnb_dense_bwd_data": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "dnb_conv2d_bwd_data": (_i, [_p, _p, _p, _W, _p, _i, _p]),
     "dnb_conv2d_ws_bytes": (_z, [_W, _i]),
     "dnb_conv2d_fwd": (_i, [_p, _p, _p, _p, _W, _p, _i, _p]),
     "dnb_conv2d_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _W, _f, _R, _R, _f, _p, _i, _p]),

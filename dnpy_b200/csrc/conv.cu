@@ -677,6 +677,26 @@ int dnb_conv2d_bwd(const float* x, const float* w, const float* b, const float* 
     return DNB_OK;
 }
 
+// Data gradient alone (the second half of Conv2D.backward, convolution.py:244-250,271-273): what a caller runs when the
+// parent's delta is wanted but the parameter gradients are not (Net materialises the delta of an Input layer lazily —
+// nothing on the training path consumes it).  Same kernel selection as dnb_conv2d_bwd.
+int dnb_conv2d_bwd_data(const float* w, const float* dy, float* dx, const dnb_win_t* g, void* ws, int math,
+                        dnb_stream_t stream) {
+    int rc = check_win("conv2d_bwd_data", g);
+    if (rc) return rc;
+    if (g->B == 0) return DNB_OK;
+    DNB_CHECK_ARG(w && dy && dx, "conv2d_bwd_data: null pointer");
+    cudaStream_t st = S(stream);
+    const bool thin = thin_conv_supported(g);
+    const bool thin_tc = thin && g->C >= 3 && (long)g->OH * g->OW >= 1024 && !(getenv("DNB_THIN_TC_WGRAD") && atoi(getenv("DNB_THIN_TC_WGRAD")) == 0);
+    const bool tc = math >= DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_DGRAD);
+    if (thin && !(thin_tc && tc)) return thin_conv_bwd(nullptr, w, dy, dx, nullptr, nullptr, g, 0.f, /*skip_wgrad=*/true, st);
+    if (tc) return tc_conv_dgrad(dy, w, dx, g, ws, math == DNB_MATH_BF16, st);
+    GatherArgs a{dy, w, nullptr, dx, g->B, g->F, g->OH, g->OW, g->C, g->H, g->W, g->kh, g->kw,
+                 1, 1, g->sy, g->sx, g->kh - 1 - g->pt, g->kw - 1 - g->pl, 0, 0.f};
+    return launch_gather<true>("conv2d_bwd_data", a, st);
+}
+
 int dnb_dwconv2d_fwd(const float* x, const float* w, const float* b, float* y, const dnb_win_t* g, dnb_stream_t stream) {
     int rc = check_win("dwconv2d_fwd", g);
     if (rc) return rc;

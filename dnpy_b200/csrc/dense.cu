@@ -339,6 +339,40 @@ int dnb_dense_fwd(const float* x, const float* w, const float* b, float* y,
     return launch_sgemm<EPI_BIAS>("dense_fwd", a, S(stream));
 }
 
+// dX[B,in] = dY[B,out] . W^T (core.py:121), shared by dnb_dense_bwd and dnb_dense_bwd_data
+static int dense_dx(const float* dy, const float* w, float* dx, int B, int in, int out, int math, cudaStream_t st) {
+    int rc;
+    if (out <= SKN && B >= 64) {
+        const size_t dx_smem = ((size_t)out * in + 32 * SKN) * sizeof(float);
+        if (head_supported(B, in, out) && head_dx(dy, w, dx, B, in, out, st)) {
+            DNB_LAUNCH_CHECK("dense_bwd_dx");
+        } else if ((in & 3) == 0 && dx_smem <= 160 * 1024 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+            cudaFuncSetAttribute(skinny_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dx_smem);
+            skinny_dx_kernel<<<(B + 31) / 32, 256, dx_smem, st>>>(dy, w, dx, B, in, out, 32);
+            DNB_LAUNCH_CHECK("dense_bwd_dx");
+        } else {
+            GemmArgs a{dy, out, 1, w, 1, out, dx, B, in, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0};
+            rc = launch_sgemm<EPI_STORE>("dense_bwd_dx", a, st);
+            if (rc) return rc;
+        }
+        return DNB_OK;
+    }
+    // B(k=o, n=i) = W[i*out + o]  -> K-major B
+    if (math >= DNB_MATH_TF32 && tc_gemm_supported(B, in, out, true, true))
+        return tc_gemm(dy, w, dx, B, in, out, TC_A_KMAJOR | TC_B_KMAJOR, nullptr, nullptr, 0.f, 0.f, 0.f, st);
+    GemmArgs a{dy, out, 1, w, 1, out, dx, B, in, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0};
+    return launch_sgemm<EPI_STORE>("dense_bwd_dx", a, st);
+}
+
+// The data gradient alone: for a caller that wants the parent's delta but not the parameter gradients (Net materialises
+// the delta of an Input layer lazily).
+int dnb_dense_bwd_data(const float* w, const float* dy, float* dx, int B, int in, int out, int math, dnb_stream_t stream) {
+    DNB_CHECK_ARG(B >= 0 && in > 0 && out > 0, "dense_bwd_data: bad shape B=%d in=%d out=%d", B, in, out);
+    if (B == 0) return DNB_OK;
+    DNB_CHECK_ARG(w && dy && dx, "dense_bwd_data: null pointer");
+    return dense_dx(dy, w, dx, B, in, out, math, S(stream));
+}
+
 int dnb_dense_bwd(const float* x, const float* w, const float* b, const float* dy,
                   float* dx, float* gw, float* gb, int B, int in, int out, float inv_m,
                   dnb_reg_t reg_w, dnb_reg_t reg_b, float reg_scale, int math, dnb_stream_t stream) {
@@ -348,17 +382,9 @@ int dnb_dense_bwd(const float* x, const float* w, const float* b, const float* d
     cudaStream_t st = S(stream);
     int rc;
     if (out <= SKN && B >= 64) {
-        const size_t dx_smem = ((size_t)out * in + 32 * SKN) * sizeof(float);
         const bool head = head_supported(B, in, out);
-        if (dx && head && head_dx(dy, w, dx, B, in, out, st)) {
-            DNB_LAUNCH_CHECK("dense_bwd_dx");
-        } else if (dx && (in & 3) == 0 && dx_smem <= 160 * 1024 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
-            cudaFuncSetAttribute(skinny_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dx_smem);
-            skinny_dx_kernel<<<(B + 31) / 32, 256, dx_smem, st>>>(dy, w, dx, B, in, out, 32);
-            DNB_LAUNCH_CHECK("dense_bwd_dx");
-        } else if (dx) {
-            GemmArgs a{dy, out, 1, w, 1, out, dx, B, in, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0};
-            rc = launch_sgemm<EPI_STORE>("dense_bwd_dx", a, st);
+        if (dx) {
+            rc = dense_dx(dy, w, dx, B, in, out, math, st);
             if (rc) return rc;
         }
         if (head && head_dw(x, dy, w, gw, b, gb, B, in, out, inv_m, reg_w.l1 * reg_scale, reg_w.l2 * reg_scale,
@@ -376,13 +402,7 @@ int dnb_dense_bwd(const float* x, const float* w, const float* b, const float* d
         return DNB_OK;
     }
     if (dx) {
-        // dX[B,in] = dY[B,out] . W^T : B(k=o, n=i) = W[i*out + o]  -> K-major B
-        if (math >= DNB_MATH_TF32 && tc_gemm_supported(B, in, out, true, true)) {
-            rc = tc_gemm(dy, w, dx, B, in, out, TC_A_KMAJOR | TC_B_KMAJOR, nullptr, nullptr, 0.f, 0.f, 0.f, st);
-        } else {
-            GemmArgs a{dy, out, 1, w, 1, out, dx, B, in, out, nullptr, nullptr, 0.f, 0.f, 0.f, 0};
-            rc = launch_sgemm<EPI_STORE>("dense_bwd_dx", a, st);
-        }
+        rc = dense_dx(dy, w, dx, B, in, out, math, st);
         if (rc) return rc;
     }
     // gW[in,out] += (X^T[in,B] . dY[B,out] + reg) * inv_m : A(m=i,k=b) = X[b*in + i]  -> M-major A

@@ -209,6 +209,45 @@ class DArray:
         return np.array(self.host())
 
 
+class LazyDArray(DArray):
+    """A tensor nobody on the training path consumes (the delta of an Input layer, the pre-pool output of a fused
+    conv->pool block): it is NOT computed when the layer runs; ``thunk()`` launches the kernels that produce it the
+    first time somebody looks (``np.asarray``, ``==``, ``.ptr()`` ...) and must only read buffers that stay valid
+    until the layer runs again (static layer buffers, parameter snapshots).  ``written()`` — the layer ran again —
+    drops the materialised copy."""
+
+    def __init__(self, shape, thunk, is_int=False):
+        self.is_int = bool(is_int)
+        self._host = None
+        self._dev = None
+        self._host_ok = False
+        self._dev_ok = False
+        self._pinned = False
+        self.shape = tuple(int(s) for s in shape)
+        self._thunk = thunk
+
+    @property
+    def materialised(self):
+        return self._dev_ok or self._host_ok
+
+    def dev(self):
+        if not self.materialised:
+            self._dev = self._thunk()
+            assert tuple(self._dev.shape) == self.shape, (tuple(self._dev.shape), self.shape)
+            self._dev_ok = True
+        return super().dev()
+
+    def host(self):
+        if not self.materialised:
+            self.dev()
+        return super().host()
+
+    def written(self):
+        self._dev, self._host = None, None
+        self._dev_ok = self._host_ok = False
+        return self
+
+
 def _binary(name):
     def op(self, other):
         return getattr(self.host(), name)(np.asarray(other))

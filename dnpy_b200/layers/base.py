@@ -43,6 +43,9 @@ class Layer:
         self.index = 0
         self.debug = False
         self._bufs = {}
+        # set by Net.build for a layer whose data gradient only feeds an Input layer: nothing on the training path
+        # consumes it, so backward skips it and hands the Input a LazyDArray (computed when somebody reads it)
+        self._lazy_dx = False
 
     def __str__(self):
         return self.name
@@ -132,6 +135,12 @@ class Layer:
             self._bufs[key] = cur
             Layer.buffer_generation += 1
         return cur.ptr()
+
+    def _snapshot(self, key, src):
+        """Copy of a small tensor (weights) taken NOW, for a lazy result that may be read after the optimizer ran."""
+        snap = self._buf(key, src.shape)
+        snap.dev().copy_(src.dev())
+        return snap
 
     @staticmethod
     def _call(name, *args):

@@ -3,7 +3,7 @@ import numpy as np
 
 from .base import Layer
 from .. import initializers
-from ..darray import DArray, ParamDict
+from ..darray import DArray, LazyDArray, ParamDict
 from ..regularizers import reg_coeffs
 from ..runtime import config
 from .._lib import Reg
@@ -101,13 +101,24 @@ class Dense(Layer):
         x = self._in()
         dy = self._delta()
         b, fin = x.shape
-        dx = self._buf('dx', (b, fin))
+        lazy = self._lazy_dx and not self.debug
+        dx = None if lazy else self._buf('dx', (b, fin))
         self._call("dnb_dense_bwd", x.ptr(), self.params['w1'].ptr(), self.params['b1'].ptr(), dy.ptr(),
-                   dx.ptr(), self.grads['w1'].ptr(), self.grads['b1'].ptr(), b, fin, self.units,
+                   None if lazy else dx.ptr(), self.grads['w1'].ptr(), self.grads['b1'].ptr(), b, fin, self.units,
                    self._inv_m(b), Reg(*reg_coeffs(self.kernel_regularizer)), Reg(*reg_coeffs(self.bias_regularizer)),
                    config.reg_scale, config.math)
         self.grads['w1'].written()
         self.grads['b1'].written()
+        if lazy:
+            # only an Input layer would receive this delta: dead on the training path, computed on demand from this
+            # step's dy buffer and a snapshot of the weights
+            w_now, math, units = self._snapshot('w_snap', self.params['w1']), config.math, self.units
+
+            def materialise():
+                out = self._buf('dx', (b, fin))
+                self._call("dnb_dense_bwd_data", w_now.ptr(), dy.ptr(), out.ptr(), b, fin, units, math)
+                return out.dev()
+            dx = LazyDArray((b, fin), materialise)
         self.parents[0].delta = dx
 
 
@@ -137,7 +148,14 @@ class Reshape(Layer):
     def backward(self):
         dy = self._delta()
         new_shape = (-1, *self.parents[0].oshape) if not self.include_batch else self.oshape_batch
-        self.parents[0].delta = DArray.device(dy.dev().view(*[int(s) for s in new_shape]))
+        new_shape = [int(s) for s in new_shape]
+        if isinstance(dy, LazyDArray) and not dy.materialised:        # stay lazy: a view of a delta nobody computed yet
+            full = [int(s) for s in new_shape]
+            if full[0] == -1:
+                full[0] = dy.size // max(1, int(np.prod(full[1:])))
+            self.parents[0].delta = LazyDArray(full, lambda: dy.dev().view(*new_shape))
+            return
+        self.parents[0].delta = DArray.device(dy.dev().view(*new_shape))
 
 
 class Flatten(Reshape):

@@ -130,7 +130,16 @@ class Net:
         OPT-IN (DNPY_B200_FUSION=1): correct (the GPU suite passes with it), but measured slower on B200 — the third output
         forces smaller ring chunks, the pool forward goes 171 -> 250 us to save the activation's 49 us (1.375 -> 1.404 ms/step)."""
         import os
-        from .layers import MaxPool2D, LeakyRelu
+        from .layers import MaxPool2D, LeakyRelu, Conv2D, Dense, Input, Reshape, DepthwiseConv2D
+        # dead data gradients: a Conv2D / Dense whose delta would only travel (through Reshape views) to an Input layer
+        # skips it; the Input's `delta` becomes a LazyDArray that runs the data-gradient kernel if somebody reads it
+        for l in self.fts_layers:
+            l._lazy_dx = False
+            if isinstance(l, (Conv2D, Dense)) and not isinstance(l, DepthwiseConv2D) and not os.environ.get("DNPY_B200_EAGER_DX"):
+                p = l.parents[0]
+                while isinstance(p, Reshape):
+                    p = p.parents[0]
+                l._lazy_dx = isinstance(p, Input)
         consumers = {}
         for l in self.fts_layers:
             for p in l.parents:

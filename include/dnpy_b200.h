@@ -93,6 +93,10 @@ int dnb_dense_fwd(const float* x, const float* w, const float* b, float* y,
 int dnb_dense_bwd(const float* x, const float* w, const float* b, const float* dy,
                   float* dx, float* gw, float* gb, int B, int in, int out, float inv_m,
                   dnb_reg_t reg_w, dnb_reg_t reg_b, float reg_scale, int math, dnb_stream_t stream);
+/* dx[B,in] = dy @ w^T alone (core.py:121 without 129-135): the delta of an Input layer is dead on the training
+ * path, so Net skips it in dnb_dense_bwd (dx = NULL) and runs this only when somebody reads `l_in.delta`. */
+int dnb_dense_bwd_data(const float* w, const float* dy, float* dx, int B, int in, int out, int math,
+                       dnb_stream_t stream);
 
 /* ---- Conv2D / PointwiseConv2D (layers/convolution.py:193-273, 276-284) ------ */
 size_t dnb_conv2d_ws_bytes(const dnb_win_t* g, int math);
@@ -105,6 +109,9 @@ int dnb_conv2d_bwd(const float* x, const float* w, const float* b, const float* 
                    float* dx, float* gw, float* gb, const dnb_win_t* g, float inv_m,
                    dnb_reg_t reg_w, dnb_reg_t reg_b, float reg_scale,
                    void* ws, int math, dnb_stream_t stream);
+/* dx alone (convolution.py:244-250,271-273 without 258-268): lazily materialised delta of an Input layer. */
+int dnb_conv2d_bwd_data(const float* w, const float* dy, float* dx, const dnb_win_t* g, void* ws, int math,
+                        dnb_stream_t stream);
 
 /* ---- DepthwiseConv2D (layers/convolution.py:323-388); w is [C,1,kh,kw] ------- */
 int dnb_dwconv2d_fwd(const float* x, const float* w, const float* b, float* y,

