@@ -44,6 +44,11 @@ SIGNATURES = {
     "dnb_conv2d_ws_bytes": (_z, [_W, _i]),
     "dnb_conv2d_fwd": (_i, [_p, _p, _p, _p, _W, _p, _i, _p]),
     "dnb_conv2d_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _W, _f, _R, _R, _f, _p, _i, _p]),
+    "dnb_conv_pool_act_supported": (_i, [_W, _W]),
+    "dnb_conv_pool_act_fwd": (_i, [_p, _p, _p, _p, _p, _W, _W, _f, _p]),
+    "dnb_conv_pool_act_bwd": (_i, [_p, _p, _p, _p, _p, _W, _W, _f, _f, _p]),
+    "dnb_idx_gate_unpack": (_i, [_p, _p, _z, _p]),
+    "dnb_idx_gate_set": (_i, [_p, _p, _z, _p]),
     "dnb_dwconv2d_fwd": (_i, [_p, _p, _p, _p, _W, _p]),
     "dnb_dwconv2d_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _W, _f, _R, _f, _p]),
     "dnb_maxpool2d_fwd": (_i, [_p, _p, _p, _W, _p]),

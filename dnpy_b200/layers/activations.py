@@ -3,7 +3,7 @@ import numpy as np
 
 from .base import Layer
 from .. import initializers
-from ..darray import ParamDict
+from ..darray import LazyDArray, ParamDict
 
 
 class LeakyRelu(Layer):
@@ -18,6 +18,8 @@ class LeakyRelu(Layer):
         self.gate = None
 
     def forward(self):
+        if self.__dict__.pop("_cpa_skip_fwd", False):      # the fused conv->pool->act block wrote self.output already
+            return
         x = self._in()
         pre, self._precomputed = getattr(self, "_precomputed", None), None
         if pre is not None and pre[0] is x:              # the producing MaxPool2D already wrote this layer's output
@@ -27,11 +29,21 @@ class LeakyRelu(Layer):
         self._call("dnb_leakyrelu_fwd", x.ptr(), out.ptr(), x.size, float(self.alpha))
         self.output = out
 
-    def backward(self):
+    def _backward_now(self):
         x, dy = self._in(), self._delta()
         dx = self._buf('dx', x.shape)
         self._call("dnb_leakyrelu_bwd", x.ptr(), dy.ptr(), dx.ptr(), x.size, float(self.alpha))
-        self.parents[0].delta = dx
+        return dx
+
+    def backward(self):
+        block = getattr(self, "_cpa_block", None)
+        if block is not None and block._cpa_live is not None:
+            # fused block (layers/convolution.py): the conv layer consumes THIS layer's incoming delta directly; the
+            # pool's delta exists only if somebody reads it
+            self._delta()
+            self.parents[0].delta = LazyDArray(self.parents[0].output.shape, lambda: self._backward_now().dev())
+            return
+        self.parents[0].delta = self._backward_now()
 
 
 class Relu(LeakyRelu):

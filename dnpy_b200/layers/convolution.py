@@ -9,7 +9,7 @@ import numpy as np
 
 from .base import Layer
 from .. import initializers, utils, _lib
-from ..darray import LazyDArray, ParamDict
+from ..darray import DArray, LazyDArray, ParamDict
 from ..regularizers import reg_coeffs
 from ..runtime import config
 from .._lib import Reg, Win
@@ -87,8 +87,58 @@ class Conv2D(Conv):
         assert len(self.kernel_size) == 3
         assert len(self.strides) == 2
 
+    # ---- fused Conv2D -> MaxPool2D -> LeakyRelu/Relu block (csrc/fused_cpa.cu), planned by Net.build -----------------
+    _cpa = None           # (pool, act) when this layer heads a fusable block
+    _cpa_live = None      # state of the block between this step's forward and backward
+
+    def _cpa_usable(self):
+        # the fused backward implements the PER_SAMPLE pool routing; LITERAL (pooling.py:95 as written) keeps the
+        # layer-by-layer kernels
+        return (self._cpa is not None and not self.debug and config.maxpool_route == _lib.ROUTE_PER_SAMPLE
+                and self.kernel_regularizer is None and self.bias_regularizer is None)
+
+    def _forward_fused(self, x):
+        pool, act = self._cpa
+        b = x.shape[0]
+        g, gp = self._win(b), pool._win(b)
+        n_pool = b * int(np.prod(pool.oshape))
+        aout = act._buf('out', (b, *act.oshape))
+        ig = self._raw('cpa_idx_gate', n_pool)                  # one byte per pooled element: argmax offset | gate << 4
+        self._call("dnb_conv_pool_act_fwd", x.ptr(), self.params['w1'].ptr(), self.params['b1'].ptr(), aout.ptr(), ig,
+                   g, gp, float(act.alpha))
+        # the tensors the fused kernel never wrote stay observable (computed by the layer-by-layer kernels on a read)
+        w_now, b_now = self._snapshot('w_snap_f', self.params['w1']), self._snapshot('b_snap_f', self.params['b1'])
+        math = config.math
+
+        def conv_out():
+            out = self._buf('out', (b, *self.oshape))
+            ws = self._raw('ws', _lib.load().dnb_conv2d_ws_bytes(g, math))
+            self._call("dnb_conv2d_fwd", x.ptr(), w_now.ptr(), b_now.ptr(), out.ptr(), g, ws, math)
+            return out.dev()
+        self.output = LazyDArray((b, *self.oshape), conv_out)
+        conv_lazy = self.output
+
+        def pool_out():
+            out = pool._buf('out', (b, *pool.oshape))
+            idx = pool._buf('idx', (b, *pool.oshape), is_int=True)
+            pool._call("dnb_maxpool2d_fwd", conv_lazy.ptr(), out.ptr(), idx.ptr(), gp)
+            return out.dev()
+
+        def pool_idx():
+            idx = pool._buf('idx_unpacked', (b, *pool.oshape), is_int=True)
+            pool._call("dnb_idx_gate_unpack", ig, idx.ptr(), n_pool)
+            return idx.dev()
+        pool.output = LazyDArray((b, *pool.oshape), pool_out)
+        pool.output_idxs = LazyDArray((b, *pool.oshape), pool_idx, is_int=True)
+        act.output = aout
+        pool._cpa_skip_fwd = act._cpa_skip_fwd = True
+        self._cpa_live = dict(ig=ig, idx=pool.output_idxs, x=x)
+
     def forward(self):
         x = self._in()
+        self._cpa_live = None
+        if self._cpa_usable():
+            return self._forward_fused(x)
         b = x.shape[0]
         g = self._win(b)
         out = self._buf('out', (b, *self.oshape))
@@ -97,7 +147,33 @@ class Conv2D(Conv):
                    g, ws, config.math)
         self.output = out
 
+    def _backward_fused(self, live):
+        """gW / gb straight from the activation's delta (PER_SAMPLE routing); the parent's delta stays lazy."""
+        pool, act = self._cpa
+        x = live['x']
+        b = x.shape[0]
+        g, gp = self._win(b), pool._win(b)
+        if pool.output_idxs is not live['idx']:        # the caller assigned its own argmax tensor: route through it
+            user = DArray.wrap(pool.output_idxs, is_int=True)
+            self._call("dnb_idx_gate_set", user.ptr(), live['ig'], user.size)
+        self._call("dnb_conv_pool_act_bwd", x.ptr(), act._delta().ptr(), live['ig'], self.grads['w1'].ptr(),
+                   self.grads['b1'].ptr(), g, gp, float(act.alpha), self._inv_m(b))
+        self.grads['w1'].written()
+        self.grads['b1'].written()
+        w_now, math = self._snapshot('w_snap', self.params['w1']), config.math
+
+        def materialise():              # Input.delta on demand: pool.delta -> conv.delta -> data gradient, layer by layer
+            dy = self._delta()
+            out = self._buf('dx', x.shape)
+            ws = self._raw('ws', _lib.load().dnb_conv2d_ws_bytes(g, math))
+            self._call("dnb_conv2d_bwd_data", w_now.ptr(), dy.ptr(), out.ptr(), g, ws, math)
+            return out.dev()
+        self.parents[0].delta = LazyDArray(x.shape, materialise)
+
     def backward(self):
+        live, self._cpa_live = self._cpa_live, None
+        if live is not None and self._cpa_usable() and self._lazy_dx:
+            return self._backward_fused(live)
         x, dy = self._in(), self._delta()
         b = x.shape[0]
         g = self._win(b)

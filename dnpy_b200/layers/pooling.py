@@ -3,6 +3,7 @@ import numpy as np
 
 from .base import Layer
 from .. import utils, _lib
+from ..darray import DArray, LazyDArray
 from ..runtime import config
 from .._lib import Win
 
@@ -47,6 +48,8 @@ class MaxPool2D(Pool):
         self.output_idxs = None
 
     def forward(self):
+        if self.__dict__.pop("_cpa_skip_fwd", False):      # the fused conv->pool->act block set output / output_idxs (lazy)
+            return
         x = self._in()
         b = x.shape[0]
         out = self._buf('out', (b, *self.oshape))
@@ -67,15 +70,25 @@ class MaxPool2D(Pool):
         self.output = out
         self.output_idxs = idx
 
-    def backward(self):
+    def _backward_now(self, route):
         x, dy = self._in(), self._delta()
         b = x.shape[0]
         g = self._win(b)
         dx = self._buf('dx', x.shape)
-        route = config.maxpool_route
         ws = self._raw('ws', _lib.load().dnb_maxpool2d_bwd_ws_bytes(g, route))
-        self._call("dnb_maxpool2d_bwd", dy.ptr(), self.output_idxs.ptr(), dx.ptr(), g, route, ws)
-        self.parents[0].delta = dx
+        self._call("dnb_maxpool2d_bwd", dy.ptr(), DArray.wrap(self.output_idxs, is_int=True).ptr(), dx.ptr(), g, route, ws)
+        return dx
+
+    def backward(self):
+        route = config.maxpool_route
+        block = getattr(self, "_cpa_block", None)
+        if block is not None and block._cpa_live is not None:
+            # fused block: the conv layer computes its gradients from the activation's delta; this layer's 4.7x larger
+            # delta (the conv layer's dY) is only materialised if somebody reads it
+            shape = (self.output.shape[0], *self.parents[0].oshape)
+            self.parents[0].delta = LazyDArray(shape, lambda: self._backward_now(route).dev())
+            return
+        self.parents[0].delta = self._backward_now(route)
 
 
 class GlobalMaxPool2D(MaxPool2D):

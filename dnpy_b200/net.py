@@ -144,6 +144,29 @@ class Net:
         for l in self.fts_layers:
             for p in l.parents:
                 consumers.setdefault(id(p), []).append(l)
+        # fused first block (csrc/fused_cpa.cu): Conv2D(C=1, 3x3) -> MaxPool2D(3x3/2) -> LeakyRelu/Relu, each the only
+        # consumer of its parent: one forward kernel and one backward kernel, the conv output / gradient never reach HBM
+        for l in self.fts_layers:
+            l._cpa = None
+            l._cpa_block = None
+        for l in self.fts_layers:
+            cons = consumers.get(id(l), [])
+            if type(l) is not Conv2D or len(cons) != 1 or type(cons[0]) is not MaxPool2D or os.environ.get("DNPY_B200_NO_CPA"):
+                continue
+            pool = cons[0]
+            cons2 = consumers.get(id(pool), [])
+            if len(cons2) != 1 or type(cons2[0]).__name__ not in ("LeakyRelu", "Relu") or not isinstance(cons2[0], LeakyRelu):
+                continue
+            act = cons2[0]
+            if l in self.l_out or pool in self.l_out or not l._lazy_dx:
+                continue
+            try:
+                ok = _lib.load().dnb_conv_pool_act_supported(l._win(1), pool._win(1))
+            except ValueError:
+                ok = 0
+            if ok:
+                l._cpa = (pool, act)
+                pool._cpa_block = act._cpa_block = l
         for l in self.fts_layers:
             l._fused_act = None
             cons = consumers.get(id(l), [])
@@ -506,7 +529,7 @@ class Net:
     def _mark_written(self):
         """After a replay the host copies of everything the step wrote are stale."""
         for l in self.fts_layers:
-            for d in (l.output, l.delta):
+            for d in (l.output, l.delta, getattr(l, "output_idxs", None)):
                 if isinstance(d, DArray):
                     d.written()
             for d in list(l.params.values()) + list(l.grads.values()):

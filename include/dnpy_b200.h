@@ -113,6 +113,23 @@ int dnb_conv2d_bwd(const float* x, const float* w, const float* b, const float* 
 int dnb_conv2d_bwd_data(const float* w, const float* dy, float* dx, const dnb_win_t* g, void* ws, int math,
                         dnb_stream_t stream);
 
+/* ---- fused block: Conv2D(C=1, 3x3, stride 1, "none") -> MaxPool2D(3x3, stride 2, "none") -> LeakyRelu/Relu ------
+ * (convolution.py:193-273 + pooling.py:43-99 + activations.py:17-22 in one pass: the F-channel convolution output and
+ * its gradient never reach HBM).  `idx_gate` holds one byte per pooled element: bits 0-3 = MaxPool2D.output_idxs
+ * (row-major offset of the first maximum in the window), bit 4 = the activation's gate (pool output > 0).
+ * _supported: 1 when the two geometries are eligible.  _fwd writes act_out = LeakyRelu(pool(conv(x))) and idx_gate.
+ * _bwd (PER_SAMPLE pool routing): gw += inv_m * sum, gb += inv_m * sum of the conv gradients, computed straight from the
+ * activation's incoming delta (act_delta); no regulariser term.  dnb_idx_gate_unpack recovers the int32 argmax tensor. */
+int dnb_conv_pool_act_supported(const dnb_win_t* conv, const dnb_win_t* pool);
+int dnb_conv_pool_act_fwd(const float* x, const float* w, const float* b, float* act_out, uint8_t* idx_gate,
+                          const dnb_win_t* conv, const dnb_win_t* pool, float alpha, dnb_stream_t stream);
+int dnb_conv_pool_act_bwd(const float* x, const float* act_delta, const uint8_t* idx_gate, float* gw, float* gb,
+                          const dnb_win_t* conv, const dnb_win_t* pool, float alpha, float inv_m, dnb_stream_t stream);
+int dnb_idx_gate_unpack(const uint8_t* idx_gate, int32_t* idx, size_t n, dnb_stream_t stream);
+/* the inverse for a caller that ASSIGNS MaxPool2D.output_idxs (pooling.py:74-76 stores it as a plain attribute): the
+ * argmax nibble of every byte is replaced, the gate bit kept */
+int dnb_idx_gate_set(const int32_t* idx, uint8_t* idx_gate, size_t n, dnb_stream_t stream);
+
 /* ---- DepthwiseConv2D (layers/convolution.py:323-388); w is [C,1,kh,kw] ------- */
 int dnb_dwconv2d_fwd(const float* x, const float* w, const float* b, float* y,
                      const dnb_win_t* g, dnb_stream_t stream);
