@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace dnb {
 
@@ -62,7 +63,7 @@ struct CpaFwd {
 //   fast path (NANSAFE = false): value = FMNMX3.NAN of the three conv outputs of the row, position by equality (first
 //   match = first maximum); returns true when a NaN reached any maximum, and the caller repeats the column with the
 //   NaN-exact comparisons of np.argmax (first NaN wins and sticks).  Never taken on finite data.
-template <int OH, int OW, int W, bool NANSAFE>
+template <int OH, int OW, int W, bool NANSAFE, bool PACKED = true>
 __device__ __forceinline__ bool cpa_walk(const float* __restrict__ img, const float2 (&w2)[3][3], float2 bias2, float alpha,
                                          uint32_t sa, uint32_t si) {
     constexpr int OP = OH * OW, R = 2 * OH + 1;       // conv rows the pool reads: 0 .. 2*OH
@@ -89,7 +90,8 @@ __device__ __forceinline__ bool cpa_walk(const float* __restrict__ img, const fl
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const float xv = X[(y + i) % 3][j + jj];
-                    acc[j] = __ffma2_rn(make_float2(xv, xv), w2[i][jj], acc[j]);
+                    if (PACKED) acc[j] = __ffma2_rn(make_float2(xv, xv), w2[i][jj], acc[j]);
+                    else { acc[j].x = fmaf(xv, w2[i][jj].x, acc[j].x); acc[j].y = fmaf(xv, w2[i][jj].y, acc[j].y); }
                 }
         const int dy = (y & 1) ? 1 : 0;               // window row of a window that STARTED at the last even row
 #pragma unroll
@@ -129,7 +131,7 @@ __device__ __forceinline__ bool cpa_walk(const float* __restrict__ img, const fl
 }
 
 // smem: [ngroups] x { full[2] mbarriers (padded to 128 B) | img[2][H*W] | act[2][F*OP] | idx[2][F*OP bytes] }
-template <int OH, int OW, int W>
+template <int OH, int OW, int W, bool PACKED = true>
 __global__ void __launch_bounds__(384, 2) cpa_fwd_kernel(CpaFwd a) {
     extern __shared__ __align__(128) uint8_t smraw[];
     constexpr int OP = OH * OW;
@@ -178,8 +180,8 @@ __global__ void __launch_bounds__(384, 2) cpa_fwd_kernel(CpaFwd a) {
         if (active) {
             const float* img = simg + (size_t)s * HW + 2 * ox;
             const uint32_t sa = sa_item + (uint32_t)(s * act_b), si = si_item + (uint32_t)(s * idx_b);
-            if (cpa_walk<OH, OW, W, false>(img, w2, bias2, a.alpha, sa, si))
-                cpa_walk<OH, OW, W, true>(img, w2, bias2, a.alpha, sa, si);
+            if (cpa_walk<OH, OW, W, false, PACKED>(img, w2, bias2, a.alpha, sa, si))
+                cpa_walk<OH, OW, W, true, PACKED>(img, w2, bias2, a.alpha, sa, si);
         }
         tc::fence_proxy_async_smem();
         group_bar(bar_id, a.gt);                        // A: staging[s] complete, image stage s no longer read
@@ -318,6 +320,11 @@ int delta_pitch(int OP) {           // smallest pitch >= OP that is a multiple o
 // forward kernels are instantiated per geometry (pooled plane, image width): MNIST (28x28 -> 12x12) and its 14x14 test variant
 template <int OH, int OW, int W>
 int launch_fwd(const CpaFwd& a, int grid, size_t smem, cudaStream_t st) {
+    if (getenv("DNB_CPA_SCALAR")) {      // experiment: scalar FFMA instead of packed FFMA2
+        cudaFuncSetAttribute(cpa_fwd_kernel<OH, OW, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cpa_fwd_kernel<OH, OW, W, false><<<grid, a.gt * a.ngroups, smem, st>>>(a);
+        return 0;
+    }
     cudaFuncSetAttribute(cpa_fwd_kernel<OH, OW, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cpa_fwd_kernel<OH, OW, W><<<grid, a.gt * a.ngroups, smem, st>>>(a);
     return 0;
