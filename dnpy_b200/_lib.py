@@ -76,9 +76,15 @@ SIGNATURES = {
     "dnb_merge_n": (_i, [C.POINTER(_p), _i, _p, _z, _i, _f, _p]),
     "dnb_batchnorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _z, _f, _f, _i, _p]),
     "dnb_batchnorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _z, _p]),
+    "dnb_batchnorm_stats": (_i, [_p, _p, _p, _i, _z, _p]),
+    "dnb_batchnorm_fwd_synced": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _z, _f, _f, _p]),
+    "dnb_batchnorm_bwd_sums": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _z, _p]),
+    "dnb_batchnorm_bwd_synced": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _z, _p]),
     "dnb_embedding_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "dnb_embedding_bwd_ws_bytes": (_z, [_i, _i, _i]),
     "dnb_embedding_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p, _p]),
+    "dnb_embedding_bwd_prepare": (_i, [_p, _p, _i, _i, _i, _i, _f, _i, _p, _p]),
+    "dnb_embedding_bwd_apply": (_i, [_p, _p, _i, _i, _i, _f, _p]),
     "dnb_rnn_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "dnb_rnn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "dnb_loss_ws_bytes": (_z, [_i]),

@@ -32,20 +32,21 @@ __global__ void __launch_bounds__(256) embedding_mean_kernel(const float* __rest
     for (int b = 0; b < B; ++b) acc += dy[(long)b * LD + i];
     meand[i] = acc * inv_m;
 }
+// last[v] = the largest GLOBAL flat position (pos0 + i) of token v: NumPy's fancy-index "+=" keeps the last write (Q15)
 __global__ void __launch_bounds__(256) embedding_last_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ last,
-                                                             long n_tok, int V) {
+                                                             long n_tok, int V, int pos0) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_tok; i += (long)gridDim.x * blockDim.x) {
         int v = idx[i];
-        if (v >= 0 && v < V) atomicMax(last + v, (int)i);
+        if (v >= 0 && v < V) atomicMax(last + v, pos0 + (int)i);
     }
 }
 __global__ void __launch_bounds__(256) embedding_apply_kernel(const int32_t* __restrict__ last, const float* __restrict__ meand,
-                                                              float* __restrict__ gw, int V, int L, int D) {
+                                                              float* __restrict__ gw, int V, int L, int D, float scale) {
     long total = (long)V * D;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         int v = (int)(i / D), d = (int)(i % D);
         int pos = last[v];
-        if (pos >= 0) gw[i] += meand[(long)(pos % L) * D + d];
+        if (pos >= 0) gw[i] += scale * meand[(long)(pos % L) * D + d];
     }
 }
 
@@ -377,24 +378,50 @@ int dnb_embedding_fwd(const int32_t* idx, const float* w, float* y, int B, int L
 
 size_t dnb_embedding_bwd_ws_bytes(int L, int V, int D) { return ((size_t)V + (size_t)L * D) * sizeof(float); }
 
-int dnb_embedding_bwd(const int32_t* idx, const float* dy, float* gw, int B, int L, int V, int D,
-                      float inv_m, void* ws, dnb_stream_t stream) {
+// Two halves around the data-parallel exchange: prepare leaves the local part of the batch mean (inv_m = 1 over the
+// GLOBAL batch) in ws[V ..] and the last global position of every vocabulary row in ws[0 .. V); between the halves the ranks
+// all-reduce the means (SUM) and the positions (MAX); apply adds `scale` x the mean of the winning position (scale = 1/world:
+// every rank then holds 1/world of the exact gradient and the arena all-reduce restores it).
+int dnb_embedding_bwd_prepare(const int32_t* idx, const float* dy, int B, int L, int V, int D, float inv_m, int pos0,
+                              void* ws, dnb_stream_t stream) {
     DNB_CHECK_ARG(B >= 0 && L > 0 && V > 0 && D > 0, "embedding_bwd: bad shape");
-    if (B == 0) return DNB_OK;
-    DNB_CHECK_ARG(idx && dy && gw && ws, "embedding_bwd: null pointer");
+    DNB_CHECK_ARG(ws, "embedding_bwd: null workspace");
     cudaStream_t st = S(stream);
     int32_t* last = static_cast<int32_t*>(ws);
     float* meand = reinterpret_cast<float*>(last + V);
     cudaError_t e = cudaMemsetAsync(last, 0xff, (size_t)V * sizeof(int32_t), st);
     if (e != cudaSuccess) return set_err(DNB_ERR_CUDA, "embedding_bwd: %s", cudaGetErrorString(e));
     long LD = (long)L * D, n_tok = (long)B * L;
+    if (B == 0) {
+        e = cudaMemsetAsync(meand, 0, (size_t)LD * sizeof(float), st);
+        return e == cudaSuccess ? DNB_OK : set_err(DNB_ERR_CUDA, "embedding_bwd: %s", cudaGetErrorString(e));
+    }
+    DNB_CHECK_ARG(idx && dy, "embedding_bwd: null pointer");
     embedding_mean_kernel<<<(unsigned)((LD + 255) / 256), 256, 0, st>>>(dy, meand, B, LD, inv_m);
     DNB_LAUNCH_CHECK("embedding_bwd_mean");
-    embedding_last_kernel<<<ew_grid((size_t)n_tok, 256), 256, 0, st>>>(idx, last, n_tok, V);
+    embedding_last_kernel<<<ew_grid((size_t)n_tok, 256), 256, 0, st>>>(idx, last, n_tok, V, pos0);
     DNB_LAUNCH_CHECK("embedding_bwd_last");
-    embedding_apply_kernel<<<ew_grid((size_t)V * D, 256), 256, 0, st>>>(last, meand, gw, V, L, D);
+    return DNB_OK;
+}
+
+int dnb_embedding_bwd_apply(const void* ws, float* gw, int L, int V, int D, float scale, dnb_stream_t stream) {
+    DNB_CHECK_ARG(L > 0 && V > 0 && D > 0, "embedding_bwd: bad shape");
+    DNB_CHECK_ARG(ws && gw, "embedding_bwd: null pointer");
+    const int32_t* last = static_cast<const int32_t*>(ws);
+    const float* meand = reinterpret_cast<const float*>(last + V);
+    embedding_apply_kernel<<<ew_grid((size_t)V * D, 256), 256, 0, S(stream)>>>(last, meand, gw, V, L, D, scale);
     DNB_LAUNCH_CHECK("embedding_bwd_apply");
     return DNB_OK;
+}
+
+int dnb_embedding_bwd(const int32_t* idx, const float* dy, float* gw, int B, int L, int V, int D,
+                      float inv_m, void* ws, dnb_stream_t stream) {
+    DNB_CHECK_ARG(B >= 0 && L > 0 && V > 0 && D > 0, "embedding_bwd: bad shape");
+    if (B == 0) return DNB_OK;
+    DNB_CHECK_ARG(idx && dy && gw && ws, "embedding_bwd: null pointer");
+    int rc = dnb_embedding_bwd_prepare(idx, dy, B, L, V, D, inv_m, 0, ws, stream);
+    if (rc) return rc;
+    return dnb_embedding_bwd_apply(ws, gw, L, V, D, 1.0f, stream);
 }
 
 int dnb_rnn_fwd(const float* x, const float* waa, const float* wax, const float* ba,

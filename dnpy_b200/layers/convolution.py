@@ -94,7 +94,7 @@ class Conv2D(Conv):
     def _cpa_usable(self):
         # the fused backward implements the PER_SAMPLE pool routing; LITERAL (pooling.py:95 as written) keeps the
         # layer-by-layer kernels
-        return (self._cpa is not None and not self.debug and config.maxpool_route == _lib.ROUTE_PER_SAMPLE
+        return (self._cpa is not None and not self.debug and config.route == _lib.ROUTE_PER_SAMPLE
                 and self.kernel_regularizer is None and self.bias_regularizer is None)
 
     def _forward_fused(self, x):

@@ -54,9 +54,24 @@ class Embedding(Layer):
         b, l = idx.shape
         v, d = self.params['w1'].shape
         from .. import _lib
-        ws = self._raw('ws', _lib.load().dnb_embedding_bwd_ws_bytes(l, v, d))
-        self._call("dnb_embedding_bwd", idx.ptr(), dy.ptr(), self.grads['w1'].ptr(), b, l, v, d,
-                   self._inv_m(b), ws)
+        nbytes = _lib.load().dnb_embedding_bwd_ws_bytes(l, v, d)
+        if config.world > 1:
+            # exact under data parallelism: the batch mean over ALL ranks' rows (SUM of the local parts) and the
+            # last GLOBAL position of every vocabulary row (MAX); every rank then adds 1/world of the exact gradient, which
+            # the gradient all-reduce sums back
+            from .. import parallel
+            import torch
+            wsb = self._buf('ws_dp', ((nbytes + 3) // 4,))
+            raw = wsb.dev()
+            self._call("dnb_embedding_bwd_prepare", idx.ptr(), dy.ptr(), b, l, v, d, self._inv_m(b),
+                       config.rank * b * l, wsb.ptr())
+            parallel.allreduce(raw[:v].view(torch.int32), "max")
+            parallel.allreduce(raw[v:v + l * d], "sum")
+            self._call("dnb_embedding_bwd_apply", wsb.ptr(), self.grads['w1'].ptr(), l, v, d, config.inv_world)
+        else:
+            ws = self._raw('ws', nbytes)
+            self._call("dnb_embedding_bwd", idx.ptr(), dy.ptr(), self.grads['w1'].ptr(), b, l, v, d,
+                       self._inv_m(b), ws)
         self.grads['w1'].written()
 
 

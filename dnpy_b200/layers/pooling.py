@@ -80,7 +80,7 @@ class MaxPool2D(Pool):
         return dx
 
     def backward(self):
-        route = config.maxpool_route
+        route = config.route
         block = getattr(self, "_cpa_block", None)
         if block is not None and block._cpa_live is not None:
             # fused block: the conv layer computes its gradients from the activation's delta; this layer's 4.7x larger

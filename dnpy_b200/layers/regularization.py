@@ -155,9 +155,23 @@ class BatchNorm(Layer):
         if self.training:
             self.fw_steps += 1
         mm, mv = self._stat('moving_mu', n_feat), self._stat('moving_var', n_feat)
-        self._call("dnb_batchnorm_fwd", x.ptr(), self.params['gamma'].ptr(), self.params['beta'].ptr(),
-                   mm.ptr(), mv.ptr(), mu.ptr(), std.ptr(), out.ptr(), b, n_feat,
-                   float(self.momentum), float(self.epsilon), int(bool(self.training)))
+        from ..runtime import config
+        if self.training and config.world > 1:
+            # the statistics of the GLOBAL minibatch (regularization.py:98-99 over all ranks' rows): every rank's
+            # (mean, M2) lands in its row of `slots`, a SUM leaves all rows everywhere, the kernel merges them
+            from .. import parallel
+            slots = self._buf('stat_slots', (config.world, 2, n_feat))
+            slots.dev().zero_()
+            mine = slots.dev()[config.rank]
+            self._call("dnb_batchnorm_stats", x.ptr(), mine[0].data_ptr(), mine[1].data_ptr(), b, n_feat)
+            parallel.gather_slots(slots.dev())
+            self._call("dnb_batchnorm_fwd_synced", x.ptr(), self.params['gamma'].ptr(), self.params['beta'].ptr(),
+                       mm.ptr(), mv.ptr(), slots.ptr(), config.world, mu.ptr(), std.ptr(), out.ptr(), b, n_feat,
+                       float(self.momentum), float(self.epsilon))
+        else:
+            self._call("dnb_batchnorm_fwd", x.ptr(), self.params['gamma'].ptr(), self.params['beta'].ptr(),
+                       mm.ptr(), mv.ptr(), mu.ptr(), std.ptr(), out.ptr(), b, n_feat,
+                       float(self.momentum), float(self.epsilon), int(bool(self.training)))
         if self.training:
             mm.written()
             mv.written()
@@ -169,9 +183,19 @@ class BatchNorm(Layer):
         b = x.shape[0]
         n_feat = x.size // max(1, b)
         dx = self._buf('dx', x.shape)
-        self._call("dnb_batchnorm_bwd", x.ptr(), self.params['gamma'].ptr(), self.cache['mu'].ptr(),
-                   self.cache['inv_var'].ptr(), dy.ptr(), dx.ptr(), self.grads['gamma'].ptr(),
-                   self.grads['beta'].ptr(), b, n_feat)
+        from ..runtime import config
+        if config.world > 1:
+            from .. import parallel
+            sums = self._buf('bwd_sums', (2, n_feat))
+            self._call("dnb_batchnorm_bwd_sums", x.ptr(), self.cache['mu'].ptr(), self.cache['inv_var'].ptr(), dy.ptr(),
+                       sums.ptr(), self.grads['gamma'].ptr(), self.grads['beta'].ptr(), b, n_feat)
+            parallel.allreduce(sums.dev(), "sum")
+            self._call("dnb_batchnorm_bwd_synced", x.ptr(), self.params['gamma'].ptr(), self.cache['mu'].ptr(),
+                       self.cache['inv_var'].ptr(), dy.ptr(), sums.ptr(), dx.ptr(), b, b * config.world, n_feat)
+        else:
+            self._call("dnb_batchnorm_bwd", x.ptr(), self.params['gamma'].ptr(), self.cache['mu'].ptr(),
+                       self.cache['inv_var'].ptr(), dy.ptr(), dx.ptr(), self.grads['gamma'].ptr(),
+                       self.grads['beta'].ptr(), b, n_feat)
         self.grads['gamma'].written()
         self.grads['beta'].written()
         self.parents[0].delta = dx

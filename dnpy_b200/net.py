@@ -244,7 +244,7 @@ class Net:
                 st = getattr(opt, name)
                 if k in st:
                     st[k].bind(arena[o:o + n].view(*shape))
-        self._arena = dict(P=P, G=G, states=states, total=total, uniform=uniform,
+        self._arena = dict(P=P, G=G, states=states, total=total, uniform=uniform, offsets=offs,
                            keys=[(id(l.params[k]), id(l.grads[k])) for l, k in slots], slots=slots)
         self._graphs = {}
         return self._arena
@@ -342,13 +342,20 @@ class Net:
                 l.print_stats()
 
     def backward(self):
+        buckets = None
+        if config.world > 1:
+            from . import parallel
+            buckets = parallel.GradBuckets(self)
         for l in self.bts_layers:
             l.backward()
             if self.debug:
                 l.print_stats()
-        if config.world > 1:
-            from . import parallel
-            parallel.allreduce_grads(self)
+            if buckets is not None:
+                buckets.layer_done(l)          # this layer's gradients are final: start their all-reduce now
+        if buckets is not None:
+            buckets.finish()
+            for l, k in self._arena["slots"]:
+                l.grads[k].written()
 
     @staticmethod
     def _opt_hyper(o):
@@ -459,7 +466,7 @@ class Net:
         if not (self.use_graph and not self.debug and self._graph_ok_for_world()):
             return self._step_body(xs, ys)
         key = (tuple(x.ptr() for x in xs), tuple(y.ptr() for y in ys), tuple(x.shape for x in xs), self.mode,
-               config.math, config.maxpool_route, self._uniform_hyper(), self._layer_generation())
+               config.math, config.route, self._uniform_hyper(), self._layer_generation())
         ent = self._graphs.get(key)
         if ent is None:
             ent = self._graphs[key] = dict(calls=0, graph=None, outs=None)

@@ -7,11 +7,17 @@ The reference has no distributed code; this is the natural sharding of ``Net.fit
   * BatchNorm and SimpleRNN gradients are batch SUMS -> plain sum;
   * regulariser terms are batch independent -> each rank adds 1/world of them;
   * the loss scalar is the mean of per-rank means (equal shards).
-Not exchanged (documented in DESIGN.md): BatchNorm batch statistics, Embedding's last-write-wins
-scatter and MaxPool's literal routing are per-rank under data parallelism.
+Exchanged besides the gradients, so that N ranks compute exactly what one process computes on the global
+minibatch: BatchNorm's batch statistics (forward: every rank's (mean, M2); backward: the two
+column sums), Embedding's batch-mean delta (SUM) and last-position table (MAX); Dropout / GaussianNoise draw
+the global block from the shared NumPy stream and keep their rows.  MaxPool2D's LITERAL routing (every delta
+lands in global sample 0, pooling.py:95) does not shard: with world > 1 the PER_SAMPLE routing is used.
+The gradient all-reduce is issued in buckets from inside backward (reverse layer order = arena order), so
+all but the last bucket overlap the remaining backward kernels.
 """
 import os
 
+from . import _lib
 from .runtime import config
 
 
@@ -28,6 +34,10 @@ def init(backend=None):
         dist.init_process_group(backend=backend)
     config.world = dist.get_world_size()
     config.rank = dist.get_rank()
+    if config.world > 1 and config.maxpool_route == _lib.ROUTE_LITERAL:
+        # pooling.py:95 routes EVERY sample's delta into sample 0 of the (global) minibatch: that does not shard
+        if config.rank == 0:
+            print("[INFO] data parallel: MaxPool2D uses the per-sample routing (the literal routing does not shard)")
     return config.rank, config.world
 
 
@@ -60,6 +70,21 @@ def allreduce_flat(tensor):
     return tensor
 
 
+def allreduce(tensor, op="sum", async_op=False):
+    """In-place all-reduce of a device tensor ("sum" or "max"); returns the work handle when async."""
+    import torch.distributed as dist
+    if config.world == 1:
+        return None
+    return dist.all_reduce(tensor, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX, async_op=async_op)
+
+
+def gather_slots(slots):
+    """All-gather through a SUM: ``slots`` is a zeroed [world, ...] device tensor in which this rank filled row
+    ``config.rank``; adding the ranks' tensors leaves every row in place on every rank (x + 0 is exact), on any
+    backend and inside a captured step graph."""
+    return allreduce(slots, "sum")
+
+
 def mean_over_ranks(values):
     """Average a short list of Python floats over the ranks (equal shards => global mean)."""
     import torch
@@ -73,8 +98,45 @@ def mean_over_ranks(values):
 
 
 def allreduce_grads(net):
-    """The single exchange step of the data-parallel path: between backward and apply_grads."""
+    """The whole gradient arena in one all-reduce (the un-bucketed form; Net.backward issues buckets instead)."""
     a = net._bind_arenas()
     allreduce_flat(a["G"])
     for l, k in a["slots"]:
         l.grads[k].written()
+
+
+class GradBuckets:
+    """Bucketed, overlapped gradient exchange.  The arena is laid out in backward order (Net._trainable walks
+    bts_layers), so the gradients of the layers that have ALREADY run backward form a growing prefix: after a layer
+    that owns parameters, the finished, not yet sent range [sent, end) goes out as one asynchronous all-reduce
+    (it runs on the process group's communication stream, after the kernels queued so far, concurrently with the
+    backward kernels that follow).  ``finish`` sends the remainder and makes the compute stream wait for all of
+    them before the optimizer.  Buckets smaller than ``min_bytes`` are merged into the next one, except the last."""
+
+    def __init__(self, net, min_bytes=16 << 10):
+        a = net._bind_arenas()
+        self.G = a["G"]
+        self.end_of = {}
+        pos = 0
+        for (l, k), nxt in zip(a["slots"], a["offsets"][1:] + [a["total"]]):
+            self.end_of[id(l)] = nxt          # the arena position just past this layer's last slot
+        self.total = a["total"]
+        self.min_floats = max(1, min_bytes // 4)
+        self.sent = 0
+        self.works = []
+
+    def layer_done(self, layer):
+        end = self.end_of.get(id(layer))
+        if end is None or end - self.sent < self.min_floats:
+            return
+        self.works.append(allreduce(self.G[self.sent:end], "sum", async_op=True))
+        self.sent = end
+
+    def finish(self):
+        if self.sent < self.total:
+            self.works.append(allreduce(self.G[self.sent:self.total], "sum", async_op=True))
+            self.sent = self.total
+        for w in self.works:
+            if w is not None:
+                w.wait()
+        self.works = []

@@ -30,6 +30,12 @@ class _Config:
         self.rank = 0
 
     @property
+    def route(self):
+        """The MaxPool2D backward routing in effect: the literal routing (every delta into sample 0 of the minibatch,
+        pooling.py:95) does not shard, so data-parallel runs always use the per-sample routing."""
+        return self.maxpool_route if self.world == 1 else _lib.ROUTE_PER_SAMPLE
+
+    @property
     def inv_world(self):
         return 1.0 / float(self.world)
 

@@ -190,8 +190,7 @@ int dnb_add_n(const float* const* xs, int n_in, float* y, size_t n, dnb_stream_t
 int dnb_merge_n(const float* const* xs, int n_in, float* y, size_t n, int op, float post_scale, dnb_stream_t stream);
 /* BatchNorm over axis 0 of x[B, n_feat] (regularization.py:94-136).  training: computes
  * mu/var (biased) into save_mu/save_std (std = sqrt(var+eps)) and updates moving_* in place
- * with `momentum`; test: uses moving_*.  stat_sync, when non-NULL, is unused here (reserved
- * for the host-driven cross-GPU statistics exchange). */
+ * with `momentum`; test: uses moving_*.  (Sharded batches: see dnb_batchnorm_stats / _fwd_synced below.) */
 int dnb_batchnorm_fwd(const float* x, const float* gamma, const float* beta,
                       float* moving_mu, float* moving_var, float* save_mu, float* save_std,
                       float* y, int B, size_t n_feat, float momentum, float eps, int training,
@@ -201,6 +200,22 @@ int dnb_batchnorm_fwd(const float* x, const float* gamma, const float* beta,
 int dnb_batchnorm_bwd(const float* x, const float* gamma, const float* save_mu, const float* save_std,
                       const float* dy, float* dx, float* ggamma, float* gbeta,
                       int B, size_t n_feat, dnb_stream_t stream);
+/* The same layer with the batch sharded over ranks (one process per GPU): the rank-local halves around the two exchanges
+ * that make N ranks compute the single-process statistics (regularization.py:98-99 and 148-152 over the GLOBAL batch).
+ *   forward : dnb_batchnorm_stats -> every rank's (mean, M2) gathered into stats_all[world][2][n_feat] ->
+ *             dnb_batchnorm_fwd_synced (Chan merge of equal-count partitions, normalise, moving statistics)
+ *   backward: dnb_batchnorm_bwd_sums (local sum_b dy, sum_b dy*xn into sums[2][n_feat]; ggamma / gbeta are batch SUMS and
+ *             are accumulated here, the gradient all-reduce adds the ranks' parts) -> all-reduce(sums) ->
+ *             dnb_batchnorm_bwd_synced (dx with m = B_global) */
+int dnb_batchnorm_stats(const float* x, float* mean, float* m2, int B, size_t n_feat, dnb_stream_t stream);
+int dnb_batchnorm_fwd_synced(const float* x, const float* gamma, const float* beta, float* moving_mu, float* moving_var,
+                             const float* stats_all, int world, float* save_mu, float* save_std, float* y,
+                             int B, size_t n_feat, float momentum, float eps, dnb_stream_t stream);
+int dnb_batchnorm_bwd_sums(const float* x, const float* save_mu, const float* save_std, const float* dy, float* sums,
+                           float* ggamma, float* gbeta, int B, size_t n_feat, dnb_stream_t stream);
+int dnb_batchnorm_bwd_synced(const float* x, const float* gamma, const float* save_mu, const float* save_std,
+                             const float* dy, const float* sums, float* dx, int B, int B_global, size_t n_feat,
+                             dnb_stream_t stream);
 
 /* ---- Embedding (layers/core.py:54-65) --------------------------------------- */
 int dnb_embedding_fwd(const int32_t* idx, const float* w, float* y, int B, int L, int V, int D, dnb_stream_t stream);
@@ -209,6 +224,13 @@ int dnb_embedding_fwd(const int32_t* idx, const float* w, float* y, int B, int L
 size_t dnb_embedding_bwd_ws_bytes(int L, int V, int D);
 int dnb_embedding_bwd(const int32_t* idx, const float* dy, float* gw, int B, int L, int V, int D,
                       float inv_m, void* ws, dnb_stream_t stream);
+/* The two halves of dnb_embedding_bwd, for a sharded batch: prepare leaves last[V] (int32: largest GLOBAL flat position
+ * pos0 + b*L + l of every vocabulary row, -1 if unused) followed by the local part of mean_b(dy) (inv_m = 1/B_global) in
+ * ws; the ranks all-reduce the positions (MAX) and the means (SUM); apply adds scale * mean[l*] to gw (scale = 1/world:
+ * the gradient all-reduce then restores the exact single-process value). */
+int dnb_embedding_bwd_prepare(const int32_t* idx, const float* dy, int B, int L, int V, int D, float inv_m, int pos0,
+                              void* ws, dnb_stream_t stream);
+int dnb_embedding_bwd_apply(const void* ws, float* gw, int L, int V, int D, float scale, dnb_stream_t stream);
 
 /* ---- SimpleRNN (layers/recurrent.py:12-23, 153-266) ------------------------- */
 /* states[B,T,H]: h_t = tanh(h_{t-1} waa^T + x_t wax^T + ba), h_0 = 0; y[B,H] = states[:, T-1] */

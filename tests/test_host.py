@@ -152,6 +152,73 @@ def test_two_rank_gloo_gradient_exchange(tmp_path):
     assert r.stdout.count("ok") == 2
 
 
+@pytest.mark.timeout(180)
+def test_two_rank_gloo_exact_exchanges(tmp_path):
+    """world_size-2 CPU run of the host logic that makes data parallelism EXACT: bucketed gradient all-reduce in
+    arena order, BatchNorm (mean, M2) slots merged with Chan's formula, Embedding mean (SUM) / last position (MAX), and the
+    global Dropout draw split into row blocks."""
+    script = tmp_path / "dp2.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys, types
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch
+        from dnpy_b200 import parallel
+        from dnpy_b200.runtime import config
+        from dnpy_b200.layers.regularization import _global_draw
+        rank, world = parallel.init(backend="gloo")
+        rs = np.random.RandomState(0)
+        # 1. gradient buckets: three 'layers' own arena ranges [0,40) [40,48) [48,64); min bucket 32 floats
+        G = torch.full((64,), float(rank + 1))
+        layers = [object(), object(), object()]
+        slots = [(layers[0], 'w'), (layers[0], 'b'), (layers[1], 'w'), (layers[2], 'w')]
+        arena = dict(G=G, slots=slots, offsets=[0, 32, 40, 48], total=64)
+        fake = types.SimpleNamespace(_bind_arenas=lambda: arena)
+        bk = parallel.GradBuckets(fake, min_bytes=128)
+        bk.layer_done(layers[0]); assert bk.sent == 40          # 40 floats >= 32: sent
+        bk.layer_done(layers[1]); assert bk.sent == 40          # 8 floats: merged into the next bucket
+        bk.layer_done(layers[2]); assert bk.sent == 40          # 24 floats still under the minimum
+        bk.finish(); assert bk.sent == 64
+        assert torch.all(G == 3.0), G
+        # 2. BatchNorm statistics: slots + Chan merge == statistics of the global batch
+        x = rs.randn(12, 5) * 3 + 1
+        xs = parallel.shard_rows(x)
+        st = torch.zeros(world, 2, 5, dtype=torch.float64)
+        st[rank, 0] = torch.from_numpy(xs.mean(0)); st[rank, 1] = torch.from_numpy(((xs - xs.mean(0)) ** 2).sum(0))
+        parallel.gather_slots(st)
+        n, mu, M2 = len(xs), st[0, 0].numpy().copy(), st[0, 1].numpy().copy()
+        for r in range(1, world):
+            d = st[r, 0].numpy() - mu; nt = n + len(xs)
+            mu = mu + d * len(xs) / nt; M2 = M2 + st[r, 1].numpy() + d * d * n * len(xs) / nt; n = nt
+        assert np.allclose(mu, x.mean(0)) and np.allclose(M2 / n, x.var(0))
+        # 3. Embedding: last GLOBAL position per vocabulary row (MAX), batch mean of the delta (SUM of local parts)
+        idx = rs.randint(0, 7, (4, 3)); d = rs.randn(4, 3, 2)
+        lo, hi = parallel.shard_bounds(4)
+        last = torch.full((7,), -1, dtype=torch.int32)
+        for b in range(lo, hi):
+            for l in range(3):
+                last[idx[b, l]] = max(int(last[idx[b, l]]), b * 3 + l)
+        mean = torch.from_numpy(d[lo:hi].sum(0) / 4.0)
+        parallel.allreduce(last, "max"); parallel.allreduce(mean, "sum")
+        want_last = np.full(7, -1)
+        for i, v in enumerate(idx.ravel()):
+            want_last[v] = i
+        assert np.array_equal(last.numpy(), want_last) and np.allclose(mean.numpy(), d.mean(0))
+        # 4. the global Dropout draw: this rank's row block of the single-process draw
+        np.random.seed(5); full = np.random.random((6, 4))
+        np.random.seed(5); mine = _global_draw(np.random.random, (3, 4))
+        assert np.array_equal(mine, full[rank * 3:(rank + 1) * 3])
+        assert config.route == 1                               # the literal pool routing does not shard: per-sample in effect
+        parallel.shutdown()
+        print("rank", rank, "ok")
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29534")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29534", str(script)],
+                       capture_output=True, text=True, env=env, timeout=170)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
+
+
 def test_evaluate_chunking_policy_and_resident_slices(ns, monkeypatch):
     """Host logic of SURVEY 8f-1/2 that needs no device: which (loss, metric) sets may be evaluated in chunks, the
     resident-slice view protocol, and that without a device the datasets are left on the host."""
