@@ -306,6 +306,80 @@ __global__ void __launch_bounds__(CPA_MAX_THREADS + 32) cpa_bwd_kernel(CpaBwd a)
     }
 }
 
+// ---- LITERAL pool routing (dnpy/layers/pooling.py:95 as written) ------------------------------------------
+// `delta_view.flat[idxs[:, z, y, x]] += delta[:, z, y, x]` indexes the (B, 3, 3) window view with offsets in [0, 9): every
+// sample's delta lands in SAMPLE 0's window, and NumPy's buffered fancy-index "+=" keeps, per offset, only the LAST sample
+// that chose it.  So only image 0 carries a conv gradient, built from <= 9 (sample, delta) pairs per pooled position:
+//   last[f, pos, off] = max { b : argmax[b, f, pos] == off }                       (cpa_last_kernel)
+//   gW[f, i, j] += inv_m * sum_{pos, off} gate * delta[last, f, pos] * x0[2oy + off/3 + i, 2ox + off%3 + j]   (cpa_bwd_literal_kernel)
+constexpr int CPL_CHUNK = 256;      // samples per CTA row of the scan
+
+// grid (ceil(F*OP / 256), ceil(B / CPL_CHUNK)): a thread owns one pooled position of one filter and scans its chunk of
+// samples from the newest down (coalesced: consecutive threads read consecutive bytes of a sample), stopping when all nine
+// offsets have been seen; one atomicMax per offset found.
+__global__ void __launch_bounds__(256) cpa_last_kernel(const uint8_t* __restrict__ idxg, int32_t* __restrict__ last,
+                                                       int B, int FOP) {
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= FOP) return;
+    const int b_hi = min(B, (int)(blockIdx.y + 1) * CPL_CHUNK) - 1, b_lo = blockIdx.y * CPL_CHUNK;
+    unsigned seen = 0;
+    int found[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) found[k] = -1;
+    for (int b = b_hi; b >= b_lo && seen != 0x1ffu; --b) {
+        const unsigned off = idxg[(size_t)b * FOP + e] & 15u;
+        if (!(seen >> off & 1u)) {
+            seen |= 1u << off;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) if (k == (int)off) found[k] = b;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+        if (found[k] >= 0) atomicMax(last + (size_t)e * 9 + k, found[k]);
+}
+
+// grid F, block >= OP threads: CTA f reduces its filter's nine taps (+ bias) over the pooled positions; no atomics.
+__global__ void __launch_bounds__(256) cpa_bwd_literal_kernel(const float* __restrict__ x0, const float* __restrict__ dact,
+                                                              const uint8_t* __restrict__ idxg, const int32_t* __restrict__ last,
+                                                              float* __restrict__ gw, float* __restrict__ gb,
+                                                              int F, int OH, int OW, int W, float alpha, float inv_m) {
+    __shared__ float red[10][8];
+    const int f = blockIdx.x, OP = OH * OW, FOP = F * OP;
+    float g[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) g[k] = 0.f;
+    for (int pos = threadIdx.x; pos < OP; pos += blockDim.x) {
+        const int oy = pos / OW, ox = pos - oy * OW;
+        const int e = f * OP + pos;
+#pragma unroll
+        for (int off = 0; off < 9; ++off) {
+            const int b = last[(size_t)e * 9 + off];
+            if (b < 0) continue;
+            const float d = dact[(size_t)b * FOP + e];
+            const float dd = (idxg[(size_t)b * FOP + e] & 16u) ? d : alpha * d;       // the activation's backward (activations.py:21-22)
+            const float* xp = x0 + (2 * oy + off / 3) * W + 2 * ox + off % 3;
+            g[9] += dd;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) g[i * 3 + j] = fmaf(dd, xp[i * W + j], g[i * 3 + j]);
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        const float v = warp_sum(g[k]);
+        if (lane == 0) red[k][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        float v = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+        if (threadIdx.x < 9) gw[f * 9 + threadIdx.x] += v * inv_m; else gb[f] += v * inv_m;
+    }
+}
+
 __global__ void __launch_bounds__(256) idx_unpack_kernel(const uint8_t* __restrict__ in, int32_t* __restrict__ out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         out[i] = (int32_t)(in[i] & 15u);
@@ -400,6 +474,31 @@ int dnb_conv_pool_act_bwd(const float* x, const float* act_delta, const uint8_t*
     const int grid = (int)std::min<long>(conv->B, (long)kNumSMs * per_sm);
     cpa_bwd_kernel<<<grid, a.ncons + 32, smem, S(stream)>>>(a);
     DNB_LAUNCH_CHECK("conv_pool_act_bwd");
+    return DNB_OK;
+}
+
+size_t dnb_conv_pool_act_bwd_literal_ws_bytes(const dnb_win_t* conv, const dnb_win_t* pool) {
+    if (!conv || !pool) return 0;
+    return (size_t)conv->F * pool->OH * pool->OW * 9 * sizeof(int32_t);
+}
+
+int dnb_conv_pool_act_bwd_literal(const float* x, const float* act_delta, const uint8_t* idx_gate, float* gw, float* gb,
+                                  const dnb_win_t* conv, const dnb_win_t* pool, float alpha, float inv_m, void* ws,
+                                  dnb_stream_t stream) {
+    DNB_CHECK_ARG(geometry_ok(conv, pool), "conv_pool_act_bwd_literal: unsupported geometry");
+    if (conv->B == 0) return DNB_OK;
+    DNB_CHECK_ARG(x && act_delta && idx_gate && gw && gb && ws, "conv_pool_act_bwd_literal: null pointer");
+    cudaStream_t st = S(stream);
+    const int OP = pool->OH * pool->OW, FOP = conv->F * OP;
+    int32_t* last = static_cast<int32_t*>(ws);
+    cudaError_t e = cudaMemsetAsync(last, 0xff, (size_t)FOP * 9 * sizeof(int32_t), st);      // -1: offset never chosen
+    if (e != cudaSuccess) return set_err(DNB_ERR_CUDA, "conv_pool_act_bwd_literal: %s", cudaGetErrorString(e));
+    dim3 grid((FOP + 255) / 256, (conv->B + CPL_CHUNK - 1) / CPL_CHUNK);
+    cpa_last_kernel<<<grid, 256, 0, st>>>(idx_gate, last, conv->B, FOP);
+    DNB_LAUNCH_CHECK("conv_pool_act_bwd_last");
+    cpa_bwd_literal_kernel<<<conv->F, 256, 0, st>>>(x, act_delta, idx_gate, last, gw, gb, conv->F, pool->OH, pool->OW, conv->W,
+                                                    alpha, inv_m);
+    DNB_LAUNCH_CHECK("conv_pool_act_bwd_literal");
     return DNB_OK;
 }
 

@@ -92,9 +92,7 @@ class Conv2D(Conv):
     _cpa_live = None      # state of the block between this step's forward and backward
 
     def _cpa_usable(self):
-        # the fused backward implements the PER_SAMPLE pool routing; LITERAL (pooling.py:95 as written) keeps the
-        # layer-by-layer kernels
-        return (self._cpa is not None and not self.debug and config.route == _lib.ROUTE_PER_SAMPLE
+        return (self._cpa is not None and not self.debug
                 and self.kernel_regularizer is None and self.bias_regularizer is None)
 
     def _forward_fused(self, x):
@@ -148,7 +146,7 @@ class Conv2D(Conv):
         self.output = out
 
     def _backward_fused(self, live):
-        """gW / gb straight from the activation's delta (PER_SAMPLE routing); the parent's delta stays lazy."""
+        """gW / gb straight from the activation's delta (either pool routing); the parent's delta stays lazy."""
         pool, act = self._cpa
         x = live['x']
         b = x.shape[0]
@@ -156,8 +154,13 @@ class Conv2D(Conv):
         if pool.output_idxs is not live['idx']:        # the caller assigned its own argmax tensor: route through it
             user = DArray.wrap(pool.output_idxs, is_int=True)
             self._call("dnb_idx_gate_set", user.ptr(), live['ig'], user.size)
-        self._call("dnb_conv_pool_act_bwd", x.ptr(), act._delta().ptr(), live['ig'], self.grads['w1'].ptr(),
-                   self.grads['b1'].ptr(), g, gp, float(act.alpha), self._inv_m(b))
+        if config.route == _lib.ROUTE_PER_SAMPLE or b == 1:
+            self._call("dnb_conv_pool_act_bwd", x.ptr(), act._delta().ptr(), live['ig'], self.grads['w1'].ptr(),
+                       self.grads['b1'].ptr(), g, gp, float(act.alpha), self._inv_m(b))
+        else:       # pooling.py:95 as written: only sample 0 receives a delta, the last sample per argmax offset wins
+            ws = self._raw('cpa_last', _lib.load().dnb_conv_pool_act_bwd_literal_ws_bytes(g, gp))
+            self._call("dnb_conv_pool_act_bwd_literal", x.ptr(), act._delta().ptr(), live['ig'], self.grads['w1'].ptr(),
+                       self.grads['b1'].ptr(), g, gp, float(act.alpha), self._inv_m(b), ws)
         self.grads['w1'].written()
         self.grads['b1'].written()
         w_now, math = self._snapshot('w_snap', self.params['w1']), config.math

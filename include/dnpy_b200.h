@@ -125,6 +125,13 @@ int dnb_conv_pool_act_fwd(const float* x, const float* w, const float* b, float*
                           const dnb_win_t* conv, const dnb_win_t* pool, float alpha, dnb_stream_t stream);
 int dnb_conv_pool_act_bwd(const float* x, const float* act_delta, const uint8_t* idx_gate, float* gw, float* gb,
                           const dnb_win_t* conv, const dnb_win_t* pool, float alpha, float inv_m, dnb_stream_t stream);
+/* the same gradients under the reference's LITERAL pool routing (pooling.py:95: every sample's delta lands in sample 0's
+ * window, the last sample per argmax offset wins): only image 0 carries a conv gradient.  ws: _ws_bytes (int32 table
+ * last[F][OH*OW][9]). */
+size_t dnb_conv_pool_act_bwd_literal_ws_bytes(const dnb_win_t* conv, const dnb_win_t* pool);
+int dnb_conv_pool_act_bwd_literal(const float* x, const float* act_delta, const uint8_t* idx_gate, float* gw, float* gb,
+                                  const dnb_win_t* conv, const dnb_win_t* pool, float alpha, float inv_m, void* ws,
+                                  dnb_stream_t stream);
 int dnb_idx_gate_unpack(const uint8_t* idx_gate, int32_t* idx, size_t n, dnb_stream_t stream);
 /* the inverse for a caller that ASSIGNS MaxPool2D.output_idxs (pooling.py:74-76 stores it as a plain attribute): the
  * argmax nibble of every byte is replaced, the gate bit kept */

@@ -467,10 +467,12 @@ def test_gaussian_noise_net_trains_through_the_captured_graph(ns):
         assert rel_err(pa, pb) <= 1e-6
 
 
+@pytest.mark.parametrize("route", ["per_sample", "literal"])
 @pytest.mark.parametrize("math", ["fp32", "bf16"])
-def test_fused_conv_pool_act_block_per_sample(math, ns):
+def test_fused_conv_pool_act_block(math, route, ns):
     """The fused first block of the CNN (csrc/fused_cpa.cu: Conv2D(1->32, 3x3) -> MaxPool2D(3x3/2) -> Relu in one forward
-    and one backward kernel, PER_SAMPLE pool routing) against the float64 oracle with the same routing: loss, every
+    and one backward kernel; PER_SAMPLE pool routing and the reference's LITERAL routing — every delta into sample 0,
+    last sample per argmax offset wins) against the float64 oracle with the same routing: loss, every
     gradient, and every tensor the fused kernels never write (conv.output, pool.output, pool.output_idxs, pool.delta,
     conv.delta, Input.delta — LazyDArrays computed by the layer-by-layer kernels on the read).  Step 2 replaces the pool's
     argmax by the oracle's (honoured by the fused backward: dnb_idx_gate_set); step 2 forces the layer-by-layer backward
@@ -478,14 +480,14 @@ def test_fused_conv_pool_act_block_per_sample(math, ns):
     import dnpy_b200
     from dnpy_b200.darray import DArray, LazyDArray
     dnpy_b200.set_math(math)
-    dnpy_b200.set_maxpool_route("per_sample")
+    dnpy_b200.set_maxpool_route(route)
     tol = 1e-4 if math == "fp32" else 2e-2
     try:
         np.random.seed(42)
         net = topologies.mnist_cnn(ns, f1=32, f2=64)
         conv, pool, act = net.fts_layers[1], net.fts_layers[2], net.fts_layers[3]
         assert conv._cpa is not None and conv._cpa[0] is pool and conv._cpa[1] is act, "block not planned"
-        onet = OracleNet.mirror(net, maxpool_route="per_sample")
+        onet = OracleNet.mirror(net, maxpool_route=route)
         net.set_mode("train"); onet.set_mode("train")
         batch = 96
         x, y = topologies.make_data("mnist_cnn", batch * 3, np.random.RandomState(1234))
@@ -521,8 +523,8 @@ def test_fused_conv_pool_act_block_per_sample(math, ns):
                     a = np.asarray(l.grads[k]).reshape(g.shape)
                     if math == "fp32":
                         e = rel_err(a, g)
-                    else:
-                        e = float(np.linalg.norm(a - g) / (np.linalg.norm(a) + np.linalg.norm(g)))
+                    else:       # (LITERAL routing: the last sample's delta wins and is zero below the second pool — 0 == 0)
+                        e = float(np.linalg.norm(a - g) / max(np.linalg.norm(a) + np.linalg.norm(g), 1e-30))
                     assert e <= tol * (depth if math != "fp32" else 1), (s, l.name, k, e)
             if s == 1 and math == "fp32":       # everything the fused kernels skipped, on demand
                 assert rel_err(np.asarray(conv.output), o_conv.output) <= 1e-5
@@ -533,7 +535,7 @@ def test_fused_conv_pool_act_block_per_sample(math, ns):
         # the same through the captured step graph: free-running product vs oracle for a few steps
         np.random.seed(42)
         net = topologies.mnist_cnn(ns, f1=32, f2=64)
-        onet = OracleNet.mirror(net, maxpool_route="per_sample")
+        onet = OracleNet.mirror(net, maxpool_route=route)
         net.set_mode("train"); onet.set_mode("train")
         got, ref = [], []
         for s in range(6):
