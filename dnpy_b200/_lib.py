@@ -49,12 +49,14 @@ SIGNATURES = {
     "dnb_conv_pool_act_bwd": (_i, [_p, _p, _p, _p, _p, _W, _W, _f, _f, _p]),
     "dnb_conv_pool_act_bwd_literal_ws_bytes": (_z, [_W, _W]),
     "dnb_conv_pool_act_bwd_literal": (_i, [_p, _p, _p, _p, _p, _W, _W, _f, _f, _p, _p]),
+    "dnb_pool_act_supported": (_i, [_W]),
+    "dnb_maxpool2d_act_fwd": (_i, [_p, _p, _p, _W, _f, _p]),
+    "dnb_pool_act_bwd": (_i, [_p, _p, _p, _W, _f, _p]),
     "dnb_idx_gate_unpack": (_i, [_p, _p, _z, _p]),
     "dnb_idx_gate_set": (_i, [_p, _p, _z, _p]),
     "dnb_dwconv2d_fwd": (_i, [_p, _p, _p, _p, _W, _p]),
     "dnb_dwconv2d_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _W, _f, _R, _f, _p]),
     "dnb_maxpool2d_fwd": (_i, [_p, _p, _p, _W, _p]),
-    "dnb_maxpool2d_fwd_act": (_i, [_p, _p, _p, _p, _f, _W, _p]),
     "dnb_maxpool2d_bwd_ws_bytes": (_z, [_W, _i]),
     "dnb_maxpool2d_bwd": (_i, [_p, _p, _p, _W, _i, _p, _p]),
     "dnb_maxpool2d_bwd_prepare": (_i, [_p, _W, _p, _p]),

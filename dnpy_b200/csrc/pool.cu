@@ -101,8 +101,7 @@ __device__ __forceinline__ void mp_bulk_s2g(void* dst, const void* src, uint32_t
 template <int K, int S, bool VEC2>
 __global__ void __launch_bounds__(MPR_THREADS, 2) maxpool_fwd_ring_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                            int32_t* __restrict__ idx, int nchunks, int G,
-                                                                           int H, int W, int OH, int OW,
-                                                                           float* __restrict__ yact, float alpha) {
+                                                                           int H, int W, int OH, int OW) {
     extern __shared__ __align__(128) uint8_t smraw[];
     const int plane = H * W, oplane = OH * OW;
     const int n_in = G * plane, n_out = G * oplane;
@@ -111,7 +110,6 @@ __global__ void __launch_bounds__(MPR_THREADS, 2) maxpool_fwd_ring_kernel(const 
     float* sin = reinterpret_cast<float*>(smraw + 128);                 // [ST][n_in]
     float* sy = sin + (size_t)MPR_ST * n_in;                            // [2][n_out]
     int32_t* si = reinterpret_cast<int32_t*>(sy + 2 * n_out);           // [2][n_out]
-    float* sa = reinterpret_cast<float*>(si + 2 * n_out);               // [2][n_out]  LeakyRelu(y) of a fused consumer (yact != nullptr)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < MPR_ST; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], MPR_CONS / 32); }
@@ -177,7 +175,6 @@ __global__ void __launch_bounds__(MPR_THREADS, 2) maxpool_fwd_ring_kernel(const 
                 }
                 oy_[e] = best;
                 oi_[e] = bi;
-                if (yact) sa[ob * n_out + e] = best > 0.f ? best : alpha * best;       // activations.py:17-19
             }
         }
         __syncwarp();
@@ -191,7 +188,6 @@ __global__ void __launch_bounds__(MPR_THREADS, 2) maxpool_fwd_ring_kernel(const 
             const long c = (long)blockIdx.x + (long)n * gridDim.x;
             mp_bulk_s2g(y + c * n_out, oy_, (uint32_t)n_out * 4u);
             mp_bulk_s2g(idx + c * n_out, oi_, (uint32_t)n_out * 4u);
-            if (yact) mp_bulk_s2g(yact + c * n_out, sa + ob * n_out, (uint32_t)n_out * 4u);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
@@ -199,33 +195,31 @@ __global__ void __launch_bounds__(MPR_THREADS, 2) maxpool_fwd_ring_kernel(const 
 }
 
 // planes per chunk for the ring kernel (0: shape not eligible)
-static int mpr_chunk_planes(long planes, int H, int W, int OH, int OW, long stage_budget = 24 * 1024) {
+static int mpr_chunk_planes(long planes, int H, int W, int OH, int OW, long stage_budget = 24 * 1024, int omult = 4) {
     const long plane = (long)H * W, oplane = (long)OH * OW;
     if (plane % 4) return 0;
     const long gmax = std::min<long>({planes, stage_budget / (plane * 4), (long)(MPR_MAXR * MPR_CONS) / oplane});
     for (long G = gmax; G >= 1; --G)
-        if (planes % G == 0 && (G * oplane) % 4 == 0) return (int)G;
+        if (planes % G == 0 && (G * oplane) % omult == 0) return (int)G;
     return 0;
 }
 template <int K, int S>
-static bool maxpool_fwd_ring(const float* x, float* y, int32_t* idx, const dnb_win_t* g, cudaStream_t st,
-                             float* yact = nullptr, float alpha = 0.f) {
+static bool maxpool_fwd_ring(const float* x, float* y, int32_t* idx, const dnb_win_t* g, cudaStream_t st) {
     const long planes = (long)g->B * g->C;
-    // the fused variant stages a third output: smaller chunks keep two CTAs per SM
-    const int G = mpr_chunk_planes(planes, g->H, g->W, g->OH, g->OW, yact ? 20 * 1024 : 24 * 1024);
+    const int G = mpr_chunk_planes(planes, g->H, g->W, g->OH, g->OW);
     if (!G || getenv("DNB_NO_POOL_RING")) return false;
     const long nchunks = planes / G;
     if (nchunks > 0x7fffffffL) return false;
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(yact)) & 15) return false;
-    const size_t smem = 128 + ((size_t)MPR_ST * G * g->H * g->W + (yact ? 6ull : 4ull) * G * g->OH * g->OW) * 4;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(idx)) & 15) return false;
+    const size_t smem = 128 + ((size_t)MPR_ST * G * g->H * g->W + 4ull * G * g->OH * g->OW) * 4;
     const int grid = (int)std::min<long>(nchunks, 2L * kNumSMs);
     const bool v2 = (S == 2) && (g->W % 2 == 0);
     if (v2) {
         cudaFuncSetAttribute(maxpool_fwd_ring_kernel<K, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        maxpool_fwd_ring_kernel<K, S, true><<<grid, MPR_THREADS, smem, st>>>(x, y, idx, (int)nchunks, G, g->H, g->W, g->OH, g->OW, yact, alpha);
+        maxpool_fwd_ring_kernel<K, S, true><<<grid, MPR_THREADS, smem, st>>>(x, y, idx, (int)nchunks, G, g->H, g->W, g->OH, g->OW);
     } else {
         cudaFuncSetAttribute(maxpool_fwd_ring_kernel<K, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        maxpool_fwd_ring_kernel<K, S, false><<<grid, MPR_THREADS, smem, st>>>(x, y, idx, (int)nchunks, G, g->H, g->W, g->OH, g->OW, yact, alpha);
+        maxpool_fwd_ring_kernel<K, S, false><<<grid, MPR_THREADS, smem, st>>>(x, y, idx, (int)nchunks, G, g->H, g->W, g->OH, g->OW);
     }
     return true;
 }
@@ -527,6 +521,305 @@ static int check_pool(const char* name, const dnb_win_t* g) {
     return DNB_OK;
 }
 
+
+// ---- MaxPool2D -> LeakyRelu/Relu pair, forward (dnb_maxpool2d_act_fwd) ------------------------------------------------------
+// The (b,c) planes stream through the same bulk-copy ring as maxpool_fwd_ring_kernel; the outputs are 5 bytes per pooled
+// element (activation value + argmax offset | gate << 4), so they leave straight from registers as coalesced stores and the
+// consumer warps never meet at a block barrier: each warp waits for a stage, takes its 32-element slices of the chunk, stores,
+// releases the stage.  Branch-free argmax: m = max.NaN tree (NaN iff the window holds one), offset = first position equal to m
+// (first NaN when m is NaN) — np.argmax order.
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+template <int K, int S, bool VEC2>
+__global__ void __launch_bounds__(MPR_THREADS, 2) maxpool_act_fwd_ring_kernel(const float* __restrict__ x, float* __restrict__ act,
+                                                                               uint8_t* __restrict__ ig, int nchunks, int G,
+                                                                               int H, int W, int OH, int OW, float alpha) {
+    extern __shared__ __align__(128) uint8_t smraw[];
+    const int plane = H * W, oplane = OH * OW;
+    const int n_in = G * plane, n_out = G * oplane;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw);
+    uint64_t* empty = full + MPR_ST;
+    float* sin = reinterpret_cast<float*>(smraw + 128);                 // [ST][n_in]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < MPR_ST; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], MPR_CONS / 32); }
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+    const int mine = (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (wid == MPR_CONS / 32) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)n_in * 4u;
+            for (int n = 0; n < mine; ++n) {
+                const int s = n % MPR_ST;
+                if (n >= MPR_ST) tc::mbar_wait(&empty[s], ((n / MPR_ST) - 1) & 1);
+                const long c = (long)blockIdx.x + (long)n * gridDim.x;
+                tc::mbar_arrive_expect_tx(&full[s], bytes);
+                mp_bulk_g2s(sin + (size_t)s * n_in, x + c * n_in, bytes, &full[s]);
+            }
+        }
+        return;
+    }
+    int in_off[MPR_MAXR];
+#pragma unroll
+    for (int r = 0; r < MPR_MAXR; ++r) {
+        const int e = min(tid + r * MPR_CONS, n_out - 1);
+        const int p = e / oplane, o = e - p * oplane;
+        const int oy = o / OW, ox = o - oy * OW;
+        in_off[r] = p * plane + oy * S * W + ox * S;
+    }
+    for (int n = 0; n < mine; ++n) {
+        const int s = n % MPR_ST;
+        tc::mbar_wait(&full[s], (n / MPR_ST) & 1);
+        const float* in = sin + (size_t)s * n_in;
+        const long c = (long)blockIdx.x + (long)n * gridDim.x;
+        float* ga = act + c * n_out;
+        uint8_t* gi = ig + c * n_out;
+#pragma unroll
+        for (int r = 0; r < MPR_MAXR; ++r) {
+            const int e = tid + r * MPR_CONS;
+            if (e < n_out) {
+                const float* wp = in + in_off[r];
+                float v[K * K];
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    if (VEC2) {          // S == 2, W even, plane even: the window row starts on an 8-byte boundary
+#pragma unroll
+                        for (int j = 0; j + 1 < K; j += 2) {
+                            const float2 f = *reinterpret_cast<const float2*>(wp + i * W + j);
+                            v[i * K + j] = f.x; v[i * K + j + 1] = f.y;
+                        }
+                        if (K & 1) v[i * K + K - 1] = wp[i * W + K - 1];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < K; ++j) v[i * K + j] = wp[i * W + j];
+                    }
+                }
+                float m = v[0];
+#pragma unroll
+                for (int q = 1; q < K * K; ++q) m = fmax_nan(m, v[q]);
+                int bi = K * K - 1;
+                if (m == m) {
+#pragma unroll
+                    for (int q = K * K - 2; q >= 0; --q) bi = (v[q] == m) ? q : bi;
+                } else {                 // np.argmax: the first NaN is the maximum
+#pragma unroll
+                    for (int q = K * K - 2; q >= 0; --q) bi = (v[q] != v[q]) ? q : bi;
+                }
+                const bool pos = m > 0.f;
+                ga[e] = pos ? m : alpha * m;                                       // activations.py:17-19
+                gi[e] = (uint8_t)(bi | (pos ? 16 : 0));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&empty[s]);
+    }
+}
+
+template <int K, int S>
+static bool maxpool_act_fwd_ring(const float* x, float* act, uint8_t* ig, const dnb_win_t* g, float alpha, cudaStream_t st) {
+    const long planes = (long)g->B * g->C;
+    const int G = mpr_chunk_planes(planes, g->H, g->W, g->OH, g->OW, 24 * 1024, 1);
+    if (!G || getenv("DNB_NO_POOL_RING")) return false;
+    const long nchunks = planes / G;
+    if (nchunks > 0x7fffffffL) return false;
+    if (reinterpret_cast<uintptr_t>(x) & 15) return false;
+    const size_t smem = 128 + (size_t)MPR_ST * G * g->H * g->W * 4;
+    const int grid = (int)std::min<long>(nchunks, 2L * kNumSMs);
+    const bool v2 = (S == 2) && (g->W % 2 == 0);
+    if (v2) {
+        cudaFuncSetAttribute(maxpool_act_fwd_ring_kernel<K, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        maxpool_act_fwd_ring_kernel<K, S, true><<<grid, MPR_THREADS, smem, st>>>(x, act, ig, (int)nchunks, G, g->H, g->W, g->OH, g->OW, alpha);
+    } else {
+        cudaFuncSetAttribute(maxpool_act_fwd_ring_kernel<K, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        maxpool_act_fwd_ring_kernel<K, S, false><<<grid, MPR_THREADS, smem, st>>>(x, act, ig, (int)nchunks, G, g->H, g->W, g->OH, g->OW, alpha);
+    }
+    return true;
+}
+
+// ---- MaxPool2D -> LeakyRelu/Relu pair, backward (dnb_pool_act_bwd, per-sample routing) -----------------------------------------
+// Scatter form of maxpool_bwd_ring_kernel without block barriers: a consumer warp OWNS G/8 whole planes of every chunk — it
+// zero-fills them in the shared dX chunk, adds its windows class by class ((oy mod CL, ox mod CL): windows of a class never
+// overlap, so a pass is plain read-modify-writes; passes separated by __syncwarp — deterministic, no atomics) and hands its
+// planes to the bulk-store engine itself.  The activation's backward (activations.py:21-22: delta where the gate bit is set,
+// alpha*delta elsewhere) happens on the way in; 5 bytes per pooled element arrive, 4 bytes per input pixel leave.
+constexpr int PAB_MAXR = 8;
+template <int K, int S>
+__global__ void __launch_bounds__(MPR_THREADS, 3) pool_act_bwd_warp_kernel(const float* __restrict__ dact, const uint8_t* __restrict__ ig,
+                                                                            float* __restrict__ dx, int nchunks, int G, int ppw,
+                                                                            int H, int W, int OH, int OW, float alpha) {
+    constexpr int CL = (K + S - 1) / S;
+    extern __shared__ __align__(128) uint8_t smraw[];
+    const int plane = H * W, oplane = OH * OW;
+    const int n_in = G * plane, n_out = G * oplane;
+    const int stage_f = n_out + ((n_out + 3) >> 2);                     // floats per stage: deltas, then the bytes
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw);
+    uint64_t* empty = full + MPR_ST;
+    float* sin = reinterpret_cast<float*>(smraw + 128);                 // [ST][stage_f]
+    float* sdx = sin + (size_t)MPR_ST * stage_f;                        // [2][n_in]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < MPR_ST; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], MPR_CONS / 32); }
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+    const int mine = (nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (wid == MPR_CONS / 32) {
+        if (lane == 0) {
+            for (int n = 0; n < mine; ++n) {
+                const int s = n % MPR_ST;
+                if (n >= MPR_ST) tc::mbar_wait(&empty[s], ((n / MPR_ST) - 1) & 1);
+                const long c = (long)blockIdx.x + (long)n * gridDim.x;
+                tc::mbar_arrive_expect_tx(&full[s], (uint32_t)n_out * 5u);
+                mp_bulk_g2s(sin + (size_t)s * stage_f, dact + c * n_out, (uint32_t)n_out * 4u, &full[s]);
+                mp_bulk_g2s(sin + (size_t)s * stage_f + n_out, ig + c * n_out, (uint32_t)n_out, &full[s]);
+            }
+        }
+        return;
+    }
+    // this warp's planes [p0, p0 + np) of a chunk and its windows e = lane + 32 r (chunk independent)
+    const int p0 = wid * ppw, np = max(0, min(ppw, G - p0));
+    const int nwin = np * oplane, npix4 = (np * plane) >> 2;
+    int base[PAB_MAXR], cls[PAB_MAXR];
+#pragma unroll
+    for (int r = 0; r < PAB_MAXR; ++r) {
+        const int e = lane + 32 * r;
+        const int ec = min(e, max(nwin - 1, 0));
+        const int p = ec / oplane, o = ec - p * oplane;
+        const int oy = o / OW, ox = o - oy * OW;
+        base[r] = (p0 + p) * plane + oy * S * W + ox * S;
+        cls[r] = e < nwin ? (oy % CL) * CL + (ox % CL) : -1;
+    }
+    for (int n = 0; n < mine; ++n) {
+        const int s = n % MPR_ST, ob = n & 1;
+        float* out = sdx + (size_t)ob * n_in;
+        // this warp's part of buffer ob was handed to the store engine two chunks ago: at most ONE newer store may be unread
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        float4* o4 = reinterpret_cast<float4*>(out + p0 * plane);
+        for (int e = lane; e < npix4; e += 32) o4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        tc::mbar_wait(&full[s], (n / MPR_ST) & 1);
+        const float* sd = sin + (size_t)s * stage_f;
+        const uint8_t* sb = reinterpret_cast<const uint8_t*>(sd + n_out);
+        float d[PAB_MAXR]; int tgt[PAB_MAXR];
+#pragma unroll
+        for (int r = 0; r < PAB_MAXR; ++r) {
+            if (cls[r] >= 0) {
+                const int e = p0 * oplane + lane + 32 * r;
+                const unsigned ib = sb[e];
+                const int off = (int)(ib & 15u);
+                const float dv = sd[e];
+                d[r] = (ib & 16u) ? dv : alpha * dv;
+                tgt[r] = base[r] + (off / K) * W + (off % K);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&empty[s]);                      // the stage has been read into registers
+#pragma unroll
+        for (int c = 0; c < CL * CL; ++c) {
+#pragma unroll
+            for (int r = 0; r < PAB_MAXR; ++r)
+                if (cls[r] == c) out[tgt[r]] += d[r];
+            __syncwarp();
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && np > 0) {
+            const long c = (long)blockIdx.x + (long)n * gridDim.x;
+            mp_bulk_s2g(dx + c * n_in + (long)p0 * plane, out + p0 * plane, (uint32_t)(np * plane) * 4u);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int K, int S>
+static bool pool_act_bwd_warp(const float* dact, const uint8_t* ig, float* dx, const dnb_win_t* g, float alpha, cudaStream_t st) {
+    const long planes = (long)g->B * g->C;
+    const long plane = (long)g->H * g->W, oplane = (long)g->OH * g->OW;
+    if (plane % 4 || getenv("DNB_NO_POOL_RING")) return false;
+    // planes per chunk: a multiple of the 8 consumer warps, <= 18 KB of dX per buffer, <= 256 windows per warp, the chunk's
+    // deltas and bytes whole 16-byte groups
+    int G = 0;
+    for (long c = std::min<long>({planes, (18 * 1024) / (plane * 4), 8 * (32L * PAB_MAXR / oplane)}) / 8 * 8; c >= 8; c -= 8)
+        if (planes % c == 0 && (c * oplane) % 16 == 0) { G = (int)c; break; }
+    if (!G) return false;
+    const long nchunks = planes / G;
+    if (nchunks > 0x7fffffffL) return false;
+    if ((reinterpret_cast<uintptr_t>(dact) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(ig)) & 15) return false;
+    const long n_out = G * oplane;
+    const size_t smem = 128 + ((size_t)MPR_ST * (n_out + ((n_out + 3) >> 2)) + 2ull * G * plane) * 4;
+    const int grid = (int)std::min<long>(nchunks, 3L * kNumSMs);
+    cudaFuncSetAttribute(pool_act_bwd_warp_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pool_act_bwd_warp_kernel<K, S><<<grid, MPR_THREADS, smem, st>>>(dact, ig, dx, (int)nchunks, G, G / 8, g->H, g->W, g->OH, g->OW, alpha);
+    return true;
+}
+
+// MaxPool2D.forward + LeakyRelu.forward, any geometry with <= 16 window positions: act and the byte tensor only
+__global__ void __launch_bounds__(256) maxpool_act_fwd_kernel(const float* __restrict__ x, float* __restrict__ act,
+                                                              uint8_t* __restrict__ ig, dnb_win_t g, float alpha) {
+    const long n = (long)g.B * g.C * g.OH * g.OW;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        int ox = (int)(i % g.OW); long t = i / g.OW; int oy = (int)(t % g.OH); long bc = t / g.OH;
+        const float* xp = x + bc * g.H * g.W;
+        float best = 0.f; int bi = 0; bool first = true;
+        for (int ii = 0; ii < g.kh; ++ii) {
+            int iy = oy * g.sy + ii - g.pt;
+            bool rowin = (iy >= 0 && iy < g.H);
+            for (int jj = 0; jj < g.kw; ++jj) {
+                int ix = ox * g.sx + jj - g.pl;
+                float v = (rowin && ix >= 0 && ix < g.W) ? __ldg(xp + (long)iy * g.W + ix) : 0.f;   // zero pad
+                if (first || v > best || (v != v && best == best)) { best = v; bi = ii * g.kw + jj; first = false; }
+            }
+        }
+        const bool pos = best > 0.f;
+        act[i] = pos ? best : alpha * best;
+        ig[i] = (uint8_t)(bi | (pos ? 16 : 0));
+    }
+}
+
+// ---- LeakyRelu.backward + MaxPool2D.backward (PER_SAMPLE routing) from the byte tensor -------------------------------
+// dx[plane][(oy*S + off/K)*W + ox*S + off%K] += gate ? delta : alpha*delta.  A CTA builds PB_G planes at a time in shared memory
+// (zero fill, one shared atomicAdd per pooled element — overlapping windows may hit the same pixel) and writes them out with
+// 128-bit stores: the only HBM traffic is delta + bytes in, dx out.
+constexpr int PB_G = 32;
+__global__ void __launch_bounds__(256) pool_act_bwd_kernel(const float* __restrict__ dact, const uint8_t* __restrict__ idxg,
+                                                           float* __restrict__ dx, long planes, int H, int W, int OH, int OW,
+                                                           int K, int S, float alpha) {
+    extern __shared__ __align__(16) float sp[];           // [PB_G][H*W]
+    const int plane = H * W, OP = OH * OW;
+    const long groups = (planes + PB_G - 1) / PB_G;
+    for (long gidx = blockIdx.x; gidx < groups; gidx += gridDim.x) {
+        const long p0 = gidx * PB_G;
+        const int np = (int)min((long)PB_G, planes - p0);
+        const int n_in = np * plane, n_out = np * OP;
+        for (int e = threadIdx.x; e < (n_in >> 2); e += 256) reinterpret_cast<float4*>(sp)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = (n_in & ~3) + threadIdx.x; e < n_in; e += 256) sp[e] = 0.f;
+        __syncthreads();
+        for (int e = threadIdx.x; e < n_out; e += 256) {
+            const int pl = e / OP, o = e - pl * OP;
+            const int oy = o / OW, ox = o - oy * OW;
+            const float d = __ldg(dact + p0 * OP + e);
+            const unsigned ib = __ldg(idxg + p0 * OP + e);
+            const int off = (int)(ib & 15u);
+            const float dd = (ib & 16u) ? d : alpha * d;
+            atomicAdd(sp + pl * plane + (oy * S + off / K) * W + ox * S + off % K, dd);
+        }
+        __syncthreads();
+        float* out = dx + p0 * plane;
+        if (((plane * PB_G) & 3) == 0 && !(reinterpret_cast<uintptr_t>(dx) & 15)) {
+            for (int e = threadIdx.x; e < (n_in >> 2); e += 256) reinterpret_cast<float4*>(out)[e] = reinterpret_cast<const float4*>(sp)[e];
+            for (int e = (n_in & ~3) + threadIdx.x; e < n_in; e += 256) out[e] = sp[e];
+        } else {
+            for (int e = threadIdx.x; e < n_in; e += 256) out[e] = sp[e];
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace dnb
 
 using namespace dnb;
@@ -568,27 +861,63 @@ size_t dnb_maxpool2d_bwd_ws_bytes(const dnb_win_t* g, int route) {
     return (size_t)g->C * g->OH * g->OW * (g->kh * g->kw + 1) * sizeof(int32_t);      // last[npos][P] + done[npos]
 }
 
-// MaxPool2D.forward fused with a LeakyRelu / Relu consumer (activations.py:17-19): the pooled values, the argmax offsets AND
-// the consumer's output leave the ring kernel together — the activation's own pass over the pooled tensor (one read + one
-// write) disappears.  Only for the shapes the ring kernel takes; DNB_ERR_UNSUPPORTED otherwise (the host then runs the two
-// layers separately).
-int dnb_maxpool2d_fwd_act(const float* x, float* y, int32_t* idx, float* yact, float alpha, const dnb_win_t* g, dnb_stream_t stream) {
-    int rc = check_pool("maxpool2d_fwd_act", g);
+int dnb_pool_act_supported(const dnb_win_t* pool) {
+    if (!pool || check_pool("pool_act_supported", pool)) return 0;
+    if (pool->kh != pool->kw || pool->sy != pool->sx || (pool->pt | pool->pb | pool->pl | pool->pr) || pool->kh * pool->kw > 16) return 0;
+    if ((pool->OH - 1) * pool->sy + pool->kh > pool->H || (pool->OW - 1) * pool->sx + pool->kw > pool->W) return 0;
+    return (size_t)PB_G * pool->H * pool->W * sizeof(float) <= 200 * 1024 ? 1 : 0;
+}
+
+int dnb_maxpool2d_act_fwd(const float* x, float* act_out, uint8_t* idx_gate, const dnb_win_t* g, float alpha, dnb_stream_t stream) {
+    int rc = check_pool("maxpool2d_act_fwd", g);
     if (rc) return rc;
-    if ((long)g->B * g->C * g->OH * g->OW == 0) return DNB_OK;
-    DNB_CHECK_ARG(x && y && idx && yact, "maxpool2d_fwd_act: null pointer");
-    bool done = false;
+    if (g->kh * g->kw > 16) return set_err(DNB_ERR_UNSUPPORTED, "maxpool2d_act_fwd: windows of more than 16 positions do not fit the byte format");
+    const long n = (long)g->B * g->C * g->OH * g->OW;
+    if (n == 0) return DNB_OK;
+    DNB_CHECK_ARG(x && act_out && idx_gate, "maxpool2d_act_fwd: null pointer");
     if (!(g->pt | g->pb | g->pl | g->pr) && g->kh == g->kw && g->sy == g->sx &&
         (g->OH - 1) * g->sy + g->kh <= g->H && (g->OW - 1) * g->sx + g->kw <= g->W) {
-        if (g->kh == 3 && g->sy == 2) done = maxpool_fwd_ring<3, 2>(x, y, idx, g, S(stream), yact, alpha);
-        else if (g->kh == 2 && g->sy == 2) done = maxpool_fwd_ring<2, 2>(x, y, idx, g, S(stream), yact, alpha);
-        else if (g->kh == 3 && g->sy == 1) done = maxpool_fwd_ring<3, 1>(x, y, idx, g, S(stream), yact, alpha);
-        else if (g->kh == 2 && g->sy == 1) done = maxpool_fwd_ring<2, 1>(x, y, idx, g, S(stream), yact, alpha);
+        bool done = false;
+        if (g->kh == 3 && g->sy == 2) done = maxpool_act_fwd_ring<3, 2>(x, act_out, idx_gate, g, alpha, S(stream));
+        else if (g->kh == 2 && g->sy == 2) done = maxpool_act_fwd_ring<2, 2>(x, act_out, idx_gate, g, alpha, S(stream));
+        else if (g->kh == 3 && g->sy == 1) done = maxpool_act_fwd_ring<3, 1>(x, act_out, idx_gate, g, alpha, S(stream));
+        else if (g->kh == 2 && g->sy == 1) done = maxpool_act_fwd_ring<2, 1>(x, act_out, idx_gate, g, alpha, S(stream));
+        if (done) { DNB_LAUNCH_CHECK("maxpool2d_act_fwd"); return DNB_OK; }
     }
-    if (!done) return set_err(DNB_ERR_UNSUPPORTED, "maxpool2d_fwd_act: shape not taken by the ring kernel");
-    DNB_LAUNCH_CHECK("maxpool2d_fwd");
+    maxpool_act_fwd_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(x, act_out, idx_gate, *g, alpha);
+    DNB_LAUNCH_CHECK("maxpool2d_act_fwd");
     return DNB_OK;
 }
+
+/* LeakyRelu.backward (activations.py:21-22) + MaxPool2D.backward with the per-sample routing, straight from the activation's
+ * incoming delta and the byte tensor: dx is the pool's parent delta [B][C][H][W] */
+int dnb_pool_act_bwd(const float* act_delta, const uint8_t* idx_gate, float* dx, const dnb_win_t* pool, float alpha,
+                     dnb_stream_t stream) {
+    DNB_CHECK_ARG(pool && pool->kh == pool->kw && pool->sy == pool->sx && !(pool->pt | pool->pb | pool->pl | pool->pr) &&
+                  (pool->OH - 1) * pool->sy + pool->kh <= pool->H && (pool->OW - 1) * pool->sx + pool->kw <= pool->W,
+                  "pool_act_bwd: square unpadded pools only");
+    const long planes = (long)pool->B * pool->C;
+    if (planes == 0) return DNB_OK;
+    DNB_CHECK_ARG(act_delta && idx_gate && dx, "pool_act_bwd: null pointer");
+    {
+        bool done = false;
+        if (pool->kh == 3 && pool->sy == 2) done = pool_act_bwd_warp<3, 2>(act_delta, idx_gate, dx, pool, alpha, S(stream));
+        else if (pool->kh == 2 && pool->sy == 2) done = pool_act_bwd_warp<2, 2>(act_delta, idx_gate, dx, pool, alpha, S(stream));
+        else if (pool->kh == 3 && pool->sy == 1) done = pool_act_bwd_warp<3, 1>(act_delta, idx_gate, dx, pool, alpha, S(stream));
+        else if (pool->kh == 2 && pool->sy == 1) done = pool_act_bwd_warp<2, 1>(act_delta, idx_gate, dx, pool, alpha, S(stream));
+        if (done) { DNB_LAUNCH_CHECK("pool_act_bwd"); return DNB_OK; }
+    }
+    const size_t smem = (size_t)PB_G * pool->H * pool->W * sizeof(float);
+    DNB_CHECK_ARG(smem <= 200 * 1024, "pool_act_bwd: plane of %d x %d is too large", pool->H, pool->W);
+    cudaFuncSetAttribute(pool_act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long groups = (planes + PB_G - 1) / PB_G;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
+    pool_act_bwd_kernel<<<(unsigned)std::min<long>(groups, (long)kNumSMs * per_sm), 256, smem, S(stream)>>>(
+        act_delta, idx_gate, dx, planes, pool->H, pool->W, pool->OH, pool->OW, pool->kh, pool->sy, alpha);
+    DNB_LAUNCH_CHECK("pool_act_bwd");
+    return DNB_OK;
+}
+
 
 int dnb_maxpool2d_bwd(const float* dy, const int32_t* idx, float* dx, const dnb_win_t* g,
                       int route, void* ws, dnb_stream_t stream) {

@@ -18,13 +18,9 @@ class LeakyRelu(Layer):
         self.gate = None
 
     def forward(self):
-        if self.__dict__.pop("_cpa_skip_fwd", False):      # the fused conv->pool->act block wrote self.output already
+        if self.__dict__.pop("_cpa_skip_fwd", False):      # the fused (conv->)pool->act kernel wrote self.output already
             return
         x = self._in()
-        pre, self._precomputed = getattr(self, "_precomputed", None), None
-        if pre is not None and pre[0] is x:              # the producing MaxPool2D already wrote this layer's output
-            self.output = pre[1]
-            return
         out = self._buf('out', x.shape)
         self._call("dnb_leakyrelu_fwd", x.ptr(), out.ptr(), x.size, float(self.alpha))
         self.output = out
@@ -38,8 +34,8 @@ class LeakyRelu(Layer):
     def backward(self):
         block = getattr(self, "_cpa_block", None)
         if block is not None and block._cpa_live is not None:
-            # fused block (layers/convolution.py): the conv layer consumes THIS layer's incoming delta directly; the
-            # pool's delta exists only if somebody reads it
+            # fused block (layers/convolution.py, layers/pooling.py): the conv / pool layer consumes THIS layer's incoming
+            # delta directly; the pool's delta exists only if somebody reads it
             self._delta()
             self.parents[0].delta = LazyDArray(self.parents[0].output.shape, lambda: self._backward_now().dev())
             return

@@ -47,26 +47,52 @@ class MaxPool2D(Pool):
         super().__init__(l_in, pool_size=pool_size, strides=strides, padding=padding, name=name)
         self.output_idxs = None
 
+    # ---- fused MaxPool2D -> LeakyRelu/Relu pair (dnb_maxpool2d_act_fwd / dnb_pool_act_bwd), planned by Net.build -------
+    _pa = None            # the activation, when it is this pool's only consumer and the geometry fits the byte format
+    _cpa_live = None      # state of the pair between this step's forward and backward (the name the activation looks for)
+
+    def _pa_usable(self, batch):
+        # the byte-tensor backward implements the per-sample routing (identical to the literal one for a single sample)
+        return (self._pa is not None and not self.debug and
+                (config.route == _lib.ROUTE_PER_SAMPLE or batch == 1))
+
+    def _forward_pair(self, x):
+        act = self._pa
+        b = x.shape[0]
+        g = self._win(b)
+        n = b * int(np.prod(self.oshape))
+        aout = act._buf('out', (b, *self.oshape))
+        ig = self._raw('pa_idx_gate', n)                   # one byte per pooled element: argmax offset | gate << 4
+        self._call("dnb_maxpool2d_act_fwd", x.ptr(), aout.ptr(), ig, g, float(act.alpha))
+
+        # the tensors the fused kernel never wrote stay observable (computed by the plain kernel on a read)
+        def pool_out():
+            out = self._buf('out', (b, *self.oshape))
+            idx = self._buf('idx', (b, *self.oshape), is_int=True)
+            self._call("dnb_maxpool2d_fwd", x.ptr(), out.ptr(), idx.ptr(), g)
+            return out.dev()
+
+        def pool_idx():
+            idx = self._buf('idx_unpacked', (b, *self.oshape), is_int=True)
+            self._call("dnb_idx_gate_unpack", ig, idx.ptr(), n)
+            return idx.dev()
+        self.output = LazyDArray((b, *self.oshape), pool_out)
+        self.output_idxs = LazyDArray((b, *self.oshape), pool_idx, is_int=True)
+        act.output = aout
+        act._cpa_skip_fwd = True
+        self._cpa_live = dict(ig=ig, idx=self.output_idxs, b=b)
+
     def forward(self):
         if self.__dict__.pop("_cpa_skip_fwd", False):      # the fused conv->pool->act block set output / output_idxs (lazy)
             return
         x = self._in()
         b = x.shape[0]
+        self._cpa_live = None
+        if self._pa_usable(b):
+            return self._forward_pair(x)
         out = self._buf('out', (b, *self.oshape))
         idx = self._buf('idx', (b, *self.oshape), is_int=True)
-        act = getattr(self, "_fused_act", None)          # set by Net.build: a LeakyRelu/Relu that is this layer's only consumer
-        fused = False
-        if act is not None and not getattr(self, "_fused_unsupported", False):
-            aout = act._buf('out', (b, *self.oshape))
-            try:
-                self._call("dnb_maxpool2d_fwd_act", x.ptr(), out.ptr(), idx.ptr(), aout.ptr(), float(act.alpha), self._win(b))
-                aout.written()
-                act._precomputed = (out, aout)           # valid for exactly this output object
-                fused = True
-            except NotImplementedError:
-                self._fused_unsupported = True          # shape outside the ring kernel: run the two layers separately
-        if not fused:
-            self._call("dnb_maxpool2d_fwd", x.ptr(), out.ptr(), idx.ptr(), self._win(b))
+        self._call("dnb_maxpool2d_fwd", x.ptr(), out.ptr(), idx.ptr(), self._win(b))
         self.output = out
         self.output_idxs = idx
 
@@ -81,6 +107,17 @@ class MaxPool2D(Pool):
 
     def backward(self):
         route = config.route
+        live, self._cpa_live = self._cpa_live, None
+        if live is not None and self._pa_usable(live['b']):
+            # LeakyRelu.backward + MaxPool2D.backward in one pass over the activation's delta and the byte tensor
+            act, b = self._pa, live['b']
+            if self.output_idxs is not live['idx']:        # the caller assigned its own argmax tensor: route through it
+                user = DArray.wrap(self.output_idxs, is_int=True)
+                self._call("dnb_idx_gate_set", user.ptr(), live['ig'], user.size)
+            dx = self._buf('dx', (b, *self.parents[0].oshape))
+            self._call("dnb_pool_act_bwd", act._delta().ptr(), live['ig'], dx.ptr(), self._win(b), float(act.alpha))
+            self.parents[0].delta = dx
+            return
         block = getattr(self, "_cpa_block", None)
         if block is not None and block._cpa_live is not None:
             # fused block: the conv layer computes its gradients from the activation's delta; this layer's 4.7x larger

@@ -125,10 +125,9 @@ class Net:
         self._plan_fusions()
 
     def _plan_fusions(self):
-        """MaxPool2D -> LeakyRelu/Relu where the activation is the pool's ONLY consumer: the pool's forward kernel also
-        writes the activation's output (dnb_maxpool2d_fwd_act); every layer still exposes its own output/delta buffers.
-        OPT-IN (DNPY_B200_FUSION=1): correct (the GPU suite passes with it), but measured slower on B200 — the third output
-        forces smaller ring chunks, the pool forward goes 171 -> 250 us to save the activation's 49 us (1.375 -> 1.404 ms/step)."""
+        """Decided once per build: dead data gradients (lazy), the fused first block Conv2D(C=1) -> MaxPool2D -> LeakyRelu/Relu
+        (csrc/fused_cpa.cu) and fused MaxPool2D -> LeakyRelu/Relu pairs (dnb_maxpool2d_act_fwd / dnb_pool_act_bwd).  Every
+        layer still exposes its own output / delta: what a fused kernel never wrote is a LazyDArray."""
         import os
         from .layers import MaxPool2D, LeakyRelu, Conv2D, Dense, Input, Reshape, DepthwiseConv2D
         # dead data gradients: a Conv2D / Dense whose delta would only travel (through Reshape views) to an Input layer
@@ -167,12 +166,24 @@ class Net:
             if ok:
                 l._cpa = (pool, act)
                 pool._cpa_block = act._cpa_block = l
+        # MaxPool2D -> LeakyRelu/Relu pairs outside a fused first block: the pool's kernel writes the activation's output and
+        # one byte per pooled element; the backward pair is one pass from the activation's delta
         for l in self.fts_layers:
-            l._fused_act = None
+            if isinstance(l, MaxPool2D):
+                l._pa = None
+        for l in self.fts_layers:
             cons = consumers.get(id(l), [])
-            if (isinstance(l, MaxPool2D) and len(cons) == 1 and type(cons[0]).__name__ in ("LeakyRelu", "Relu")
-                    and isinstance(cons[0], LeakyRelu) and l not in self.l_out and os.environ.get("DNPY_B200_FUSION")):
-                l._fused_act = cons[0]
+            if (not isinstance(l, MaxPool2D) or len(cons) != 1 or type(cons[0]).__name__ not in ("LeakyRelu", "Relu")
+                    or not isinstance(cons[0], LeakyRelu) or l in self.l_out or l._cpa_block is not None
+                    or os.environ.get("DNPY_B200_NO_POOL_ACT")):
+                continue
+            try:
+                ok = _lib.load().dnb_pool_act_supported(l._win(1))
+            except ValueError:
+                ok = 0
+            if ok:
+                l._pa = cons[0]
+                cons[0]._cpa_block = l
 
     def fts(self):
         self.fts_layers = list(self.bts_layers)

@@ -132,6 +132,17 @@ size_t dnb_conv_pool_act_bwd_literal_ws_bytes(const dnb_win_t* conv, const dnb_w
 int dnb_conv_pool_act_bwd_literal(const float* x, const float* act_delta, const uint8_t* idx_gate, float* gw, float* gb,
                                   const dnb_win_t* conv, const dnb_win_t* pool, float alpha, float inv_m, void* ws,
                                   dnb_stream_t stream);
+/* MaxPool2D -> LeakyRelu/Relu where the activation is the pool's only consumer (pooling.py:43-99 + activations.py:17-22).
+ * Forward: ONLY the activation's output and one byte per pooled element (argmax offset | gate << 4) are written, 5 bytes per
+ * pooled element instead of 16 (pool output, int32 argmax, activation output).  Backward (per-sample routing):
+ * LeakyRelu.backward + MaxPool2D.backward in one pass from the activation's delta and the byte tensor into the pool's
+ * parent delta dx[B][C][H][W].  dnb_pool_act_supported: 1 when both calls take the geometry (<= 16 window positions,
+ * square unpadded windows inside the plane). */
+int dnb_pool_act_supported(const dnb_win_t* pool);
+int dnb_maxpool2d_act_fwd(const float* x, float* act_out, uint8_t* idx_gate, const dnb_win_t* pool, float alpha,
+                          dnb_stream_t stream);
+int dnb_pool_act_bwd(const float* act_delta, const uint8_t* idx_gate, float* dx, const dnb_win_t* pool, float alpha,
+                     dnb_stream_t stream);
 int dnb_idx_gate_unpack(const uint8_t* idx_gate, int32_t* idx, size_t n, dnb_stream_t stream);
 /* the inverse for a caller that ASSIGNS MaxPool2D.output_idxs (pooling.py:74-76 stores it as a plain attribute): the
  * argmax nibble of every byte is replaced, the gate bit kept */
@@ -147,9 +158,6 @@ int dnb_dwconv2d_bwd(const float* x, const float* w, const float* b, const float
 /* ---- MaxPool2D / AvgPool2D (layers/pooling.py:43-99, 118-174) --------------- */
 /* idx[B,C,OH,OW] int32: first max of the zero-padded row-major window (bit-exact vs np.argmax) */
 int dnb_maxpool2d_fwd(const float* x, float* y, int32_t* idx, const dnb_win_t* g, dnb_stream_t stream);
-/* MaxPool2D.forward + the forward of a LeakyRelu/Relu that consumes it (activations.py:17-19), one kernel:
- * yact = y > 0 ? y : alpha*y.  Returns DNB_ERR_UNSUPPORTED for shapes outside the bulk-copy ring kernel. */
-int dnb_maxpool2d_fwd_act(const float* x, float* y, int32_t* idx, float* yact, float alpha, const dnb_win_t* g, dnb_stream_t stream);
 size_t dnb_maxpool2d_bwd_ws_bytes(const dnb_win_t* g, int route);
 int dnb_maxpool2d_bwd(const float* dy, const int32_t* idx, float* dx, const dnb_win_t* g,
                       int route, void* ws, dnb_stream_t stream);

@@ -548,3 +548,89 @@ def test_fused_conv_pool_act_block(math, route, ns):
     finally:
         dnpy_b200.set_math("fp32")
         dnpy_b200.set_maxpool_route("literal")
+
+
+@pytest.mark.parametrize("pool_geom", [((3, 3), (2, 2), 12), ((2, 2), (2, 2), 12), ((3, 3), (1, 1), 8), ((4, 4), (3, 3), 13)])
+@pytest.mark.parametrize("math", ["fp32", "bf16"])
+def test_fused_pool_act_pair(math, pool_geom, ns):
+    """MaxPool2D -> LeakyRelu where the activation is the pool's only consumer (here behind the tcgen05 Conv2D 32 -> 64 of the
+    CNN): the pool's forward kernel writes ONLY the activation's output and one byte per pooled element
+    (dnb_maxpool2d_act_fwd), the backward pair is one pass from the activation's delta and the bytes (dnb_pool_act_bwd,
+    per-sample routing).  Ring-kernel geometries (3x3/2, 2x2/2, 3x3/1) and a generic one (4x4/3); 600 images.  Against the
+    float64 oracle: activation output, argmax, and — with the oracle's argmax teacher-forced — every gradient and delta;
+    the tensors the fused kernels never wrote (pool.output, pool.output_idxs, pool.delta) come back through the lazies."""
+    import dnpy_b200
+    from dnpy_b200.darray import DArray, LazyDArray
+    L = ns.L
+    dnpy_b200.set_math(math)
+    dnpy_b200.set_maxpool_route("per_sample")
+    tol = 1e-5 if math == "fp32" else 2e-2
+    size = pool_geom[2]
+
+    def build(optimizer=None):
+        np.random.seed(7)
+        l_in = L.Input(shape=(32, size, size))
+        conv = L.Conv2D(l_in, filters=64, kernel_size=(3, 3), strides=(1, 1), padding="same")
+        pool = L.MaxPool2D(conv, pool_size=pool_geom[0], strides=pool_geom[1], padding="none")
+        act = L.LeakyRelu(pool, alpha=0.3)
+        l_out = L.Softmax(L.Dense(L.Reshape(act, shape=(-1)), 10))
+        net = ns.Net()
+        net.build(l_in=[l_in], l_out=[l_out], optimizer=optimizer or ns.opt.Adam(lr=0.001), losses=[ns.losses.CrossEntropy()],
+                  metrics=[[ns.metrics.CategoricalAccuracy()]], debug=False, smart_derivatives=True)
+        return net, conv, pool, act
+    try:
+        net, conv, pool, act = build()
+        assert pool._pa is act and act._cpa_block is pool, "pair not planned"
+        onet = OracleNet.mirror(net, maxpool_route="per_sample")
+        net.set_mode("train"); onet.set_mode("train")
+        batch = 600
+        rs = np.random.RandomState(5)
+        x = rs.randn(batch, 32, size, size)
+        y = np.eye(10)[rs.randint(0, 10, batch)]
+        b1 = rs.randn(64) * 0.1                        # a non-zero bias (the reference adds it K times)
+        net.fts_layers[1].params['b1'] = b1
+        onet.fts[1].params['b1'] = b1.copy()
+        net.feed_input([x])
+        net.forward()
+        assert isinstance(pool.output, LazyDArray) and not pool.output.materialised, "fused forward did not run"
+        lo, de = net.compute_losses(y_target=[y])
+        want = onet.step([x], [y])[0]
+        assert abs(lo[0] - want) <= max(tol, 2e-5) * max(1.0, abs(want))
+        o_conv, o_pool, o_act = onet.fts[1], onet.fts[2], onet.fts[3]
+        assert rel_err(np.asarray(act.output), o_act.output) <= tol
+        flips = float(np.mean(np.asarray(pool.output_idxs) != o_pool.cache["idx"]))
+        assert flips <= (1e-4 if math == "fp32" else 0.03), flips
+        pool.output_idxs = DArray(host=o_pool.cache["idx"], is_int=True)
+        net.reset_grads()
+        net.do_delta(de)
+        net.backward()
+        assert not pool.output.materialised, "the backward pass must not need the pooled pre-activation"
+        for l, n in zip(net.fts_layers, onet.fts):
+            for k, g in n.grads.items():
+                a = np.asarray(l.grads[k]).reshape(g.shape)
+                e = float(np.linalg.norm(a - g) / max(np.linalg.norm(a) + np.linalg.norm(g), 1e-30))
+                assert e <= max(tol, 1e-5), (l.name, k, e)
+        if math == "fp32":       # a bf16 sign flip of a near-zero pooled value swaps delta <-> alpha*delta: compared in fp32 only
+            assert rel_err(np.asarray(conv.delta), o_conv.delta) <= 1e-5       # dY rebuilt from the byte tensor
+        # everything the fused forward / backward skipped, on demand (the layer-by-layer kernels)
+        assert rel_err(np.asarray(pool.output), o_pool.output) <= tol
+        if math == "fp32":
+            assert rel_err(np.asarray(pool.delta), o_pool.delta) <= 1e-5
+        # the captured step graph: fused pair against the two layers run separately, free running (momentum SGD: parameter
+        # differences stay proportional to gradient differences — Adam turns the round-off of a near-zero gradient into lr)
+        outs = []
+        for fused in (True, False):
+            n2, c2, p2, a2 = build(ns.opt.SGD(lr=0.01, momentum=0.9))
+            if not fused:
+                p2._pa = None
+                a2._cpa_block = None
+            n2.set_mode("train")
+            for s in range(4):
+                n2.train_step([x[:256]], [y[:256]])
+            assert (p2._bufs.get('pa_idx_gate') is not None) == fused
+            outs.append([np.asarray(v).copy() for l in n2.fts_layers for v in l.params.values()])
+        for pa, pb in zip(*outs):
+            assert rel_err(pa, pb) <= 1e-5          # identical arithmetic up to the order of atomic partial sums in the weight gradients
+    finally:
+        dnpy_b200.set_math("fp32")
+        dnpy_b200.set_maxpool_route("literal")
