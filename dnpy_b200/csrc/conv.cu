@@ -677,6 +677,22 @@ int dnb_conv2d_bwd(const float* x, const float* w, const float* b, const float* 
     return DNB_OK;
 }
 
+// Conv2D (tensor-core shifted-view shapes) -> MaxPool2D -> LeakyRelu in one launch: convolution.py:193-225 + pooling.py:43-99 +
+// activations.py:17-19; the convolution output and the pooled pre-activation never reach HBM (idx_gate: csrc/fused_cpa.cu format)
+int dnb_conv2d_pool_act_supported(const dnb_win_t* conv, const dnb_win_t* pool, int math) {
+    if (!conv || !pool || math != DNB_MATH_BF16 || getenv("DNB_NO_SV") || check_win("conv2d_pool_act", conv)) return 0;
+    return tc_conv_svp_supported(conv, pool) ? 1 : 0;
+}
+
+int dnb_conv2d_pool_act_fwd(const float* x, const float* w, const float* b, float* act_out, uint8_t* idx_gate,
+                            const dnb_win_t* conv, const dnb_win_t* pool, float alpha, void* ws, int math,
+                            dnb_stream_t stream) {
+    DNB_CHECK_ARG(dnb_conv2d_pool_act_supported(conv, pool, math), "conv2d_pool_act_fwd: unsupported geometry / math mode");
+    if (conv->B == 0) return DNB_OK;
+    DNB_CHECK_ARG(x && w && b && act_out && idx_gate, "conv2d_pool_act_fwd: null pointer");
+    return tc_conv_fwd_pool(x, w, b, act_out, idx_gate, alpha, conv, pool, ws, S(stream));
+}
+
 // Data gradient alone (the second half of Conv2D.backward, convolution.py:244-250,271-273): what a caller runs when the
 // parent's delta is wanted but the parameter gradients are not (Net materialises the delta of an Input layer lazily —
 // nothing on the training path consumes it).  Same kernel selection as dnb_conv2d_bwd.

@@ -660,6 +660,16 @@ int tc_conv_fwd(const float* x, const float* w, const float* b, float* y, const 
     return run_gather("tc_conv2d_fwd", wp, n_pad, p, st);
 }
 
+int tc_conv_fwd_pool(const float* x, const float* w, const float* b, float* act, unsigned char* idx_gate, float alpha,
+                     const dnb_win_t* g, const dnb_win_t* pool, void* ws, cudaStream_t st) {
+    if (!ws) return set_err(DNB_ERR_INVALID, "conv2d_pool_act_fwd: workspace required");
+    const int cp = round_up(g->C, 4), Kp = round_up(cp * g->kh * g->kw, CBK), n_pad = round_up(g->F, 128);
+    float* wp = static_cast<float*>(ws);
+    prep_weights_kernel<<<(n_pad * Kp + 255) / 256, 256, 0, st>>>(w, wp, g->F, g->C, g->kh, g->kw, n_pad, Kp, cp, 0, 1);
+    DNB_LAUNCH_CHECK("conv2d_prep_weights");
+    return tc_conv_svp_run(x, wp, n_pad, Kp, b, (float)(g->C * g->kh * g->kw), act, idx_gate, alpha, g, pool, st);
+}
+
 int tc_conv_dgrad(const float* dy, const float* w, float* dx, const dnb_win_t* g, void* ws, bool bf16, cudaStream_t st) {
     if (!ws) return set_err(DNB_ERR_INVALID, "conv2d_bwd(tf32): workspace required");
     const int cp = round_up(g->F, 4), Kp = round_up(cp * g->kh * g->kw, CBK), n_pad = round_up(g->C, 128);

@@ -21,6 +21,15 @@ bool tc_conv_sv_bf16_supported(const dnb_win_t* g, bool dgrad);
 int tc_conv_sv_run(const char* name, const float* src, const void* wprep, int n_pad, int Kp, const float* bias, float bias_k,
                    float* dst, const dnb_win_t* g, bool dgrad, bool bf16, cudaStream_t st);
 
+// tc_conv_svp.cu: 3x3 'same' stride-1 convolution (32 / 64 input channels, <= 64 filters, BF16 operands) with the
+// MaxPool2D -> LeakyRelu pair behind it in the epilogue.  Operand roles are swapped against tc_conv_sv.cu (filters = M,
+// the pixels of the staged image = N): a TMEM lane holds one filter's whole image, so pooling is register work.
+bool tc_conv_svp_supported(const dnb_win_t* g, const dnb_win_t* pool);
+int tc_conv_svp_run(const float* x, const void* wprep, int n_pad, int Kp, const float* bias, float bias_k, float* act,
+                    unsigned char* idx_gate, float alpha, const dnb_win_t* g, const dnb_win_t* pool, cudaStream_t st);
+int tc_conv_fwd_pool(const float* x, const float* w, const float* b, float* act, unsigned char* idx_gate, float alpha,
+                     const dnb_win_t* g, const dnb_win_t* pool, void* ws, cudaStream_t st);
+
 // tc_conv_wg.cu: shifted-view weight gradient (3x3 stride 1, 32 input channels, small images)
 bool tc_conv_wgrad_sv_supported(const dnb_win_t* g);
 int tc_conv_wgrad_sv(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, bool bf16, cudaStream_t st);

@@ -421,6 +421,7 @@ tc_conv_sv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         }
                     } else {
                         tmem_ld_wait();
+                        if (p.prof) tq1 = clock64();
 #pragma unroll
                         for (int j = 0; j < NC; ++j) bv[j] += __uint_as_float(v[j]);
                     }

@@ -132,12 +132,46 @@ class Conv2D(Conv):
         pool._cpa_skip_fwd = act._cpa_skip_fwd = True
         self._cpa_live = dict(ig=ig, idx=pool.output_idxs, x=x)
 
+    # ---- tensor-core Conv2D whose epilogue runs the MaxPool2D -> LeakyRelu/Relu pair behind it (csrc/tc_conv_sv.cu) ------
+    _tcp = None           # the pool, when it is this layer's only consumer and heads a fused pair (planned by Net.build)
+
+    def _tcp_usable(self, b):
+        pool = self._tcp
+        if pool is None or self.debug or config.math < _lib.MATH_TF32 or not pool._pa_usable(b):
+            return False
+        ok = self.__dict__.setdefault("_tcp_ok", {})
+        if config.math not in ok:
+            ok[config.math] = bool(_lib.load().dnb_conv2d_pool_act_supported(self._win(1), pool._win(1), config.math))
+        return ok[config.math]
+
+    def _forward_tc_pool(self, x):
+        """convolution + pool + activation in ONE launch: only the activation's output and one byte per pooled element are
+        written; this layer's output stays observable (the plain kernel runs if somebody reads it)."""
+        pool = self._tcp
+        b = x.shape[0]
+        g, gp, math = self._win(b), pool._win(b), config.math
+        aout, ig = pool._pair_buffers(b)
+        ws = self._raw('ws', _lib.load().dnb_conv2d_ws_bytes(g, math))
+        self._call("dnb_conv2d_pool_act_fwd", x.ptr(), self.params['w1'].ptr(), self.params['b1'].ptr(), aout.ptr(), ig,
+                   g, gp, float(pool._pa.alpha), ws, math)
+        w_now, b_now = self._snapshot('w_snap_f', self.params['w1']), self._snapshot('b_snap_f', self.params['b1'])
+
+        def conv_out():
+            out = self._buf('out', (b, *self.oshape))
+            self._call("dnb_conv2d_fwd", x.ptr(), w_now.ptr(), b_now.ptr(), out.ptr(), g, ws, math)
+            return out.dev()
+        self.output = LazyDArray((b, *self.oshape), conv_out)
+        pool._install_pair(self.output, aout, ig, b)
+        pool._pair_done = True
+
     def forward(self):
         x = self._in()
         self._cpa_live = None
         if self._cpa_usable():
             return self._forward_fused(x)
         b = x.shape[0]
+        if self._tcp_usable(b):
+            return self._forward_tc_pool(x)
         g = self._win(b)
         out = self._buf('out', (b, *self.oshape))
         ws = self._raw('ws', _lib.load().dnb_conv2d_ws_bytes(g, config.math))

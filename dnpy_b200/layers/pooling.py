@@ -56,16 +56,17 @@ class MaxPool2D(Pool):
         return (self._pa is not None and not self.debug and
                 (config.route == _lib.ROUTE_PER_SAMPLE or batch == 1))
 
-    def _forward_pair(self, x):
-        act = self._pa
-        b = x.shape[0]
-        g = self._win(b)
+    def _pair_buffers(self, b):
+        """(activation output, byte tensor) the fused forward writes."""
         n = b * int(np.prod(self.oshape))
-        aout = act._buf('out', (b, *self.oshape))
-        ig = self._raw('pa_idx_gate', n)                   # one byte per pooled element: argmax offset | gate << 4
-        self._call("dnb_maxpool2d_act_fwd", x.ptr(), aout.ptr(), ig, g, float(act.alpha))
+        return self._pa._buf('out', (b, *self.oshape)), self._raw('pa_idx_gate', n)
 
-        # the tensors the fused kernel never wrote stay observable (computed by the plain kernel on a read)
+    def _install_pair(self, x, aout, ig, b):
+        """State after a fused forward wrote ``aout`` / ``ig`` (this layer's kernel, or the epilogue of the tensor-core
+        convolution in front of it): the tensors nobody wrote stay observable, computed by the plain kernel on a read."""
+        act, g = self._pa, self._win(b)
+        n = b * int(np.prod(self.oshape))
+
         def pool_out():
             out = self._buf('out', (b, *self.oshape))
             idx = self._buf('idx', (b, *self.oshape), is_int=True)
@@ -82,8 +83,16 @@ class MaxPool2D(Pool):
         act._cpa_skip_fwd = True
         self._cpa_live = dict(ig=ig, idx=self.output_idxs, b=b)
 
+    def _forward_pair(self, x):
+        b = x.shape[0]
+        aout, ig = self._pair_buffers(b)                   # ig: one byte per pooled element, argmax offset | gate << 4
+        self._call("dnb_maxpool2d_act_fwd", x.ptr(), aout.ptr(), ig, self._win(b), float(self._pa.alpha))
+        self._install_pair(x, aout, ig, b)
+
     def forward(self):
         if self.__dict__.pop("_cpa_skip_fwd", False):      # the fused conv->pool->act block set output / output_idxs (lazy)
+            return
+        if self.__dict__.pop("_pair_done", False):         # the tensor-core convolution in front ran this pair in its epilogue
             return
         x = self._in()
         b = x.shape[0]

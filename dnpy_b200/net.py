@@ -184,6 +184,15 @@ class Net:
             if ok:
                 l._pa = cons[0]
                 cons[0]._cpa_block = l
+        # a tensor-core Conv2D whose only consumer heads such a pair runs the pair in its epilogue (decided per step:
+        # tf32 / bf16 math modes, geometry taken by dnb_conv2d_pool_act_fwd)
+        for l in self.fts_layers:
+            if type(l) is Conv2D:
+                cons = consumers.get(id(l), [])
+                l._tcp = None
+                if (len(cons) == 1 and isinstance(cons[0], MaxPool2D) and cons[0]._pa is not None and l not in self.l_out
+                        and not os.environ.get("DNPY_B200_NO_CPA_TC")):
+                    l._tcp = cons[0]
 
     def fts(self):
         self.fts_layers = list(self.bts_layers)

@@ -132,6 +132,15 @@ size_t dnb_conv_pool_act_bwd_literal_ws_bytes(const dnb_win_t* conv, const dnb_w
 int dnb_conv_pool_act_bwd_literal(const float* x, const float* act_delta, const uint8_t* idx_gate, float* gw, float* gb,
                                   const dnb_win_t* conv, const dnb_win_t* pool, float alpha, float inv_m, void* ws,
                                   dnb_stream_t stream);
+/* Conv2D -> MaxPool2D -> LeakyRelu/Relu behind a TENSOR-CORE convolution (the shifted-view tcgen05 kernels: stride 1, 32*k
+ * input channels, one band per image — conv2 of the CNN; tf32 / bf16 math modes): the epilogue stages the output image in
+ * shared memory and pools it there, so only act_out and idx_gate (one byte per pooled element: argmax offset | gate << 4) are
+ * written — convolution.py:193-225 + pooling.py:43-99 + activations.py:17-19.  The backward pair is dnb_pool_act_bwd (it
+ * rebuilds the convolution's dY) followed by dnb_conv2d_bwd. */
+int dnb_conv2d_pool_act_supported(const dnb_win_t* conv, const dnb_win_t* pool, int math);
+int dnb_conv2d_pool_act_fwd(const float* x, const float* w, const float* b, float* act_out, uint8_t* idx_gate,
+                            const dnb_win_t* conv, const dnb_win_t* pool, float alpha, void* ws, int math,
+                            dnb_stream_t stream);
 /* MaxPool2D -> LeakyRelu/Relu where the activation is the pool's only consumer (pooling.py:43-99 + activations.py:17-22).
  * Forward: ONLY the activation's output and one byte per pooled element (argmax offset | gate << 4) are written, 5 bytes per
  * pooled element instead of 16 (pool output, int32 argmax, activation output).  Backward (per-sample routing):

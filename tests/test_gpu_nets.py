@@ -593,6 +593,12 @@ def test_fused_pool_act_pair(math, pool_geom, ns):
         net.feed_input([x])
         net.forward()
         assert isinstance(pool.output, LazyDArray) and not pool.output.materialised, "fused forward did not run"
+        # in the tensor-core modes the pair runs in the EPILOGUE of the tcgen05 convolution where the kernel takes the geometry
+        # (dnb_conv2d_pool_act_fwd: the convolution output never reaches HBM either)
+        in_epilogue = isinstance(conv.output, LazyDArray)
+        assert in_epilogue == conv._tcp_usable(batch), (math, pool_geom, in_epilogue)
+        if pool_geom[:2] == ((3, 3), (2, 2)):              # the CNN's own geometry
+            assert in_epilogue == (math == "bf16")
         lo, de = net.compute_losses(y_target=[y])
         want = onet.step([x], [y])[0]
         assert abs(lo[0] - want) <= max(tol, 2e-5) * max(1.0, abs(want))
@@ -605,6 +611,7 @@ def test_fused_pool_act_pair(math, pool_geom, ns):
         net.do_delta(de)
         net.backward()
         assert not pool.output.materialised, "the backward pass must not need the pooled pre-activation"
+        assert not (in_epilogue and conv.output.materialised), "nor the convolution output"
         for l, n in zip(net.fts_layers, onet.fts):
             for k, g in n.grads.items():
                 a = np.asarray(l.grads[k]).reshape(g.shape)
@@ -614,6 +621,7 @@ def test_fused_pool_act_pair(math, pool_geom, ns):
             assert rel_err(np.asarray(conv.delta), o_conv.delta) <= 1e-5       # dY rebuilt from the byte tensor
         # everything the fused forward / backward skipped, on demand (the layer-by-layer kernels)
         assert rel_err(np.asarray(pool.output), o_pool.output) <= tol
+        assert rel_err(np.asarray(conv.output), o_conv.output) <= tol
         if math == "fp32":
             assert rel_err(np.asarray(pool.delta), o_pool.delta) <= 1e-5
         # the captured step graph: fused pair against the two layers run separately, free running (momentum SGD: parameter
@@ -624,6 +632,7 @@ def test_fused_pool_act_pair(math, pool_geom, ns):
             if not fused:
                 p2._pa = None
                 a2._cpa_block = None
+                c2._tcp = None
             n2.set_mode("train")
             for s in range(4):
                 n2.train_step([x[:256]], [y[:256]])
