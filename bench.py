@@ -130,6 +130,14 @@ def algo_work(layer, kernel, B):
         byts = B * c * h * w * s + npool * (s + 1)
         fl = 2.0 * B * f * oh * ow * c * 9 if kernel.endswith("fwd") else 2.0 * npool * 10
         return byts, fl
+    if kernel == "tc_conv2d_pool_act_fwd":
+        # Conv2D -> MaxPool2D -> LeakyRelu in one tcgen05 launch: the image in, 5 bytes per pooled element out; the FLOPs of
+        # the convolution
+        pool = layer._tcp
+        c, h, w = layer.parents[0].oshape
+        f, oh, ow = layer.oshape
+        kh, kw = layer.kernel_size[-2:]
+        return B * c * h * w * s + B * int(np.prod(pool.oshape)) * (s + 1), 2.0 * B * f * oh * ow * c * kh * kw
     if kind == "Embedding":
         l, d = layer.oshape
         return (B * l * (4 + d * s) if "fwd" in kernel else B * l * (4 + d * s) + layer.input_dim * d * s), 0.0
@@ -174,6 +182,10 @@ def algo_work(layer, kernel, B):
         nin, nout = B * c * h * w, B * c * oh * ow
         if kernel == "maxpool2d_fwd":
             return (nin + 2 * nout) * s, 0.0
+        if kernel == "maxpool2d_act_fwd":                   # pool + activation: the planes in, value + byte per pooled element out
+            return nin * s + nout * (s + 1), 0.0
+        if kernel == "pool_act_bwd":                        # activation delta + byte per pooled element in, the planes out
+            return nin * s + nout * (s + 1), 0.0
         if kernel == "maxpool2d_bwd_last_top":
             return min(B, 128) * c * oh * ow * s, 0.0       # argmax offsets of the newest 128 samples
         if kernel == "maxpool2d_bwd_last":

@@ -47,15 +47,20 @@ enum { LOSS_CE = 0, LOSS_CE_SM = 1, LOSS_BCE = 2, LOSS_MSE = 3, LOSS_RMSE = 4, L
 
 __device__ __forceinline__ int bad_bits(float v) { return (v != v ? 4 : 0) | (isinf(v) ? 8 : 0); }
 
+// One launch per loss: a warp per row writes the delta and the row's loss term; the LAST CTA to finish (ticket counter in the
+// workspace) adds the row terms in a fixed order — run-to-run deterministic — writes [loss, flags] and leaves the counter and
+// the flags zeroed for the next call (the workspace is zeroed once by its owner; no memset / finish launches per step).
 template <int KIND>
 __global__ void __launch_bounds__(256) loss_rows_kernel(const float* __restrict__ p, const float* __restrict__ t,
                                                         float* __restrict__ delta, float* __restrict__ rows,
-                                                        int* __restrict__ flags, int B, int n) {
+                                                        int* __restrict__ flags, float* __restrict__ out, int B, int n,
+                                                        float scale, int root) {
+    __shared__ float red[32];
+    __shared__ unsigned s_ticket;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= B) return;
     float acc = 0.f;
     int bits = 0;
-    for (int j = lane; j < n; j += 32) {
+    for (int j = lane; row < B && j < n; j += 32) {
         size_t i = (size_t)row * n + j;
         float pv = p[i], tv = t[i], d, v;
         if (KIND == LOSS_CE || KIND == LOSS_CE_SM) {
@@ -90,24 +95,28 @@ __global__ void __launch_bounds__(256) loss_rows_kernel(const float* __restrict_
     acc = warp_sum(acc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
-    if (lane == 0) {
+    if (lane == 0 && row < B) {
         rows[row] = acc;
         if (bits) atomicOr(flags, bits);
     }
-}
-
-__global__ void __launch_bounds__(1024) loss_finish_kernel(const float* __restrict__ rows, const int* __restrict__ flags,
-                                                           float* __restrict__ out, int B, float scale, int root) {
-    __shared__ float red[32];
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < B; i += 1024) acc += rows[i];
-    float s = block_sum<1024>(acc, red);
+    unsigned* ticket = reinterpret_cast<unsigned*>(flags + 1);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < B; i += 256) sum += __ldcg(rows + i);
+    const float tot = block_sum<256>(sum, red);
     if (threadIdx.x == 0) {
-        float loss = s * scale;
+        float loss = tot * scale;
         if (root) loss = sqrtf(loss);                       // RMSE
-        int f = *flags | (loss != loss ? 1 : 0) | (isinf(loss) ? 2 : 0);
+        const int f = __ldcg(flags) | (loss != loss ? 1 : 0) | (isinf(loss) ? 2 : 0);
         out[0] = loss;
         out[1] = (float)f;
+        *flags = 0;
+        *ticket = 0u;
     }
 }
 
@@ -117,12 +126,8 @@ static int run_loss(const char* name, const float* p, const float* t, float* del
     DNB_CHECK_ARG(B > 0 && n > 0, "%s: empty batch", name);
     DNB_CHECK_ARG(p && t && delta && out && ws, "%s: null pointer", name);
     float* rows = static_cast<float*>(ws);
-    int* flags = reinterpret_cast<int*>(rows + B);
-    cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int), st);
-    if (e != cudaSuccess) return set_err(DNB_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e));
-    loss_rows_kernel<KIND><<<(B + 7) / 8, 256, 0, st>>>(p, t, delta, rows, flags, B, n);
-    DNB_LAUNCH_CHECK(name);
-    loss_finish_kernel<<<1, 1024, 0, st>>>(rows, flags, out, B, scale, KIND == LOSS_RMSE ? 1 : 0);
+    int* flags = reinterpret_cast<int*>(rows + B);          // [flags, ticket]: zero on entry, left zero on exit
+    loss_rows_kernel<KIND><<<(B + 7) / 8, 256, 0, st>>>(p, t, delta, rows, flags, out, B, n, scale, KIND == LOSS_RMSE ? 1 : 0);
     DNB_LAUNCH_CHECK(name);
     return DNB_OK;
 }

@@ -64,7 +64,10 @@ bool make_tmap_bf16_sw64(CUtensorMap* out, const void* base, int rank, const uin
     return r == CUDA_SUCCESS;
 }
 
-constexpr int BM = 128, BK = 32, STAGES = 4;
+constexpr int BM = 128, BK = 32;
+// ring depth: a TMA round trip is ~0.8 us on B200, so a k block costs latency / stages while the ring is latency bound —
+// as many stages as fit next to the epilogue staging (BN = 128: 6 x 32 KB, BN = 64: 8 x 24 KB, BN = 32: 10 x 20 KB)
+template <int BN> struct GemmStages { static constexpr int value = BN == 128 ? 6 : (BN == 64 ? 8 : 10); };
 constexpr int GEMM_THREADS = 192;     // warp 0: TMA, warp 1: MMA issue, warps 2-5: epilogue
 
 struct GemmParams {
@@ -86,7 +89,7 @@ __device__ __forceinline__ void gemm_stamp(const GemmParams& p, int slot) {
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
-    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGES = GemmStages<BN>::value;
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms
@@ -189,44 +192,72 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 *reinterpret_cast<float4*>(stg + rl * PITCH + c0 + j) =
                     make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         }
+        if (warp == 2 && lane == 0) gemm_stamp(p, 5);
         asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps
+        if (warp == 2 && lane == 0) gemm_stamp(p, 6);
         const bool vec = (p.N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
-        for (int r = warp - 2; r < BM; r += 4) {
-            const int grow = m0 + r;
-            if (grow >= p.M) break;
-            for (int c4 = lane; c4 < BN / 4; c4 += 32) {
-                const int col = n0 + c4 * 4;
-                if (col >= p.N) continue;
-                const float4 a4 = *reinterpret_cast<const float4*>(stg + r * PITCH + c4 * 4);
-                float a[4] = {a4.x, a4.y, a4.z, a4.w};
-                const size_t o = (size_t)grow * p.N + col;
-                const int nv = min(4, p.N - col);
-                if (!p.grad) {
+        // a lane owns ONE 4-column group of the tile (BN <= 128): everything that depends on the column only — the bias,
+        // the regulariser term of a weight-gradient tile — stays out of the row loop, and the rows go RB at a time (loads of
+        // all RB rows in flight before the first store: the loop is latency bound otherwise, ~5 us per tile on B200)
+        static_assert(BN / 4 <= 32, "one column group per lane");
+        const int c4 = lane, col = n0 + c4 * 4;
+        if (c4 < BN / 4 && col < p.N) {
+            const int nv = min(4, p.N - col);
+            float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (!p.grad && p.bias)
+                for (int e = 0; e < nv; ++e) bias4[e] = __ldg(p.bias + col + e);
+            const bool reg = p.grad && blockIdx.z == 0 && (p.l1 != 0.f || p.l2 != 0.f);
+            constexpr int RB = 8;
+            for (int r0 = warp - 2; r0 < BM; r0 += 4 * RB) {
+                float a[RB][4], c[RB][4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) if (e < nv && p.bias) a[e] += __ldg(p.bias + col + e);
-                    if (vec) *reinterpret_cast<float4*>(p.C + o) = make_float4(a[0], a[1], a[2], a[3]);
-                    else for (int e = 0; e < nv; ++e) p.C[o + e] = a[e];
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        a[e] *= p.inv_m;
-                        if (e < nv && blockIdx.z == 0 && (p.l1 != 0.f || p.l2 != 0.f)) a[e] += reg_term(p.W[o + e], p.l1, p.l2) * p.inv_m;
-                    }
-                    if (gridDim.z == 1) {
-                        if (vec) {
-                            float4 c4v = *reinterpret_cast<const float4*>(p.C + o);
-                            c4v.x += a[0]; c4v.y += a[1]; c4v.z += a[2]; c4v.w += a[3];
-                            *reinterpret_cast<float4*>(p.C + o) = c4v;
-                        } else {
-                            for (int e = 0; e < nv; ++e) p.C[o + e] += a[e];
+                for (int u = 0; u < RB; ++u) {
+                    const int r = r0 + 4 * u, grow = m0 + r;
+                    if (r < BM && grow < p.M) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(stg + r * PITCH + c4 * 4);
+                        a[u][0] = a4.x; a[u][1] = a4.y; a[u][2] = a4.z; a[u][3] = a4.w;
+                        const size_t o = (size_t)grow * p.N + col;
+                        if (p.grad && gridDim.z == 1) {
+                            if (vec) {
+                                const float4 c4v = *reinterpret_cast<const float4*>(p.C + o);
+                                c[u][0] = c4v.x; c[u][1] = c4v.y; c[u][2] = c4v.z; c[u][3] = c4v.w;
+                            } else {
+                                for (int e = 0; e < nv; ++e) c[u][e] = p.C[o + e];
+                            }
                         }
-                    } else {
-                        for (int e = 0; e < nv; ++e) atomicAdd(p.C + o + e, a[e]);
+                        if (reg)
+                            for (int e = 0; e < nv; ++e) c[u][e] = (p.grad && gridDim.z == 1 ? c[u][e] : 0.f) + reg_term(p.W[o + e], p.l1, p.l2) * p.inv_m;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < RB; ++u) {
+                    const int r = r0 + 4 * u, grow = m0 + r;
+                    if (r < BM && grow < p.M) {
+                        const size_t o = (size_t)grow * p.N + col;
+                        if (!p.grad) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) a[u][e] += bias4[e];
+                            if (vec) *reinterpret_cast<float4*>(p.C + o) = make_float4(a[u][0], a[u][1], a[u][2], a[u][3]);
+                            else for (int e = 0; e < nv; ++e) p.C[o + e] = a[u][e];
+                        } else if (gridDim.z == 1) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) a[u][e] = a[u][e] * p.inv_m + c[u][e];
+                            if (vec) *reinterpret_cast<float4*>(p.C + o) = make_float4(a[u][0], a[u][1], a[u][2], a[u][3]);
+                            else for (int e = 0; e < nv; ++e) p.C[o + e] = a[u][e];
+                        } else if (vec) {           // split-K partial: one 16-byte vector reduction per lane
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.C + o),
+                                         "f"(a[u][0] * p.inv_m + (reg ? c[u][0] : 0.f)), "f"(a[u][1] * p.inv_m + (reg ? c[u][1] : 0.f)),
+                                         "f"(a[u][2] * p.inv_m + (reg ? c[u][2] : 0.f)), "f"(a[u][3] * p.inv_m + (reg ? c[u][3] : 0.f))
+                                         : "memory");
+                        } else {
+                            for (int e = 0; e < nv; ++e) atomicAdd(p.C + o + e, a[u][e] * p.inv_m + (reg ? c[u][e] : 0.f));
+                        }
                     }
                 }
             }
         }
     }
+    if (warp == 2 && lane == 0) gemm_stamp(p, 7);
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) gemm_stamp(p, 4);
@@ -235,7 +266,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 template <int BN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int splits, cudaStream_t st) {
-    constexpr size_t smem = STAGES * (BM * BK * 4 + BN * BK * 4) + 256 + 1024;
+    constexpr size_t smem = GemmStages<BN>::value * (BM * BK * 4 + BN * BK * 4) + 256 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -264,7 +295,12 @@ int tc_gemm(const float* A, const float* B, float* C, int M, int N, int K, int f
     const int a_mn = (flags & TC_A_MMAJOR) ? 1 : 0, b_mn = (flags & TC_B_NMAJOR) ? 1 : 0, grad = (flags & TC_ACCUM_GRAD) ? 1 : 0;
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
         return set_err(DNB_ERR_INVALID, "tc_gemm: operands must be 16-byte aligned");
-    const int BN = N >= 96 ? 128 : (N >= 48 ? 64 : 32);
+    int BN = N >= 96 ? 128 : (N >= 48 ? 64 : 32);
+    // small problems: narrower N tiles until the grid covers most of the SMs — a CTA pulls its operands from L2 at
+    // ~64 B/clk, so a 32-CTA grid leaves the k loop (270 ns per 32-wide k block at BN = 128) bound by per-SM L2 bandwidth
+    // (weight gradients fill the machine by splitting K instead)
+    if (!grad)
+        while (BN > 32 && ((M + BM - 1) / BM) * ((N + BN - 1) / BN) < (kNumSMs * 3) / 4) BN >>= 1;
     CUtensorMap ta, tb;
     uint64_t dims[2], str[1];
     uint32_t box[2];
@@ -294,8 +330,8 @@ int tc_gemm(const float* A, const float* B, float* C, int M, int N, int K, int f
         unsigned long long h[8];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, p.prof, sizeof(h), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[gemm prof] M=%d N=%d K=%d BN=%d splits=%d: setup %llu ns, first stage landed +%llu, accumulator complete +%llu, epilogue done +%llu\n",
-                M, N, K, BN, splits, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0]);
+        fprintf(stderr, "[gemm prof] M=%d N=%d K=%d BN=%d splits=%d: setup %llu ns, first stage landed +%llu, accumulator complete +%llu (staged +%llu, barrier +%llu, stored +%llu), epilogue done +%llu\n",
+                M, N, K, BN, splits, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[4] - h[0]);
     }
     return rc;
 }

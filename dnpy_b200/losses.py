@@ -45,7 +45,8 @@ class Loss:
         bufs = self._bufs.get(key)
         if bufs is None:
             ws_bytes = _lib.load().dnb_loss_ws_bytes(b)
-            bufs = (DArray.device(dev_empty((b, n))), dev_empty((2,)), dev_empty(((ws_bytes + 3) // 4,)))
+            # the workspace carries the kernel's [flags, ticket] words: zeroed ONCE here, every launch leaves them zeroed
+            bufs = (DArray.device(dev_empty((b, n))), dev_empty((2,)), dev_empty(((ws_bytes + 3) // 4,)).zero_())
             self._bufs = {key: bufs}
         delta, out, ws = bufs
         # mean over the LOCAL rows; under data parallelism Net averages the per-rank means when it reports

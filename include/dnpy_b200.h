@@ -268,7 +268,8 @@ int dnb_rnn_bwd(const float* x, const float* states, const float* dy, const floa
 /* ---- Losses (dnpy/losses.py) + the NaN/Inf guard of net.py:342-350 ---------- */
 /* out[0] = loss, out[1] = flag bits: 1 NaN loss, 2 Inf loss, 4 NaN delta, 8 Inf delta.
  * Deltas are never divided by the batch (Q17).  loss_scale = 1/B (1/B_global when sharded).
- * ws: dnb_loss_ws_bytes(B) bytes. */
+ * ws: dnb_loss_ws_bytes(B) bytes, ZERO-FILLED by its owner before the first call; every call leaves it ready for the next
+ * (it carries the ticket counter through which the last CTA of the single launch reduces the row terms in a fixed order). */
 size_t dnb_loss_ws_bytes(int B);
 int dnb_loss_ce(const float* p, const float* t, float* delta, float* out, int B, int n,
                 int softmax_output, float loss_scale, void* ws, dnb_stream_t stream);   /* :82-94 */
