@@ -501,7 +501,7 @@ class Harness:
             else:
                 ach = byts / (per_launch_ms * 1e-3) / 1e9
                 r = dict(bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"])
-            r.update(traffic=traffic_tab.get(kname), kernel=f"{tag}/{kname}", ms_per_launch=per_launch_ms,
+            r.update(traffic=traffic_tab.get(f"{tag}/{kname}", traffic_tab.get(kname)), kernel=f"{tag}/{kname}", ms_per_launch=per_launch_ms,
                      share_of_step=e["ms"] / total_ms, algorithmic_bytes=byts, algorithmic_flops=flops, peak_source=pk["source"])
             if flops > 0:
                 r["algorithmic_tflops"] = flops / (per_launch_ms * 1e-3) / 1e12      # fp32 SIMT kernels: of ~72 TFLOP/s nominal
