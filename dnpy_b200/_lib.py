@@ -106,6 +106,12 @@ SIGNATURES = {
     "dnb_opt_adam": (_i, [_p, _p, _p, _p, _z, _f, _f, _f, _f, _p]),
     "dnb_opt_rmsprop": (_i, [_p, _p, _p, _z, _f, _f, _f, _p]),
     "dnb_opt_sgd": (_i, [_p, _p, _p, _z, _f, _f, _i, _p]),
+    "dnb_dp_flag_bytes": (_z, []),
+    "dnb_ipc_alloc": (_i, [C.POINTER(_p), _z, _p]),
+    "dnb_ipc_open": (_i, [_p, C.POINTER(_p)]),
+    "dnb_ipc_close": (_i, [_p]),
+    "dnb_ipc_free": (_i, [_p]),
+    "dnb_dp_allreduce": (_i, [C.POINTER(_p), C.POINTER(_p), _p, _z, _i, _i, _p]),
     "dnb_gemm_tf32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
 }
 

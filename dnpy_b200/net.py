@@ -245,6 +245,17 @@ class Net:
             pos += (l.params[k].size + _ALIGN - 1) // _ALIGN * _ALIGN
         total = max(pos, _ALIGN)
         P, G = dev_zeros((total,)), dev_zeros((total,))
+        peer = None
+        if self._arena is not None and self._arena.get("peer") is not None:
+            self._arena["peer"].close()             # the arena is being rebuilt (set_params replaced the dicts)
+        if config.world > 1:
+            # data parallel on one node: the gradient arena lives in CUDA-IPC memory every rank maps; the exchange is one kernel
+            # over NVLink peer memory (parallel.PeerArena, csrc/dp_peer.cu) instead of NCCL all-reduces
+            from . import parallel
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_backend() == "nccl" and parallel.peer_exchange_possible():
+                peer = parallel.PeerArena(total)
+                G = peer.tensor[:total]
         states = {}
         kind = type(self.optimizer).__name__
         for name in ("V", "S"):
@@ -264,7 +275,7 @@ class Net:
                 st = getattr(opt, name)
                 if k in st:
                     st[k].bind(arena[o:o + n].view(*shape))
-        self._arena = dict(P=P, G=G, states=states, total=total, uniform=uniform, offsets=offs,
+        self._arena = dict(P=P, G=G, states=states, total=total, uniform=uniform, offsets=offs, peer=peer,
                            keys=[(id(l.params[k]), id(l.grads[k])) for l, k in slots], slots=slots)
         self._graphs = {}
         return self._arena
@@ -362,18 +373,23 @@ class Net:
                 l.print_stats()
 
     def backward(self):
-        buckets = None
+        buckets = peer = None
         if config.world > 1:
             from . import parallel
-            buckets = parallel.GradBuckets(self)
+            peer = self._bind_arenas()["peer"]
+            if peer is None:
+                buckets = parallel.GradBuckets(self)
         for l in self.bts_layers:
             l.backward()
             if self.debug:
                 l.print_stats()
             if buckets is not None:
                 buckets.layer_done(l)          # this layer's gradients are final: start their all-reduce now
+        if peer is not None:
+            peer.allreduce()                   # one kernel: every rank's arena now holds the global sum
         if buckets is not None:
             buckets.finish()
+        if peer is not None or buckets is not None:
             for l, k in self._arena["slots"]:
                 l.grads[k].written()
 

@@ -105,6 +105,84 @@ def allreduce_grads(net):
         l.grads[k].written()
 
 
+class _RawCuda:
+    """A raw device allocation behind the CUDA array interface (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr="<f4", data=(int(ptr), False), version=2)
+
+
+class PeerArena:
+    """The flat gradient arena in CUDA-IPC memory that every rank of the node maps, and the one-kernel exchange over it
+    (csrc/dp_peer.cu: flags + 16-byte loads through NVLink / NVSwitch peer memory, no NCCL call on the step path).
+    ``tensor`` is this rank's arena as a torch tensor; ``allreduce()`` leaves the global sum in it on every rank."""
+
+    def __init__(self, nfloats):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        lib = _lib.load()
+        self.n = (int(nfloats) + 3) // 4 * 4
+        self.rank, self.world = config.rank, config.world
+
+        def alloc(nbytes):
+            ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+            _lib.check(lib.dnb_ipc_alloc(C.byref(ptr), nbytes, handle))
+            return ptr.value, handle.raw
+        self._own = [alloc(self.n * 4), alloc(int(lib.dnb_dp_flag_bytes()))]
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, [h for _, h in self._own])
+        self._opened = []
+        ptrs = [[], []]
+        for r in range(self.world):
+            for j in range(2):
+                if r == self.rank:
+                    ptrs[j].append(self._own[j][0])
+                else:
+                    p = C.c_void_p()
+                    _lib.check(lib.dnb_ipc_open(gathered[r][j], C.byref(p)))
+                    self._opened.append(p.value)
+                    ptrs[j].append(p.value)
+        self._bufs = (C.c_void_p * self.world)(*ptrs[0])
+        self._flags = (C.c_void_p * self.world)(*ptrs[1])
+        self._raw = _RawCuda(self._own[0][0], self.n)
+        self.tensor = torch.as_tensor(self._raw, device="cuda")
+        self.scratch = torch.empty(self.n, dtype=torch.float32, device="cuda")
+        dist.barrier()                              # every rank has mapped every arena before the first exchange
+
+    def close(self):
+        """Unmap the peers' arenas and free this rank's (every rank must call it at the same point)."""
+        import torch
+        import torch.distributed as dist
+        lib = _lib.load()
+        torch.cuda.synchronize()
+        dist.barrier()                              # nobody is still reading this arena
+        for p in self._opened:
+            lib.dnb_ipc_close(p)
+        self._opened = []
+        dist.barrier()
+        for p, _ in self._own:
+            lib.dnb_ipc_free(p)
+        self._own = []
+
+    def allreduce(self):
+        from .darray import stream_ptr
+        _lib.call("dnb_dp_allreduce", self._bufs, self._flags, self.scratch.data_ptr(), self.n, self.rank, self.world,
+                  stream_ptr())
+
+
+def peer_exchange_possible():
+    """All ranks on one node, NCCL backend (one GPU per rank or a shared test GPU), not switched off (DNPY_B200_DP_PEER=0)."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    if config.world < 2 or config.world > 8 or os.environ.get("DNPY_B200_DP_PEER", "1") == "0" or not torch.cuda.is_available():
+        return False
+    hosts = [None] * config.world
+    dist.all_gather_object(hosts, socket.gethostname())
+    return len(set(hosts)) == 1
+
+
 class GradBuckets:
     """Bucketed, overlapped gradient exchange.  The arena is laid out in backward order (Net._trainable walks
     bts_layers), so the gradients of the layers that have ALREADY run backward form a growing prefix: after a layer

@@ -305,6 +305,19 @@ int dnb_opt_sgd(float* p, const float* g, float* v, size_t n, float lr, float mo
 int dnb_gemm_tf32(const float* A, const float* Bm, float* C, int M, int N, int K,
                   int a_mmajor, int b_nmajor, dnb_stream_t stream);
 
+/* ---- data-parallel gradient exchange over NVLink / NVSwitch peer memory (csrc/dp_peer.cu) ----------------------------
+ * The shard of Net.fit's minibatch loop (net.py:176-195) across the GPUs of one box needs ONE exchange per step: the sum of
+ * the flat gradient arenas.  dnb_ipc_alloc gives zero-filled device memory plus a 64-byte handle another process of the node
+ * maps with dnb_ipc_open; dnb_dp_allreduce is one kernel per rank and step (flags and 16-byte loads through peer memory, ranks
+ * summed in order 0..N-1 so the replicas stay bit-identical): bufs[r] / flags[r] are rank r's arena and flag block
+ * (dnb_dp_flag_bytes, one block per arena) as mapped in the calling process, n a multiple of 4, scratch n local floats. */
+size_t dnb_dp_flag_bytes(void);
+int dnb_ipc_alloc(void** ptr, size_t bytes, void* handle_out64);
+int dnb_ipc_open(const void* handle64, void** ptr);
+int dnb_ipc_close(void* ptr);
+int dnb_ipc_free(void* ptr);
+int dnb_dp_allreduce(void* const* bufs, void* const* flags, float* scratch, size_t n, int rank, int world, dnb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
