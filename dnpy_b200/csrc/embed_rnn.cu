@@ -10,6 +10,7 @@
 // full-length dh chain PLUS a truncated inner loop at every t, (1-h^2) applied before the Waa
 // product, gradients summed (not averaged) over the batch.
 #include "common.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace dnb {
@@ -254,7 +255,14 @@ __global__ void rnn_bwd_kernel(const float* __restrict__ x, const float* __restr
 // T=256 on B200.  Here a sample's vectors live one element per lane; matrix-vector products read the other lanes' elements
 // from a per-warp shared scratch with broadcast LDS.128 (a quarter of the MIO operations of shuffles); the lane's
 // columns of Waa / Wax and its rows of the gradient accumulators stay in registers; no block barrier in the time loop.
+// LAGSUM (MAXL > 0, at most MAXL = trunc + 1 lags): the weight gradients of the literal truncated BPTT are linear in the lag
+// vectors S_k(t), and both pair every S_k(t) with data of step t - k (h_{t-k-1} and x_{t-k}): with
+//     W(u) = sum_k S_k(u + k)        gWaa = sum_u W(u) (x) h_{u-1},   gWax = sum_u W(u) (x) x_u,   gba = sum_u W(u)
+// the two outer products run ONCE per step instead of once per (step, lag).  W lives in a register ring: lag k of step t adds
+// into slot k, the ring shifts down once per step, slot 0 is complete when step t is done (t runs downwards).  The inner loop
+// keeps only the recurrence S <- (S (1 - h^2)) . Waa: 8 broadcast LDS.128 + 32 FMAs instead of 18 + 72.
 constexpr int RW_WARPS = 8;
+template <int MAXL>
 __global__ void __launch_bounds__(RW_WARPS * 32, 1)
 rnn_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ states, const float* __restrict__ dy,
                     const float* __restrict__ waa, const float* __restrict__ wax,
@@ -287,15 +295,79 @@ rnn_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ state
         return (c0 + c1) + (c2 + c3);
     };
     float dh = 0.f;
+    float wr[MAXL > 0 ? MAXL : 1];                                  // the lag-sum ring W(t), W(t-1), ...
+#pragma unroll
+    for (int j = 0; j < (MAXL > 0 ? MAXL : 1); ++j) wr[j] = 0.f;
     if (act) {
         const float* hs = states + (size_t)b * T * H;
         const float* xs = x + (size_t)b * T * D;
+        // LAGSUM: the states h_t .. h_{t-MAXL} of a step live in a register ring (ONE new global load per step, issued a whole
+        // step ahead of its first use, like x_t and the next step's x): no global latency on the serial chain
+        float hr[(MAXL > 0 ? MAXL : 0) + 1];
+        float x_next = 0.f;
+        if constexpr (MAXL > 0) {
+#pragma unroll
+            for (int j = 0; j <= MAXL; ++j) hr[j] = (T - 1 - j >= 0 && lane < H) ? __ldg(hs + (size_t)(T - 1 - j) * H + lane) : 0.f;
+            x_next = lane < D ? __ldg(xs + (size_t)(T - 1) * D + lane) : 0.f;
+        }
         for (int t = T - 1; t >= 0; --t) {
-            const float h = lane < H ? __ldg(hs + (size_t)t * H + lane) : 0.f;
+            float h;
+            float h_new = 0.f, xk_cur = 0.f;
+            if constexpr (MAXL > 0) {
+                h = hr[0];
+                xk_cur = x_next;
+                h_new = (t - MAXL - 1 >= 0 && lane < H) ? __ldg(hs + (size_t)(t - MAXL - 1) * H + lane) : 0.f;   // first used next step
+                x_next = (t > 0 && lane < D) ? __ldg(xs + (size_t)(t - 1) * D + lane) : 0.f;
+            } else {
+                h = lane < H ? __ldg(hs + (size_t)t * H + lane) : 0.f;
+            }
             const float d0 = (t == T - 1 && lane < H) ? __ldg(dy + (size_t)b * H + lane) : 0.f;
             const float pre = (d0 + dh) * (1.f - h * h);
             float S = pre;
             const int k_lo = max(0, t - trunc);
+            if constexpr (MAXL > 0) {
+                const int nl = t - k_lo + 1;                       // lags of this step (<= MAXL)
+#pragma unroll
+                for (int j = 0; j < MAXL; ++j) {
+                    if (j < nl) {
+                        wr[j] += S;
+                        if (j + 1 < nl) {                          // the recurrence is only needed while another lag follows
+                            const float hp = hr[j + 1];           // h_{t-j-1} (0 before the sequence starts)
+                            __syncwarp();
+                            su[lane] = S * (1.f - hp * hp);
+                            __syncwarp();
+                            S = dot32(su, wcol);                   // S <- (S * (1 - h_{k-1}^2)) . Waa   (recurrent.py:240)
+                        }
+                    }
+                }
+                // W(t) = wr[0] is complete: gWaa[lane][q] += W(t) h_{t-1}[q], gWax[lane][d] += W(t) x_t[d], gba += W(t)
+                const float wt = wr[0];
+                __syncwarp();
+                sh[lane] = hr[1];
+                sx[lane] = xk_cur;
+                __syncwarp();
+                ab += wt;
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(sh + 4 * q4);
+                    aw[4 * q4] = fmaf(wt, t4.x, aw[4 * q4]); aw[4 * q4 + 1] = fmaf(wt, t4.y, aw[4 * q4 + 1]);
+                    aw[4 * q4 + 2] = fmaf(wt, t4.z, aw[4 * q4 + 2]); aw[4 * q4 + 3] = fmaf(wt, t4.w, aw[4 * q4 + 3]);
+                }
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                    if (4 * q4 < D) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(sx + 4 * q4);
+                        ax[4 * q4] = fmaf(wt, t4.x, ax[4 * q4]); ax[4 * q4 + 1] = fmaf(wt, t4.y, ax[4 * q4 + 1]);
+                        ax[4 * q4 + 2] = fmaf(wt, t4.z, ax[4 * q4 + 2]); ax[4 * q4 + 3] = fmaf(wt, t4.w, ax[4 * q4 + 3]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j + 1 < MAXL; ++j) wr[j] = wr[j + 1];
+                wr[MAXL - 1] = 0.f;
+#pragma unroll
+                for (int j = 0; j < MAXL; ++j) hr[j] = hr[j + 1];
+                hr[MAXL] = h_new;
+            } else {
             float hp_n = (t > 0 && lane < H) ? __ldg(hs + (size_t)(t - 1) * H + lane) : 0.f;
             float xk_n = lane < D ? __ldg(xs + (size_t)t * D + lane) : 0.f;
             for (int k = t; k >= k_lo; --k) {
@@ -325,6 +397,7 @@ rnn_bwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ state
                     }
                 }
                 S = dot32(su, wcol);                               // S <- (S * (1 - h_{k-1}^2)) . Waa   (recurrent.py:240)
+            }
             }
             // dh <- pre . Waa ; dx_t = pre . Wax
             __syncwarp();
@@ -453,8 +526,14 @@ int dnb_rnn_bwd(const float* x, const float* states, const float* dy, const floa
     DNB_CHECK_ARG(x && states && dy && waa && wax && dx && gwaa && gwax && gba, "rnn_bwd: null pointer");
     if (H > 256) return set_err(DNB_ERR_UNSUPPORTED, "rnn_bwd: hidden_dim %d > 256 not supported", H);
     if (H <= 32 && D <= 32 && !getenv("DNB_RNN_TILE_BWD")) {
-        rnn_bwd_warp_kernel<<<(B + RW_WARPS - 1) / RW_WARPS, RW_WARPS * 32, 0, S(stream)>>>(x, states, dy, waa, wax, dx, gwaa, gwax, gba,
-                                                                                              B, T, D, H, trunc);
+        const int nl = std::min(T, trunc + 1);                        // lags per step
+        const dim3 grid((B + RW_WARPS - 1) / RW_WARPS);
+        if (nl <= 4 && !getenv("DNB_RNN_NO_LAGSUM"))
+            rnn_bwd_warp_kernel<4><<<grid, RW_WARPS * 32, 0, S(stream)>>>(x, states, dy, waa, wax, dx, gwaa, gwax, gba, B, T, D, H, trunc);
+        else if (nl <= 8 && !getenv("DNB_RNN_NO_LAGSUM"))
+            rnn_bwd_warp_kernel<8><<<grid, RW_WARPS * 32, 0, S(stream)>>>(x, states, dy, waa, wax, dx, gwaa, gwax, gba, B, T, D, H, trunc);
+        else
+            rnn_bwd_warp_kernel<0><<<grid, RW_WARPS * 32, 0, S(stream)>>>(x, states, dy, waa, wax, dx, gwaa, gwax, gba, B, T, D, H, trunc);
         DNB_LAUNCH_CHECK("rnn_bwd");
         return DNB_OK;
     }
