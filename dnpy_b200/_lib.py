@@ -49,6 +49,8 @@ SIGNATURES = {
     "dnb_conv_pool_act_bwd": (_i, [_p, _p, _p, _p, _p, _W, _W, _f, _f, _p]),
     "dnb_conv_pool_act_bwd_literal_ws_bytes": (_z, [_W, _W]),
     "dnb_conv_pool_act_bwd_literal": (_i, [_p, _p, _p, _p, _p, _W, _W, _f, _f, _p, _p]),
+    "dnb_conv_pool_act_tc_supported": (_i, [_W, _W, _i]),
+    "dnb_conv_pool_act_fwd_tc": (_i, [_p, _p, _p, _p, _p, _W, _W, _f, _i, _p]),
     "dnb_conv2d_pool_act_supported": (_i, [_W, _W, _i]),
     "dnb_conv2d_pool_act_fwd": (_i, [_p, _p, _p, _p, _p, _W, _W, _f, _p, _i, _p]),
     "dnb_pool_act_supported": (_i, [_W]),

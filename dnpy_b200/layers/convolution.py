@@ -102,8 +102,15 @@ class Conv2D(Conv):
         n_pool = b * int(np.prod(pool.oshape))
         aout = act._buf('out', (b, *act.oshape))
         ig = self._raw('cpa_idx_gate', n_pool)                  # one byte per pooled element: argmax offset | gate << 4
-        self._call("dnb_conv_pool_act_fwd", x.ptr(), self.params['w1'].ptr(), self.params['b1'].ptr(), aout.ptr(), ig,
-                   g, gp, float(act.alpha))
+        tc_ok = self.__dict__.setdefault("_cpa_tc_ok", {})
+        if config.math not in tc_ok:        # BF16 math mode: the block's forward on the tensor core (csrc/tc_conv_c1p.cu)
+            tc_ok[config.math] = bool(_lib.load().dnb_conv_pool_act_tc_supported(self._win(1), pool._win(1), config.math))
+        if tc_ok[config.math]:
+            self._call("dnb_conv_pool_act_fwd_tc", x.ptr(), self.params['w1'].ptr(), self.params['b1'].ptr(), aout.ptr(), ig,
+                       g, gp, float(act.alpha), config.math)
+        else:
+            self._call("dnb_conv_pool_act_fwd", x.ptr(), self.params['w1'].ptr(), self.params['b1'].ptr(), aout.ptr(), ig,
+                       g, gp, float(act.alpha))
         # the tensors the fused kernel never wrote stay observable (computed by the layer-by-layer kernels on a read)
         w_now, b_now = self._snapshot('w_snap_f', self.params['w1']), self._snapshot('b_snap_f', self.params['b1'])
         math = config.math

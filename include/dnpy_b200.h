@@ -132,6 +132,13 @@ size_t dnb_conv_pool_act_bwd_literal_ws_bytes(const dnb_win_t* conv, const dnb_w
 int dnb_conv_pool_act_bwd_literal(const float* x, const float* act_delta, const uint8_t* idx_gate, float* gw, float* gb,
                                   const dnb_win_t* conv, const dnb_win_t* pool, float alpha, float inv_m, void* ws,
                                   dnb_stream_t stream);
+/* The forward of the same block on the TENSOR CORE (csrc/tc_conv_c1p.cu; math = DNB_MATH_BF16, MNIST geometry 28x28 ->
+ * 12x12, F = 32 / 64 / 128): the 9-tap contraction runs as block-diagonal tcgen05 MMAs over 128 / F images at a time (BF16
+ * operands, fp32 accumulation, the bias carried exactly as three BF16 pieces), the epilogue pools a filter's channel in
+ * registers.  Same outputs and byte format as dnb_conv_pool_act_fwd; the backward calls above pair with either forward. */
+int dnb_conv_pool_act_tc_supported(const dnb_win_t* conv, const dnb_win_t* pool, int math);
+int dnb_conv_pool_act_fwd_tc(const float* x, const float* w, const float* b, float* act_out, uint8_t* idx_gate,
+                             const dnb_win_t* conv, const dnb_win_t* pool, float alpha, int math, dnb_stream_t stream);
 /* Conv2D -> MaxPool2D -> LeakyRelu/Relu behind a TENSOR-CORE convolution (the shifted-view tcgen05 kernels: stride 1, 32*k
  * input channels, one band per image — conv2 of the CNN; tf32 / bf16 math modes): the epilogue stages the output image in
  * shared memory and pools it there, so only act_out and idx_gate (one byte per pooled element: argmax offset | gate << 4) are

@@ -285,6 +285,50 @@ def test_tc_gemm_all_operand_orientations():
                 assert err <= 5e-3, (M, N, K, a_mn, b_mn, err)
 
 
+@pytest.mark.parametrize("B,F,alpha", [(37, 32, 0.0), (4001, 32, 0.1), (1500, 64, 0.0), (700, 128, 0.3)])
+def test_tensor_core_first_block_forward(B, F, alpha):
+    """dnb_conv_pool_act_fwd_tc (csrc/tc_conv_c1p.cu): Conv2D(1 -> F, 3x3) -> MaxPool2D(3x3 / 2) -> LeakyRelu on tcgen05 with
+    BF16 operands.  BF16 x BF16 products are exact in fp32, so against the float64 oracle evaluated on the BF16-ROUNDED image
+    and filters (the bias is carried exactly) only the fp32 accumulation order is left: values to 1e-5, argmax bytes equal
+    except at near-ties, the gate bit consistent with the value.  B = 4001: 1001 groups of four images (every CTA loops
+    over ~7 groups: raw / tile / accumulator rings wrap, both epilogue groups) with a partial last group; F = 64 / 128:
+    two / one image per MMA.  Against the un-rounded oracle (what the net-level tests see): rel 2e-2."""
+    import torch
+    from dnpy_b200 import _lib
+    from oracle import dnpy_oracle as O
+    lib = _lib.load()
+    rs = np.random.RandomState(B + F)
+    x = rs.rand(B, 1, 28, 28).astype(np.float32)
+    w = (rs.randn(F, 1, 3, 3) * 0.4).astype(np.float32)
+    b = (rs.randn(F) * 0.1).astype(np.float32)
+    g = _lib.Win(B, 1, 28, 28, F, 26, 26, 3, 3, 1, 1, 0, 0, 0, 0)
+    gp = _lib.Win(B, F, 26, 26, F, 12, 12, 3, 3, 2, 2, 0, 0, 0, 0)
+    assert lib.dnb_conv_pool_act_tc_supported(g, gp, _lib.MATH_BF16) == 1
+    assert lib.dnb_conv_pool_act_tc_supported(g, gp, _lib.MATH_FP32) == 0
+    xd, wd, bd = (torch.from_numpy(a).cuda() for a in (x, w, b))
+    act = torch.full((B, F, 12, 12), float("nan"), device="cuda")
+    ig = torch.full((B, F, 12, 12), 255, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.dnb_conv_pool_act_fwd_tc(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), act.data_ptr(), ig.data_ptr(),
+                                            g, gp, alpha, _lib.MATH_BF16, None))
+    torch.cuda.synchronize()
+    act, ig = act.cpu().numpy(), ig.cpu().numpy()
+
+    def oracle(xx, ww):
+        conv = O.conv2d_forward(xx.astype(np.float64), ww.astype(np.float64), b.astype(np.float64), (1, 1), (0, 0, 0, 0), (F, 26, 26))
+        pooled, idx = O.maxpool2d_forward(conv, (3, 3), (2, 2), (0, 0, 0, 0), (F, 12, 12))
+        return O.leakyrelu_forward(pooled, alpha), idx, pooled
+    rnd = lambda a: torch.from_numpy(a).bfloat16().float().numpy()
+    want, idx, pooled = oracle(rnd(x), rnd(w))
+    assert rel_err(act, want) <= 1e-5
+    assert float(np.mean((ig & 15) != idx)) <= 2e-4
+    clear = np.abs(pooled) > 1e-4
+    assert np.array_equal(((ig >> 4) & 1)[clear], (pooled > 0)[clear].astype(np.uint8))
+    assert np.all((ig >> 5) == 0)
+    want32, idx32, _ = oracle(x, w)
+    assert rel_err(act, want32) <= TOL_TF32
+    assert float(np.mean((ig & 15) != idx32)) <= 0.03
+
+
 @pytest.mark.parametrize("case", [c for c in cases.LAYER_CASES + BIG_CASES if c["kind"] in ("MaxPool2D", "GlobalMaxPool2D")],
                          ids=lambda c: c["name"])
 def test_maxpool_per_sample_route(case, ns):

@@ -502,9 +502,10 @@ def test_fused_conv_pool_act_block(math, route, ns):
             want = onet.step(xb, yb)[0]
             assert abs(lo[0] - want) <= (2e-5 if math == "fp32" else 2e-2) * max(1.0, abs(want))
             o_conv, o_pool, o_act = onet.fts[1], onet.fts[2], onet.fts[3]
-            assert rel_err(np.asarray(act.output), o_act.output) <= 1e-5          # the block is fp32 arithmetic in every mode
+            # fp32: the SIMT block; bf16: its forward runs on the tensor core with BF16 operands (csrc/tc_conv_c1p.cu)
+            assert rel_err(np.asarray(act.output), o_act.output) <= (1e-5 if math == "fp32" else 2e-2)
             flips = float(np.mean(np.asarray(pool.output_idxs) != o_pool.cache["idx"]))
-            assert flips <= 1e-3, flips
+            assert flips <= (1e-3 if math == "fp32" else 0.03), flips
             for l, n in zip(net.fts_layers, onet.fts):      # teacher-force the oracle's argmax (one flipped window moves ~1e-3
                 if "idx" in n.cache:                        # of a filter's gradient): the fused backward honours the assignment
                     l.output_idxs = DArray(host=n.cache["idx"], is_int=True)
