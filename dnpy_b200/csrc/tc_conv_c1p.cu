@@ -14,16 +14,21 @@
 // A chunk = 2 pooled rows = 5 conv rows x NC needed conv columns (25 of 26 for MNIST) = 125 pixel rows, N = 128; 6 chunks
 // per image group; 4 accumulator stages of 128 TMEM columns.
 //
-//   warp 0        bulk-copy producer: the G raw images of a group by ONE 1-D bulk copy (they are contiguous), ring of NRAW
-//   warp 1        A matrix (once) + MMA issue: G k-steps (M = 128, N = 128, K = 16) per chunk
-//   warps 2-3     builders: im2col of a chunk into a ring of B tiles (K-major, 128B swizzle: row n = 128 B = 4 image slots
-//                 x 16 BF16), 9 LDS + 5 cvt.pack + 2 STS.128 per (pixel, image)
+//   warp 0        raw images (the G images of a group are contiguous: ONE 1-D bulk copy, ring of 4 groups, requested as
+//                 soon as the builders have left a slot) + MMA issue: G k-steps (M = 128, N = 128, K = 16) per chunk
+//   warps 1-3     builders: im2col of a chunk into a ring of 4 B tiles (K-major, 128B swizzle: row n = 128 B = 4 image slots
+//                 x 16 BF16); the 500 (image, pixel row) pairs of a tile are dealt to the 96 threads, 9 LDS + 5 cvt.pack +
+//                 2 STS.128 per pair, all loads before the first conversion
 //   warps 4-11    epilogue: two groups of four warps (one per TMEM lane quadrant); a group owns every second image group and
 //                 two accumulator stages (chunk c -> stage c & 1).  Per chunk a thread walks the 5 conv rows: row-wise 3-max
 //                 (max.NaN) + first-equal column, then the column-wise combination with strict > (np.argmax: first maximum
 //                 in row-major order), LeakyRelu, value + byte (argmax offset | gate << 4).  Outputs of 4 pooled rows are
 //                 staged per warp in the layouts two tensor maps expect (values: 64B-swizzled boxes of 16 floats x 32 rows,
 //                 conflict-free STS.128; bytes: 48 B rows) and leave by four TMA tensor stores per warp.
+//   Measured (B = 8192, F = 32, DNB_C1P_PROF_BUILD role clocks): builders ~105 k, epilogue ~110 k, MMA warp ~77 k busy clocks
+//   of ~130 k per CTA — the three roles are balanced; the pooling is ALU-pipe work (FMNMX3 / FSETP / SEL: 62 % ALU pipe).
+//   Tried and measured slower: 16 column-split epilogue warps at 92 registers (96 us: per-warp fixed costs double), MMA
+//   issue folded into a builder warp, blocking or polled (136 / 144 us: the builder stalls behind the accumulator stages).
 //   NaN: the fast path detects a NaN maximum and repeats the chunk with the sequential comparisons of np.argmax.  Because the
 //   images of a group share MMAs through zero blocks, a non-finite INPUT value reaches the other images of its group
 //   (0 x Inf = NaN) — the loss of such a batch is NaN under the reference too, only the per-sample intermediates differ.
@@ -31,6 +36,7 @@
 #include "tc_common.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 namespace dnb {
 namespace tc {
@@ -39,15 +45,22 @@ struct C1pParams {
     const float* x; const float* w; const float* b;
     int B, F, G, H;            // images, filters, images per MMA (128 / F), image rows
     int ngroups;               // ceil(B / G)
-    int nraw;                  // raw stages (groups in flight)
     float alpha, bias_k;
+    unsigned long long* prof;  // DNB_C1P_PROF_BUILD: per-CTA clock counters of the roles (null = off)
 };
 
-constexpr int C1P_NB = 2;                                   // builder warps
-constexpr int C1P_W_TMA = 0, C1P_W_MMA = 1, C1P_W_B0 = 2, C1P_W_EPI0 = 4;
+constexpr int C1P_NB = 3;                                   // builder warps
+constexpr int C1P_W_MMA = 0, C1P_W_B0 = 1, C1P_W_EPI0 = 4;  // warp 0: raw bulk copies + MMA issue; warps 1-3: builders
 constexpr int C1P_THREADS = (C1P_W_EPI0 + 8) * 32;
-constexpr int C1P_NSLOT = 4;                                // B tiles in the ring
+constexpr int C1P_NSLOT = 4, C1P_NRAW = 4;                  // B tiles in the ring; raw image groups in flight
 static_assert(C1P_W_EPI0 % 4 == 0 && C1P_W_B0 + C1P_NB == C1P_W_EPI0, "warp roles");
+
+__device__ __forceinline__ bool c1p_mbar_test(uint64_t* bar, uint32_t parity) {       // non-blocking phase test
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 
 __device__ __forceinline__ void c1p_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -143,6 +156,12 @@ __device__ __forceinline__ bool c1p_pool_chunk(uint32_t taddr, float alpha, uint
     return chk != chk;
 }
 
+#ifdef DNB_C1P_PROF_BUILD     // per-role clock counters (build with -DDNB_C1P_PROF_BUILD, run with DNB_C1P_PROF=1)
+#define C1P_ACC(slot) do { if (prof_on) { const long long t1_ = clock64(); pc[slot] += (unsigned long long)(t1_ - tprev); tprev = t1_; } } while (0)
+#else
+#define C1P_ACC(slot) do { } while (0)
+#endif
+
 template <int OHP, int OWP, int W>
 __global__ void __launch_bounds__(C1P_THREADS, 1)
 tc_c1p_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmI, C1pParams p) {
@@ -162,7 +181,7 @@ tc_c1p_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ C
     uint8_t* sOV = sB + C1P_NSLOT * TILE_B;                    // 8 warps x NBOX boxes of 2 KB
     uint8_t* sOB = sOV + 8 * SV_WARP;                          // 8 warps x 32 rows x UNIT bytes
     uint8_t* sR = sOB + 8 * SB_WARP;                           // nraw raw groups
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (size_t)p.nraw * raw_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (size_t)C1P_NRAW * raw_bytes);
     uint64_t* raw_full = bars;            // [4]
     uint64_t* raw_empty = bars + 4;       // [4]
     uint64_t* b_full = bars + 8;          // [NSLOT]
@@ -174,6 +193,12 @@ tc_c1p_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ C
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int mine = (int)blockIdx.x < p.ngroups ? (p.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
+#ifdef DNB_C1P_PROF_BUILD
+    const bool prof_on = p.prof != nullptr && lane == 0;
+    unsigned long long pc[4] = {0, 0, 0, 0};
+    long long tprev = prof_on ? clock64() : 0;
+    const long long tstart = tprev;
+#endif
     // A (block diagonal filters + bias pieces) and the zeroed B ring
     for (int e = tid; e < 128 * 8; e += C1P_THREADS) {
         const int m = e >> 3, j = e & 7;
@@ -214,32 +239,38 @@ tc_c1p_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == C1P_W_TMA) {
-        if (elect_one()) {
-            for (int i = 0; i < mine; ++i) {
-                const int rs = i % p.nraw;
-                if (i >= p.nraw) mbar_wait(&raw_empty[rs], ((i / p.nraw) - 1) & 1);
-                const long g = (long)blockIdx.x + (long)i * gridDim.x;
-                const long left_ = p.B - g * p.G; const int nimg = left_ < p.G ? (int)left_ : p.G;
-                const uint32_t bytes = (uint32_t)nimg * HW * 4u;
-                mbar_arrive_expect_tx(&raw_full[rs], bytes);
-                bulk_load_1d(sR + (size_t)rs * raw_bytes, p.x + (size_t)g * p.G * HW, bytes, &raw_full[rs]);
-            }
-        }
-    } else if (warp == C1P_W_MMA) {
+    if (warp == C1P_W_MMA) {
         const uint32_t idesc = make_idesc_bf16(128, NPAD, 0, 0);
         const uint64_t a_d = make_smem_desc(smem_u32(sA), 16, 1024, LAYOUT_SW128);
-        int n = 0;
+        int n = 0, next_load = 0;
         for (int r = 0; 2 * r < mine; ++r)
             for (int c = 0; c < NCH; ++c)
                 for (int e = 0; e < 2; ++e) {
                     const int i = 2 * r + e;
                     if (i >= mine) continue;
+                    // raw images: one bulk copy per group into a ring of C1P_NRAW, requested as soon as the builders have left
+                    // the slot (polled here, once per task: the ring is three groups = 18 tasks ahead of the builders)
+                    if (lane == 0) {
+                        while (next_load < mine && (next_load < C1P_NRAW ||
+                                                    c1p_mbar_test(&raw_empty[next_load & (C1P_NRAW - 1)], ((next_load / C1P_NRAW) - 1) & 1))) {
+                            const int rs = next_load & (C1P_NRAW - 1);
+                            const int g = (int)blockIdx.x + next_load * (int)gridDim.x;
+                            const int nimg = min(p.G, p.B - g * p.G);
+                            const uint32_t bytes = (uint32_t)nimg * HW * 4u;
+                            mbar_arrive_expect_tx(&raw_full[rs], bytes);
+                            bulk_load_1d(sR + (size_t)rs * raw_bytes, p.x + (size_t)g * p.G * HW, bytes, &raw_full[rs]);
+                            ++next_load;
+                        }
+                    }
+                    __syncwarp();
                     const int slot = n % C1P_NSLOT, ph = (n / C1P_NSLOT) & 1;
                     ++n;
                     const int ke = r * NCH + c, st = 2 * e + (ke & 1);
+                    C1P_ACC(3);
                     mbar_wait(&b_full[slot], ph);
+                    C1P_ACC(0);
                     if (ke >= 2) mbar_wait(&acc_empty[st], ((ke >> 1) - 1) & 1);
+                    C1P_ACC(1);
                     tc_fence_after();
                     const uint64_t b_d = make_smem_desc(smem_u32(sB + (size_t)slot * TILE_B), 16, 1024, LAYOUT_SW128);
                     const uint32_t d_t = tmem_base + (uint32_t)(st * NPAD);
@@ -254,18 +285,23 @@ tc_c1p_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ C
                     __syncwarp();
                 }
     } else if (warp < C1P_W_EPI0) {
-        // builders: thread -> pixel rows nrow = btid + k * NBT of the tile (the same rows for every image and chunk)
-        constexpr int NBT = C1P_NB * 32, NR = NPAD / NBT;
-        static_assert(NPAD % NBT == 0, "builder rows");
+        // builders: the (image slot, pixel row) pairs of a tile are dealt round robin to the 96 builder threads: pair id =
+        // btid + 96 k, k < 6 (the same pairs for every task).  All loads of a thread's pairs are issued before the first
+        // conversion and every packed word has its own register before the first store: a builder warp is latency bound
+        // (measured with 2 warps: 1 900 clk per tile, the kernel's critical path), so the ILP is what counts.
+        constexpr int NBT = C1P_NB * 32, NPR = (4 * NROW + NBT - 1) / NBT;
         const int btid = tid - C1P_W_B0 * 32;
-        uint32_t src_off[NR], dst_off[NR], xr[NR];
+        uint32_t src_off[NPR], dst0[NPR], dst1[NPR];
+        int pimg[NPR];
 #pragma unroll
-        for (int k = 0; k < NR; ++k) {
-            const int nrow = btid + k * NBT;
+        for (int k = 0; k < NPR; ++k) {
+            const int id = btid + k * NBT;
+            const int pi = id / NROW, nrow = id - pi * NROW;
             const int y = nrow / NC, x = nrow - y * NC;
-            src_off[k] = nrow < NROW ? (uint32_t)(y * W + x) * 4u : 0xffffffffu;
-            dst_off[k] = (uint32_t)nrow * 128u;
-            xr[k] = (uint32_t)(nrow & 7);
+            pimg[k] = id < 4 * NROW ? pi : 4;                                    // 4 = never valid
+            src_off[k] = (uint32_t)pi * (uint32_t)HW * 4u + (uint32_t)(y * W + x) * 4u;
+            dst0[k] = (uint32_t)nrow * 128u + ((((uint32_t)(2 * pi)) ^ (uint32_t)(nrow & 7)) << 4);
+            dst1[k] = (uint32_t)nrow * 128u + ((((uint32_t)(2 * pi + 1)) ^ (uint32_t)(nrow & 7)) << 4);
         }
         const uint32_t one = 0x3f80u;
         int n = 0;
@@ -274,38 +310,51 @@ tc_c1p_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ C
                 for (int e = 0; e < 2; ++e) {
                     const int i = 2 * r + e;
                     if (i >= mine) continue;
-                    const int slot = n % C1P_NSLOT;
-                    const int rs = i % p.nraw;
-                    if (c == 0) mbar_wait(&raw_full[rs], (i / p.nraw) & 1);
+                    const int slot = n & (C1P_NSLOT - 1);
+                    const int rs = i & (C1P_NRAW - 1);
+                    C1P_ACC(3);
+                    if (c == 0) mbar_wait(&raw_full[rs], (i / C1P_NRAW) & 1);
                     if (n >= C1P_NSLOT) mbar_wait(&b_empty[slot], ((n / C1P_NSLOT) - 1) & 1);
+                    C1P_ACC(0);
                     ++n;
-                    const long g = (long)blockIdx.x + (long)i * gridDim.x;
-                    const long left_ = p.B - g * p.G; const int nimg = left_ < p.G ? (int)left_ : p.G;
+                    const int g = (int)blockIdx.x + i * (int)gridDim.x;
+                    const int nimg = min(p.G, p.B - g * p.G);
                     const uint32_t raw_s = smem_u32(sR + (size_t)rs * raw_bytes) + (uint32_t)(4 * c * W) * 4u;
                     const uint32_t tile_s = smem_u32(sB + (size_t)slot * TILE_B);
-                    for (int pi = 0; pi < nimg; ++pi) {
+                    float v[NPR][9];
 #pragma unroll
-                        for (int k = 0; k < NR; ++k) {
-                            if (src_off[k] != 0xffffffffu) {
-                                const uint32_t a = raw_s + (uint32_t)pi * (uint32_t)HW * 4u + src_off[k];
-                                float v[9];
+                    for (int k = 0; k < NPR; ++k) {
 #pragma unroll
-                                for (int ty = 0; ty < 3; ++ty)
+                        for (int t = 0; t < 9; ++t) v[k][t] = 0.f;
+                        if (pimg[k] < nimg) {
+                            const uint32_t a = raw_s + src_off[k];
 #pragma unroll
-                                    for (int tx = 0; tx < 3; ++tx) v[ty * 3 + tx] = c1p_lds32(a + (uint32_t)(ty * W + tx) * 4u);
-                                const uint32_t d = tile_s + dst_off[k];
-                                sts128u(d + (((uint32_t)(2 * pi) ^ xr[k]) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                        pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                                sts128u(d + (((uint32_t)(2 * pi + 1) ^ xr[k]) << 4), c1p_bf16_bits(v[8]) | (one << 16), one | (one << 16), 0u, 0u);
-                            }
+                            for (int ty = 0; ty < 3; ++ty)
+#pragma unroll
+                                for (int tx = 0; tx < 3; ++tx) v[k][ty * 3 + tx] = c1p_lds32(a + (uint32_t)(ty * W + tx) * 4u);
                         }
                     }
+                    uint32_t wq[NPR][5];
+#pragma unroll
+                    for (int k = 0; k < NPR; ++k) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) wq[k][t] = pack_bf16x2(v[k][2 * t], v[k][2 * t + 1]);
+                        wq[k][4] = pack_bf16x2(v[k][8], 1.0f);
+                    }
+#pragma unroll
+                    for (int k = 0; k < NPR; ++k)
+                        if (pimg[k] < nimg) {
+                            sts128u(tile_s + dst0[k], wq[k][0], wq[k][1], wq[k][2], wq[k][3]);
+                            sts128u(tile_s + dst1[k], wq[k][4], one | (one << 16), 0u, 0u);
+                        }
+                    C1P_ACC(1);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
                         mbar_arrive(&b_full[slot]);
                         if (c == NCH - 1) mbar_arrive(&raw_empty[rs]);
                     }
+                    C1P_ACC(2);
                 }
     } else {
         // epilogue: TMEM lane m = q * 32 + lane = (image m / F, filter m % F) of the group = row g * 128 + m of the outputs
@@ -329,7 +378,9 @@ tc_c1p_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ C
                 for (int h = 0; h < 2; ++h) {
                     const int c = 2 * pr + h;
                     const int ke = (i >> 1) * NCH + c, st = 2 * eg + (ke & 1);
+                    C1P_ACC(3);
                     mbar_wait(&acc_full[st], (ke >> 1) & 1);
+                    C1P_ACC(0);
                     tc_fence_after();
                     const uint32_t taddr = tlane + (uint32_t)(st * NPAD);
                     if (__any_sync(0xffffffffu, c1p_pool_chunk<NC, OWP, false>(taddr, p.alpha, sv_lane, swz, 2 * h, bw)))
@@ -337,6 +388,7 @@ tc_c1p_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ C
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[st]);
+                    C1P_ACC(1);
                 }
 #pragma unroll
                 for (int t = 0; t < UNIT / 16; ++t) sts128u(sb_lane + 16u * t, bw[4 * t], bw[4 * t + 1], bw[4 * t + 2], bw[4 * t + 3]);
@@ -350,10 +402,20 @@ tc_c1p_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ C
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 pending = true;
+                C1P_ACC(2);
             }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+#ifdef DNB_C1P_PROF_BUILD
+    if (prof_on && (warp == C1P_W_MMA || warp == C1P_W_B0 || warp == C1P_W_EPI0 || warp == C1P_W_EPI0 + 1)) {
+        const int role = warp == C1P_W_MMA ? 0 : (warp == C1P_W_B0 ? 1 : (warp == C1P_W_EPI0 ? 2 : 3));
+        C1P_ACC(3);
+        unsigned long long* o = p.prof + (size_t)blockIdx.x * 20 + role * 4;
+        for (int k = 0; k < 4; ++k) o[k] = pc[k];
+        if (role == 0) p.prof[(size_t)blockIdx.x * 20 + 16] = (unsigned long long)(clock64() - tstart);
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == C1P_W_MMA) tmem_dealloc(tmem_base, TMEM_COLS);
@@ -409,9 +471,7 @@ int dnb_conv_pool_act_fwd_tc(const float* x, const float* w, const float* b, flo
     p.ngroups = (conv->B + p.G - 1) / p.G;
     p.alpha = alpha; p.bias_k = 9.f;                                 // Q1: the bias enters C*kh*kw = 9 times
     const int HW = conv->H * W;
-    p.nraw = 4;
-    while (p.nraw > 2 && c1p_smem_bytes(p.G, HW, p.nraw, NPAD, UNIT) > 225 * 1024) --p.nraw;
-    const size_t smem = c1p_smem_bytes(p.G, HW, p.nraw, NPAD, UNIT);
+    const size_t smem = c1p_smem_bytes(p.G, HW, C1P_NRAW, NPAD, UNIT);
     if (smem > 225 * 1024) return set_err(DNB_ERR_UNSUPPORTED, "conv_pool_act_fwd_tc: image group does not fit shared memory");
     const uint64_t OP = (uint64_t)OHP * OWP, rows = (uint64_t)conv->B * conv->F;
     CUtensorMap tv, ti;
@@ -419,8 +479,25 @@ int dnb_conv_pool_act_fwd_tc(const float* x, const float* w, const float* b, flo
         !c1p_tmap(&ti, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, idx_gate, OP, rows, UNIT, 32, CU_TENSOR_MAP_SWIZZLE_NONE))
         return set_err(DNB_ERR_CUDA, "conv_pool_act_fwd_tc: cuTensorMapEncodeTiled failed");
     cudaFuncSetAttribute(tc_c1p_kernel<OHP, OWP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    tc_c1p_kernel<OHP, OWP, W><<<std::min(p.ngroups, kNumSMs), C1P_THREADS, smem, S(stream)>>>(tv, ti, p);
+    const int grid = std::min(p.ngroups, kNumSMs);
+    if (getenv("DNB_C1P_PROF")) {            // per-role clock counters (tools/time_c1p.py): synchronous, never on the step path
+        cudaMalloc(&p.prof, (size_t)grid * 20 * sizeof(unsigned long long));
+        cudaMemset(p.prof, 0, (size_t)grid * 20 * sizeof(unsigned long long));
+    }
+    tc_c1p_kernel<OHP, OWP, W><<<grid, C1P_THREADS, smem, S(stream)>>>(tv, ti, p);
     DNB_LAUNCH_CHECK("conv_pool_act_fwd_tc");
+    if (p.prof) {
+        std::vector<unsigned long long> h((size_t)grid * 20);
+        cudaDeviceSynchronize();
+        cudaMemcpy(h.data(), p.prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        cudaFree(p.prof);
+        double a[20] = {0};
+        for (int b2 = 0; b2 < grid; ++b2) for (int k = 0; k < 20; ++k) a[k] += (double)h[(size_t)b2 * 20 + k] / grid;
+        const char* names[4] = {"mma     (wait b_full | wait acc_empty | - | issue)", "builder (waits | loads-cvt-stores | fence + arrive | rest)",
+                                "epi hx0 (wait acc_full | pool | store hand-over | rest)", "epi hx1 (wait acc_full | pool | store hand-over | rest)"};
+        fprintf(stderr, "c1p prof: CTA clocks %.0f\n", a[16]);
+        for (int r = 0; r < 4; ++r) fprintf(stderr, "  %s: %.0f %.0f %.0f %.0f\n", names[r], a[r * 4], a[r * 4 + 1], a[r * 4 + 2], a[r * 4 + 3]);
+    }
     return DNB_OK;
 }
 
