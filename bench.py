@@ -119,7 +119,7 @@ class ClockSampler:
 def algo_work(layer, kernel, B):
     kind = type(layer).__name__
     s = 4
-    if kernel in ("conv_pool_act_fwd", "conv_pool_act_bwd"):
+    if kernel in ("conv_pool_act_fwd", "conv_pool_act_fwd_tc", "conv_pool_act_bwd"):
         # fused Conv2D -> MaxPool2D -> Relu block: compulsory traffic = the image, the activation tensor (its delta in
         # backward) and one argmax/gate byte per pooled element; FLOPs = the convolution (forward) / 10 FMAs per pooled
         # element (backward: the routed weight gradient)
@@ -128,7 +128,7 @@ def algo_work(layer, kernel, B):
         f, oh, ow = layer.oshape
         npool = B * int(np.prod(pool.oshape))
         byts = B * c * h * w * s + npool * (s + 1)
-        fl = 2.0 * B * f * oh * ow * c * 9 if kernel.endswith("fwd") else 2.0 * npool * 10
+        fl = 2.0 * B * f * oh * ow * c * 9 if "fwd" in kernel else 2.0 * npool * 10
         return byts, fl
     if kernel == "tc_conv2d_pool_act_fwd":
         # Conv2D -> MaxPool2D -> LeakyRelu in one tcgen05 launch: the image in, 5 bytes per pooled element out; the FLOPs of
