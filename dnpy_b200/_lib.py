@@ -95,6 +95,9 @@ SIGNATURES = {
     "dnb_embedding_bwd_apply": (_i, [_p, _p, _i, _i, _i, _f, _p]),
     "dnb_rnn_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "dnb_rnn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "dnb_rnn_bwd_tc_supported": (_i, [_i, _i, _i, _i, _i]),
+    "dnb_rnn_bwd_tc_ws_bytes": (_z, [_i, _i, _i]),
+    "dnb_rnn_bwd_tc": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p]),
     "dnb_loss_ws_bytes": (_z, [_i]),
     "dnb_loss_ce": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _p, _p]),
     "dnb_loss_bce": (_i, [_p, _p, _p, _p, _i, _i, _f, _p, _p]),

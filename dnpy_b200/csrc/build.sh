@@ -6,7 +6,7 @@ OUT="$HERE/../libdnpy_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(${DNB_EXTRA_FLAGS:-} -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17
        -Xcompiler -fPIC)
-SRCS=(elementwise.cu dense.cu dense_head.cu conv.cu conv_thin.cu pool.cu norm.cu loss.cu embed_rnn.cu tc_gemm.cu tc_conv.cu tc_conv_sv.cu tc_conv_svp.cu tc_conv_c1p.cu tc_conv_wg.cu tc_conv_thin.cu fused_cpa.cu dp_peer.cu)
+SRCS=(elementwise.cu dense.cu dense_head.cu conv.cu conv_thin.cu pool.cu norm.cu loss.cu embed_rnn.cu rnn_tc.cu tc_gemm.cu tc_conv.cu tc_conv_sv.cu tc_conv_svp.cu tc_conv_c1p.cu tc_conv_wg.cu tc_conv_thin.cu fused_cpa.cu dp_peer.cu)
 mkdir -p "$HERE/build"
 pids=()
 for s in "${SRCS[@]}"; do

@@ -3,6 +3,8 @@ timestep loop (and the truncated-BPTT inner loop) runs inside one persistent CUD
 import numpy as np
 
 from .base import Layer
+from .. import _lib
+from ..runtime import config
 from .. import initializers
 from ..darray import ParamDict
 
@@ -102,9 +104,17 @@ class SimpleRNN(BaseRNN):
         h = self.hidden_dim
         trunc = self.bptt_truncate if self.bptt_truncate else t
         dx = self._buf('dx', (b, t, d))
-        self._call("dnb_rnn_bwd", x.ptr(), self.states_h.ptr(), dy.ptr(), self.params['waa'].ptr(),
-                   self.params['wax'].ptr(), dx.ptr(), self.grads['waa'].ptr(), self.grads['wax'].ptr(),
-                   self.grads['ba'].ptr(), b, t, d, h, int(trunc))
+        lib = _lib.load()
+        if config.math >= _lib.MATH_TF32 and lib.dnb_rnn_bwd_tc_supported(t, d, h, int(trunc), config.math):
+            # tensor-core math modes: serial chain per sample + the lag recurrences of all rows as tcgen05 tiles (csrc/rnn_tc.cu)
+            ws = self._raw('ws_pre', lib.dnb_rnn_bwd_tc_ws_bytes(b, t, h))
+            self._call("dnb_rnn_bwd_tc", x.ptr(), self.states_h.ptr(), dy.ptr(), self.params['waa'].ptr(),
+                       self.params['wax'].ptr(), dx.ptr(), self.grads['waa'].ptr(), self.grads['wax'].ptr(),
+                       self.grads['ba'].ptr(), b, t, d, h, int(trunc), ws, config.math)
+        else:
+            self._call("dnb_rnn_bwd", x.ptr(), self.states_h.ptr(), dy.ptr(), self.params['waa'].ptr(),
+                       self.params['wax'].ptr(), dx.ptr(), self.grads['waa'].ptr(), self.grads['wax'].ptr(),
+                       self.grads['ba'].ptr(), b, t, d, h, int(trunc))
         for k in ('waa', 'wax', 'ba'):
             self.grads[k].written()
         self.x_t_deltas = dx

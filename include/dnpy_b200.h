@@ -272,6 +272,16 @@ int dnb_rnn_bwd(const float* x, const float* states, const float* dy, const floa
                 float* dx, float* gwaa, float* gwax, float* gba,
                 int B, int T, int D, int H, int trunc, dnb_stream_t stream);
 
+/* The same gradients for the tensor-core math modes (csrc/rnn_tc.cu; H = 32, D <= 24, at most 7 recurrences per step): the
+ * serial chain pre(t), dx_t stays a warp per sample (rnn_chain_kernel), the (trunc + 1) lag recurrences of ALL (sample, step)
+ * rows run as [128 x 32] x [32 x 32] tcgen05.mma.kind::tf32 tiles and the weight gradients as one long reduction through the
+ * lag sum W(u) = sum_k S_k(u + k)  (recurrent.py:228-247).  ws: dnb_rnn_bwd_tc_ws_bytes (pre for every row). */
+int dnb_rnn_bwd_tc_supported(int T, int D, int H, int trunc, int math);
+size_t dnb_rnn_bwd_tc_ws_bytes(int B, int T, int H);
+int dnb_rnn_bwd_tc(const float* x, const float* states, const float* dy, const float* waa, const float* wax,
+                   float* dx, float* gwaa, float* gwax, float* gba,
+                   int B, int T, int D, int H, int trunc, void* ws, int math, dnb_stream_t stream);
+
 /* ---- Losses (dnpy/losses.py) + the NaN/Inf guard of net.py:342-350 ---------- */
 /* out[0] = loss, out[1] = flag bits: 1 NaN loss, 2 Inf loss, 4 NaN delta, 8 Inf delta.
  * Deltas are never divided by the batch (Q17).  loss_scale = 1/B (1/B_global when sharded).

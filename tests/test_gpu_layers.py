@@ -208,9 +208,15 @@ PERSISTENT_CASES = [
          kw=dict(filters=64, kernel_size=(3, 3), strides=(2, 2), padding="same")),
     dict(name="sv_pointwise_b40", kind="PointwiseConv2D", in_shape=(32, 64, 64), batch=40, kw=dict(filters=32)),
     dict(name="tc_dense_b4096", kind="Dense", in_shape=(784,), batch=4096, kw=dict(units=512)),
+    # SimpleRNN backward on tcgen05 (csrc/rnn_tc.cu): tiles of 124 owned rows cross sample boundaries at every phase; 362 / 166
+    # tiles (several per CTA: operand buffers, mbarrier phases and the TMEM accumulator are reused); full-length lags (T <= 8)
+    dict(name="tc_rnn_b700_t64", kind="SimpleRNN", in_shape=(64, 8), batch=700, pscale=0.1, kw=dict(hidden_dim=32, bptt_truncate=4)),
+    dict(name="tc_rnn_b80_t256", kind="SimpleRNN", in_shape=(256, 8), batch=80, pscale=0.1, kw=dict(hidden_dim=32, bptt_truncate=4)),
+    dict(name="tc_rnn_b33_t7_full", kind="SimpleRNN", in_shape=(7, 24), batch=33, pscale=0.1, kw=dict(hidden_dim=32)),
+    dict(name="tc_rnn_b5_t50_trunc1", kind="SimpleRNN", in_shape=(50, 3), batch=5, pscale=0.1, kw=dict(hidden_dim=32, bptt_truncate=1)),
 ]
 
-TC_KINDS = ("Dense", "Conv2D", "PointwiseConv2D")
+TC_KINDS = ("Dense", "Conv2D", "PointwiseConv2D", "SimpleRNN")
 TOL_TF32 = 2e-2
 
 
