@@ -590,6 +590,127 @@ static int check_win(const char* name, const dnb_win_t* g) {
     return DNB_OK;
 }
 
+
+// ---- fp32 mode on the tensor core: 3 x TF32 -----------------------------------------------------------------------------
+// math = FP32 promises rel 1e-5 against the float64 reference.  A TF32 operand keeps 11 significant bits, so every fp32 value
+// is split as v = hi + lo with hi = v truncated to TF32 (exactly representable: the tensor core's own conversion cannot change
+// it) and lo = v - hi (exact in fp32; its TF32 conversion loses <= 2^-11 of lo = 2^-22 of v).  With fp32 accumulation
+//     a . b  =  a_hi . b_hi  +  a_lo . b_hi  +  a_hi . b_lo        (the dropped a_lo . b_lo term is 2^-22 relative)
+// so an fp32-grade convolution is THREE launches of the parity-tested TF32 kernels on the split tensors (convolution.py:193-273
+// arithmetic, 1e-6 measured), instead of the SIMT fp32 kernels (conv2 of the MNIST CNN at B = 8192: 2.5 / 3.7 / 3.7 ms).
+// Workspace behind the TF32 kernels' own: hi / lo of the filters, of the gathered tensor and of dY, two partial outputs.
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+    const size_t n4 = n >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(in)[i];
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+        reinterpret_cast<float4*>(hi)[i] = h;
+        reinterpret_cast<float4*>(lo)[i] = l;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t i = (n4 << 2) + threadIdx.x;
+        const float h = __uint_as_float(__float_as_uint(in[i]) & 0xffffe000u);
+        hi[i] = h; lo[i] = in[i] - h;
+    }
+}
+// y += t1 + t2 (the two cross terms are added to each other first: they are ~2^-11 of the main term)
+__global__ void __launch_bounds__(256) add_cross_terms_kernel(float* __restrict__ y, const float* __restrict__ t1, const float* __restrict__ t2, size_t n) {
+    const size_t n4 = n >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<float4*>(y)[i];
+        const float4 a = reinterpret_cast<const float4*>(t1)[i], b = reinterpret_cast<const float4*>(t2)[i];
+        v.x += a.x + b.x; v.y += a.y + b.y; v.z += a.z + b.z; v.w += a.w + b.w;
+        reinterpret_cast<float4*>(y)[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t i = (n4 << 2) + threadIdx.x;
+        y[i] += t1[i] + t2[i];
+    }
+}
+
+struct SplitWs {               // layout of the fp32-mode workspace (all offsets multiples of 256 bytes)
+    uint8_t* tc;               // the TF32 kernels' own workspace (prepared filters, dilated dY)
+    float *wh, *wl, *gbd, *ah, *al, *bh, *bl, *t1, *t2;
+    size_t bytes;
+};
+static SplitWs split_ws(const dnb_win_t* g, void* ws) {
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t nx = (size_t)g->B * g->C * g->H * g->W, ny = (size_t)g->B * g->F * g->OH * g->OW;
+    const size_t nw = (size_t)g->F * g->C * g->kh * g->kw;
+    SplitWs s{};
+    uint8_t* p = static_cast<uint8_t*>(ws);
+    size_t o = 0;
+    s.tc = p; o += up(tc_conv_ws_bytes(g));
+    s.wh = reinterpret_cast<float*>(p + o); o += up(nw * 4);
+    s.wl = reinterpret_cast<float*>(p + o); o += up(nw * 4);
+    s.gbd = reinterpret_cast<float*>(p + o); o += up((size_t)g->F * 4);
+    s.ah = reinterpret_cast<float*>(p + o); o += up(nx * 4);
+    s.al = reinterpret_cast<float*>(p + o); o += up(nx * 4);
+    s.bh = reinterpret_cast<float*>(p + o); o += up(ny * 4);
+    s.bl = reinterpret_cast<float*>(p + o); o += up(ny * 4);
+    s.t1 = reinterpret_cast<float*>(p + o); o += up(std::max(nx, ny) * 4);
+    s.t2 = reinterpret_cast<float*>(p + o); o += up(std::max(nx, ny) * 4);
+    s.bytes = o;
+    return s;
+}
+// eligible: a tensor-core shape with enough work to amortise the six extra passes (DNB_FP32_SIMT=1 keeps the SIMT kernels)
+static bool split_ok(const dnb_win_t* g, int kind) {
+    if (getenv("DNB_FP32_SIMT") || thin_conv_supported(g)) return false;
+    const double macs = (double)g->B * g->F * g->OH * g->OW * g->C * g->kh * g->kw;
+    return macs >= (double)(1 << 26) && tc_conv_supported(g, kind);
+}
+static int split_tensor(const char* name, const float* in, float* hi, float* lo, size_t n, cudaStream_t st) {
+    split_tf32_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, st>>>(in, hi, lo, n);
+    DNB_LAUNCH_CHECK(name);
+    return DNB_OK;
+}
+static int add_cross(float* y, const float* t1, const float* t2, size_t n, cudaStream_t st) {
+    add_cross_terms_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, st>>>(y, t1, t2, n);
+    DNB_LAUNCH_CHECK("conv2d_add_cross_terms");
+    return DNB_OK;
+}
+static int conv_fwd_split(const float* x, const float* w, const float* b, float* y, const dnb_win_t* g, void* ws, cudaStream_t st) {
+    if (!ws) return set_err(DNB_ERR_INVALID, "conv2d_fwd(fp32 on the tensor core): workspace required");
+    const SplitWs s = split_ws(g, ws);
+    const size_t nx = (size_t)g->B * g->C * g->H * g->W, ny = (size_t)g->B * g->F * g->OH * g->OW;
+    int rc = split_tensor("conv2d_split_w", w, s.wh, s.wl, (size_t)g->F * g->C * g->kh * g->kw, st);
+    if (!rc) rc = split_tensor("conv2d_split_x", x, s.ah, s.al, nx, st);
+    if (!rc) rc = tc_conv_fwd(s.ah, s.wh, b, y, g, s.tc, false, st);
+    if (!rc) rc = tc_conv_fwd(s.al, s.wh, nullptr, s.t1, g, s.tc, false, st);
+    if (!rc) rc = tc_conv_fwd(s.ah, s.wl, nullptr, s.t2, g, s.tc, false, st);
+    if (!rc) rc = add_cross(y, s.t1, s.t2, ny, st);
+    return rc;
+}
+// dy_split: dY is already split into s.bh / s.bl (dnb_conv2d_bwd splits it once for both gradients)
+static int conv_dgrad_split(const float* w, const float* dy, float* dx, const dnb_win_t* g, void* ws, bool dy_split, cudaStream_t st) {
+    if (!ws) return set_err(DNB_ERR_INVALID, "conv2d_bwd(fp32 on the tensor core): workspace required");
+    const SplitWs s = split_ws(g, ws);
+    const size_t nx = (size_t)g->B * g->C * g->H * g->W, ny = (size_t)g->B * g->F * g->OH * g->OW;
+    int rc = split_tensor("conv2d_split_w", w, s.wh, s.wl, (size_t)g->F * g->C * g->kh * g->kw, st);
+    if (!rc && !dy_split) rc = split_tensor("conv2d_split_dy", dy, s.bh, s.bl, ny, st);
+    if (!rc) rc = tc_conv_dgrad(s.bh, s.wh, dx, g, s.tc, false, st);
+    if (!rc) rc = tc_conv_dgrad(s.bl, s.wh, s.t1, g, s.tc, false, st);
+    if (!rc) rc = tc_conv_dgrad(s.bh, s.wl, s.t2, g, s.tc, false, st);
+    if (!rc) rc = add_cross(dx, s.t1, s.t2, nx, st);
+    return rc;
+}
+static int conv_wgrad_split(const float* x, const float* dy, float* gw, float* gb, const dnb_win_t* g, float inv_m, void* ws,
+                            bool dy_split, cudaStream_t st) {
+    if (!ws) return set_err(DNB_ERR_INVALID, "conv2d_bwd(fp32 on the tensor core): workspace required");
+    const SplitWs s = split_ws(g, ws);
+    const size_t nx = (size_t)g->B * g->C * g->H * g->W, ny = (size_t)g->B * g->F * g->OH * g->OW;
+    int rc = split_tensor("conv2d_split_x", x, s.ah, s.al, nx, st);
+    if (!rc && !dy_split) rc = split_tensor("conv2d_split_dy", dy, s.bh, s.bl, ny, st);
+    if (!rc) rc = tc_conv_wgrad(s.ah, s.bh, gw, gb, g, inv_m, s.tc, false, st);        // gb += sum dY_hi
+    if (!rc) rc = tc_conv_wgrad(s.al, s.bh, gw, nullptr, g, inv_m, s.tc, false, st);
+    if (!rc) rc = tc_conv_wgrad(s.ah, s.bl, gw, gb, g, inv_m, s.tc, false, st);        // gb += sum dY_lo
+    return rc;
+}
+
 }  // namespace dnb
 
 using namespace dnb;
@@ -598,7 +719,9 @@ extern "C" {
 
 size_t dnb_conv2d_ws_bytes(const dnb_win_t* g, int math) {
     if (!g) return 0;
-    return math >= DNB_MATH_TF32 ? tc_conv_ws_bytes(g) : 0;
+    if (math >= DNB_MATH_TF32) return tc_conv_ws_bytes(g);
+    if (split_ok(g, TC_CONV_FWD) || split_ok(g, TC_CONV_DGRAD) || split_ok(g, TC_CONV_WGRAD)) return split_ws(g, nullptr).bytes;
+    return 0;
 }
 
 int dnb_conv2d_fwd(const float* x, const float* w, const float* b, float* y,
@@ -608,6 +731,7 @@ int dnb_conv2d_fwd(const float* x, const float* w, const float* b, float* y,
     if (g->B == 0) return DNB_OK;
     DNB_CHECK_ARG(x && w && b && y, "conv2d_fwd: null pointer");
     if (thin_conv_supported(g)) return thin_conv_fwd(x, w, b, y, g, S(stream));
+    if (math == DNB_MATH_FP32 && split_ok(g, TC_CONV_FWD)) return conv_fwd_split(x, w, b, y, g, ws, S(stream));
     if (math >= DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_FWD))
         return tc_conv_fwd(x, w, b, y, g, ws, math == DNB_MATH_BF16, S(stream));
     GatherArgs a{x, w, b, y, g->B, g->C, g->H, g->W, g->F, g->OH, g->OW, g->kh, g->kw,
@@ -647,7 +771,13 @@ int dnb_conv2d_bwd(const float* x, const float* w, const float* b, const float* 
             if (rc) return rc;
         }
     }
-    if (dx && !thin) {
+    const bool sp_d = math == DNB_MATH_FP32 && dx && !thin && split_ok(g, TC_CONV_DGRAD);
+    const bool sp_w = math == DNB_MATH_FP32 && !thin && split_ok(g, TC_CONV_WGRAD);
+    if (sp_d) {
+        rc = conv_dgrad_split(w, dy, dx, g, ws, false, st);
+        if (rc) return rc;
+    }
+    if (dx && !thin && !sp_d) {
         if (math >= DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_DGRAD)) {
             rc = tc_conv_dgrad(dy, w, dx, g, ws, math == DNB_MATH_BF16, st);
         } else {
@@ -659,6 +789,8 @@ int dnb_conv2d_bwd(const float* x, const float* w, const float* b, const float* 
     }
     if (thin && !tc_wgrad) {
         // gradients already accumulated above
+    } else if (sp_w) {
+        rc = conv_wgrad_split(x, dy, gw, gb, g, inv_m, ws, /*dy_split=*/sp_d, st);
     } else if (tc_wgrad) {
         rc = tc_conv_wgrad(x, dy, gw, gb, g, inv_m, ws, math == DNB_MATH_BF16, st);
     } else {
@@ -708,6 +840,7 @@ int dnb_conv2d_bwd_data(const float* w, const float* dy, float* dx, const dnb_wi
     const bool tc = math >= DNB_MATH_TF32 && tc_conv_supported(g, TC_CONV_DGRAD);
     if (thin && !(thin_tc && tc)) return thin_conv_bwd(nullptr, w, dy, dx, nullptr, nullptr, g, 0.f, /*skip_wgrad=*/true, st);
     if (tc) return tc_conv_dgrad(dy, w, dx, g, ws, math == DNB_MATH_BF16, st);
+    if (math == DNB_MATH_FP32 && split_ok(g, TC_CONV_DGRAD)) return conv_dgrad_split(w, dy, dx, g, ws, false, st);
     GatherArgs a{dy, w, nullptr, dx, g->B, g->F, g->OH, g->OW, g->C, g->H, g->W, g->kh, g->kw,
                  1, 1, g->sy, g->sx, g->kh - 1 - g->pt, g->kw - 1 - g->pl, 0, 0.f};
     return launch_gather<true>("conv2d_bwd_data", a, st);

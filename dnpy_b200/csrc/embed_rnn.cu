@@ -24,13 +24,30 @@ __global__ void __launch_bounds__(256) embedding_fwd_kernel(const int32_t* __res
         y[i] = (v >= 0 && v < V) ? w[(long)v * D + d] : 0.f;
     }
 }
-// meand[l,d] = inv_m * sum_b dy[b,l,d]
-__global__ void __launch_bounds__(256) embedding_mean_kernel(const float* __restrict__ dy, float* __restrict__ meand,
-                                                             int B, long LD, float inv_m) {
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+// meand[l,d] = inv_m * sum_b dy[b,l,d] in two deterministic stages: EMB_BS batch slices (rows by, by + EMB_BS, ...) summed by
+// one CTA row each with four independent accumulators, then the slices added in a fixed order (one thread per column looping
+// over all B rows ran on 8 CTAs: 75 us at B=1024, L*D=2048)
+constexpr int EMB_BS = 32;
+__global__ void __launch_bounds__(256) embedding_mean_partial_kernel(const float* __restrict__ dy, float* __restrict__ part,
+                                                                     int B, long LD) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= LD) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = blockIdx.y;
+    for (; b + 3 * EMB_BS < B; b += 4 * EMB_BS) {
+        a0 += dy[(long)b * LD + i]; a1 += dy[(long)(b + EMB_BS) * LD + i];
+        a2 += dy[(long)(b + 2 * EMB_BS) * LD + i]; a3 += dy[(long)(b + 3 * EMB_BS) * LD + i];
+    }
+    for (; b < B; b += EMB_BS) a0 += dy[(long)b * LD + i];
+    part[(long)blockIdx.y * LD + i] = (a0 + a1) + (a2 + a3);
+}
+__global__ void __launch_bounds__(256) embedding_mean_finish_kernel(const float* __restrict__ part, float* __restrict__ meand,
+                                                                    long LD, float inv_m) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= LD) return;
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += dy[(long)b * LD + i];
+#pragma unroll 8
+    for (int s = 0; s < EMB_BS; ++s) acc += part[(long)s * LD + i];
     meand[i] = acc * inv_m;
 }
 // last[v] = the largest GLOBAL flat position (pos0 + i) of token v: NumPy's fancy-index "+=" keeps the last write (Q15)
@@ -456,7 +473,7 @@ int dnb_embedding_fwd(const int32_t* idx, const float* w, float* y, int B, int L
     return DNB_OK;
 }
 
-size_t dnb_embedding_bwd_ws_bytes(int L, int V, int D) { return ((size_t)V + (size_t)L * D) * sizeof(float); }
+size_t dnb_embedding_bwd_ws_bytes(int L, int V, int D) { return ((size_t)V + (size_t)(1 + EMB_BS) * L * D) * sizeof(float); }
 
 // Two halves around the data-parallel exchange: prepare leaves the local part of the batch mean (inv_m = 1 over the
 // GLOBAL batch) in ws[V ..] and the last global position of every vocabulary row in ws[0 .. V); between the halves the ranks
@@ -477,8 +494,11 @@ int dnb_embedding_bwd_prepare(const int32_t* idx, const float* dy, int B, int L,
         return e == cudaSuccess ? DNB_OK : set_err(DNB_ERR_CUDA, "embedding_bwd: %s", cudaGetErrorString(e));
     }
     DNB_CHECK_ARG(idx && dy, "embedding_bwd: null pointer");
-    embedding_mean_kernel<<<(unsigned)((LD + 255) / 256), 256, 0, st>>>(dy, meand, B, LD, inv_m);
+    float* part = meand + LD;
+    embedding_mean_partial_kernel<<<dim3((unsigned)((LD + 255) / 256), EMB_BS), 256, 0, st>>>(dy, part, B, LD);
     DNB_LAUNCH_CHECK("embedding_bwd_mean");
+    embedding_mean_finish_kernel<<<(unsigned)((LD + 255) / 256), 256, 0, st>>>(part, meand, LD, inv_m);
+    DNB_LAUNCH_CHECK("embedding_bwd_mean_finish");
     embedding_last_kernel<<<ew_grid((size_t)n_tok, 256), 256, 0, st>>>(idx, last, n_tok, V, pos0);
     DNB_LAUNCH_CHECK("embedding_bwd_last");
     return DNB_OK;

@@ -98,14 +98,14 @@ rnn_lags_tc_kernel(const __grid_constant__ CUtensorMap tmPre, const __grid_const
 
     int it = 0;
     uint32_t ph1 = 0;
+    if (tid == 0 && (long)blockIdx.x < p.ntiles) {
+        const long r0 = (long)blockIdx.x * p.step;
+        mbar_arrive_expect_tx(ld_full, 16384 + (128 + RL_HALO) * 128);
+        tma_load_2d(sPre, &tmPre, 0, (int)r0, ld_full);
+        tma_load_2d(sH, &tmH, 0, (int)(r0 - RL_HALO), ld_full);
+    }
     for (long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const long r0 = tile * p.step;
-        if (it > 0) mbar_wait(mma2, (it - 1) & 1);               // the previous reduction has read sWt / sHX
-        if (tid == 0) {
-            mbar_arrive_expect_tx(ld_full, 16384 + (128 + RL_HALO) * 128);
-            tma_load_2d(sPre, &tmPre, 0, (int)r0, ld_full);
-            tma_load_2d(sH, &tmH, 0, (int)(r0 - RL_HALO), ld_full);
-        }
         const long row = r0 + tid;
         const bool valid = row < p.R;
         const int t = valid ? (int)(row % p.T) : 0;
@@ -115,18 +115,14 @@ rnn_lags_tc_kernel(const __grid_constant__ CUtensorMap tmPre, const __grid_const
 #pragma unroll
         for (int d = 0; d < 24; ++d) xv[d] = (owned && d < p.D) ? __ldg(p.x + row * p.D + d) : 0.f;
         mbar_wait(ld_full, it & 1);
+        // S_0 = the thread's row of the pre tile; the tile itself becomes the lag-sum rows W(u) (rows past the end are zero)
+        const uint32_t myrow = sPre_s + (uint32_t)(tid * 128);
         float S[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const float4 v = rl_lds128(sPre_s + (uint32_t)(tid * 128 + ((c ^ xs) << 4)));
+            const float4 v = rl_lds128(myrow + ((c ^ xs) << 4));
             S[4 * c] = v.x; S[4 * c + 1] = v.y; S[4 * c + 2] = v.z; S[4 * c + 3] = v.w;
         }
-        if (!valid) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) S[i] = 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sts32(rl_kaddr(sWt_s, 32, i, tid), S[i]);             // lag 0: Wt[i][u = tid] = S_0
         for (int k = 0; k < p.trunc; ++k) {
             // A = S_k * (1 - h(row-k-1)^2); a lag that does not exist (t - k - 1 < 0) contributes zeros from here on
             const bool live = valid && t - k - 1 >= 0;
@@ -143,7 +139,7 @@ rnn_lags_tc_kernel(const __grid_constant__ CUtensorMap tmPre, const __grid_const
             }
             fence_proxy_async_smem();
             tc_fence_before();
-            __syncthreads();
+            __syncthreads();                                     // also orders the lag-sum updates of lag k - 1 before those of lag k
             if (tid == 0) {
                 tc_fence_after();
 #pragma unroll
@@ -153,24 +149,38 @@ rnn_lags_tc_kernel(const __grid_constant__ CUtensorMap tmPre, const __grid_const
                 }
                 mma_commit(mma1);
             }
-            mbar_wait(mma1, ph1);
+            mbar_wait_spin(mma1, ph1);                           // a few hundred clocks: poll, do not suspend
             ph1 ^= 1;
             tc_fence_after();
             tmem_ld_32x32(tq + (d1 - tmem_base), reinterpret_cast<uint32_t (&)[32]>(S));
             tmem_ld_wait();
             tc_fence_before();
-            // lag sum: S_{k+1}(row) belongs to W(row - k - 1)
+            // lag sum: S_{k+1}(row) belongs to W(row - k - 1): a 128-bit read-modify-write of that row (one thread per row)
             const int u = tid - k - 1;
             if (u >= 0 && live) {
+                const uint32_t ur = sPre_s + (uint32_t)(u * 128);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const uint32_t a = rl_kaddr(sWt_s, 32, i, u);
-                    sts32(a, rl_lds32(a) + S[i]);
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t a = ur + ((c ^ (u & 7)) << 4);
+                    float4 w = rl_lds128(a);
+                    w.x += S[4 * c]; w.y += S[4 * c + 1]; w.z += S[4 * c + 2]; w.w += S[4 * c + 3];
+                    sts128(a, w);
                 }
             }
         }
-        // reduction operands: HXt[q][u] = h(u-1)[q] (zero before the sequence starts), HXt[32 + d][u] = x(u)[d], HXt[32 + D][u] = 1
+        __syncthreads();                                         // every W(u) is complete
+        if (it > 0) mbar_wait(mma2, (it - 1) & 1);               // the previous reduction has read sWt / sHX
+        // reduction operands (K = rows, transposed): Wt[i][u] = W(u)[i]; HXt[q][u] = h(u-1)[q] (zero before the sequence starts),
+        // HXt[32 + d][u] = x(u)[d], HXt[32 + D][u] = 1; columns a tile does not own are zero in HXt
         {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 w = rl_lds128(myrow + ((c ^ xs) << 4));
+                sts32(rl_kaddr(sWt_s, 32, 4 * c, tid), w.x);
+                sts32(rl_kaddr(sWt_s, 32, 4 * c + 1, tid), w.y);
+                sts32(rl_kaddr(sWt_s, 32, 4 * c + 2, tid), w.z);
+                sts32(rl_kaddr(sWt_s, 32, 4 * c + 3, tid), w.w);
+            }
             const int hr = tid + RL_HALO - 1;
             const bool hp = owned && t >= 1;
 #pragma unroll
@@ -188,8 +198,15 @@ rnn_lags_tc_kernel(const __grid_constant__ CUtensorMap tmPre, const __grid_const
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        __syncthreads();
+        __syncthreads();                                         // sPre / sH are free: the next tile's loads overlap the reduction
         if (tid == 0) {
+            const long nt = tile + gridDim.x;
+            if (nt < p.ntiles) {
+                const long n0 = nt * p.step;
+                mbar_arrive_expect_tx(ld_full, 16384 + (128 + RL_HALO) * 128);
+                tma_load_2d(sPre, &tmPre, 0, (int)n0, ld_full);
+                tma_load_2d(sH, &tmH, 0, (int)(n0 - RL_HALO), ld_full);
+            }
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < 16; ++ks) {

@@ -50,7 +50,7 @@ def test_pure_host_entry_points():
     assert lib.dnb_maxpool2d_bwd_ws_bytes(g, _lib.ROUTE_LITERAL) == 3 * 3 * 3 * (9 + 1) * 4   # last[npos][P] + done[npos]
     assert lib.dnb_maxpool2d_bwd_ws_bytes(g, _lib.ROUTE_PER_SAMPLE) == 0
     assert lib.dnb_loss_ws_bytes(10) == 14 * 4
-    assert lib.dnb_embedding_bwd_ws_bytes(5, 7, 3) == (7 + 15) * 4
+    assert lib.dnb_embedding_bwd_ws_bytes(5, 7, 3) == (7 + 15 * (1 + 32)) * 4        # last[V] + mean[L*D] + 32 batch-slice partials
 
 
 def test_no_cpu_fallback_without_device():
