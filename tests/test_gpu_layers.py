@@ -212,6 +212,7 @@ PERSISTENT_CASES = [
     # tiles (several per CTA: operand buffers, mbarrier phases and the TMEM accumulator are reused); full-length lags (T <= 8)
     dict(name="tc_rnn_b700_t64", kind="SimpleRNN", in_shape=(64, 8), batch=700, pscale=0.1, kw=dict(hidden_dim=32, bptt_truncate=4)),
     dict(name="tc_rnn_b80_t256", kind="SimpleRNN", in_shape=(256, 8), batch=80, pscale=0.1, kw=dict(hidden_dim=32, bptt_truncate=4)),
+    dict(name="tc_rnn_b1024_t256", kind="SimpleRNN", in_shape=(256, 8), batch=1024, pscale=0.1, kw=dict(hidden_dim=32, bptt_truncate=4)),
     dict(name="tc_rnn_b33_t7_full", kind="SimpleRNN", in_shape=(7, 24), batch=33, pscale=0.1, kw=dict(hidden_dim=32)),
     dict(name="tc_rnn_b5_t50_trunc1", kind="SimpleRNN", in_shape=(50, 3), batch=5, pscale=0.1, kw=dict(hidden_dim=32, bptt_truncate=1)),
 ]
