@@ -10,6 +10,7 @@
 // full-length dh chain PLUS a truncated inner loop at every t, (1-h^2) applied before the Waa
 // product, gradients summed (not averaged) over the batch.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -167,6 +168,89 @@ rnn_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ waa, 
             states[((size_t)b * T + t) * H + lane] = hn;
             if (t == T - 1) y[(size_t)b * H + lane] = hn;
         }
+    }
+}
+
+// Blocked form for H = 32, D <= 8.  The kernel above broadcasts the whole 32-vector to every lane (8 + 2 LDS.128 of 512 B
+// register write-back each per step and warp): the LSU return path (128 B/clk per SM) bounds it at ~580 clk per step with 8
+// warps per SM.  Here lane (a, b) = (lane / 4, lane % 4) owns the 4 x 8 block of Waa (units 4a .. 4a+3, inputs 8b .. 8b+7):
+// it reads only ITS 8 inputs (2 LDS.128), the four lanes of a unit block add their partial sums with two xor-shuffle rounds
+// (8 SHFL of 128 B), and lane 4a + b keeps unit 4a + b — the natural one-unit-per-lane layout for tanh, the store and the
+// next step's scratch.  Half the LSU traffic per step.
+// The inputs do NOT travel through a register ring here: ncu showed the ring's consumer stalled on the long scoreboard every
+// step (a scoreboard wait covers ALL loads in flight on it, the newest included — the "prefetch" exposed one full L2 / HBM
+// round trip per step, ~600 clk, in every form of this kernel).  x arrives by per-warp bulk copies (chunks of RB_CH steps,
+// double buffered, mbarrier) and is read from shared memory.
+constexpr int RB_CH = 64;
+// tanh(v) = 1 - 2 / (exp(2 v) + 1) on the SFU (ex2.approx + rcp.approx, ~2 ulp of the result; saturates cleanly at +-1):
+// tanhf() is ~35 instructions with a branch — a third of this kernel's issue slots at 2 warps per scheduler
+__device__ __forceinline__ float rnn_tanh(float v) { return 1.f - __fdividef(2.f, __expf(2.f * v) + 1.f); }
+__global__ void __launch_bounds__(RF_WARPS * 32)
+rnn_fwd_blk_kernel(const float* __restrict__ x, const float* __restrict__ waa, const float* __restrict__ wax,
+                   const float* __restrict__ ba, float* __restrict__ states, float* __restrict__ y, int B, int T, int D) {
+    __shared__ __align__(16) float scratch[RF_WARPS][32];
+    __shared__ __align__(16) float sx[RF_WARPS][2][RB_CH * 8];
+    __shared__ __align__(8) uint64_t full[RF_WARPS][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * RF_WARPS + warp;
+    if (b >= B) return;
+    const int a = lane >> 2, bq = lane & 3;
+    float w[8][4], wx[2][4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i][jj] = __ldg(waa + (4 * a + jj) * 32 + 8 * bq + i);      // Waa[j][q]
+#pragma unroll
+        for (int e = 0; e < 2; ++e) wx[e][jj] = (2 * bq + e < D) ? __ldg(wax + (4 * a + jj) * D + 2 * bq + e) : 0.f;
+    }
+    const float bj = __ldg(ba + lane);
+    float* sh = scratch[warp];
+    sh[lane] = 0.f;
+    const float* xs = x + (size_t)b * T * D;
+    const int nch = (T + RB_CH - 1) / RB_CH;
+    auto fetch = [&](int c) {                               // lane 0: chunk c of the sample's inputs -> buffer c & 1
+        const int steps = min(RB_CH, T - c * RB_CH);
+        const uint32_t bytes = (uint32_t)steps * D * 4u;
+        tc::mbar_arrive_expect_tx(&full[warp][c & 1], bytes);
+        tc::bulk_load_1d(sx[warp][c & 1], xs + (size_t)c * RB_CH * D, bytes, &full[warp][c & 1]);
+    };
+    if (lane == 0) {
+        tc::mbar_init(&full[warp][0], 1); tc::mbar_init(&full[warp][1], 1);
+        tc::fence_barrier_init();
+        fetch(0);
+    }
+    __syncwarp();
+    const int xo0 = min(2 * bq, D - 1), xo1 = min(2 * bq + 1, D - 1);      // (the weights of columns >= D are zero)
+    for (int t = 0; t < T; ++t) {
+        const int c = t / RB_CH, i = t - c * RB_CH;
+        if (i == 0) {
+            if (lane == 0 && c + 1 < nch) fetch(c + 1);      // buffer (c + 1) & 1 was last read in chunk c - 1
+            tc::mbar_wait_spin(&full[warp][c & 1], (c >> 1) & 1);
+        }
+        __syncwarp();
+        const float4 v0 = *reinterpret_cast<const float4*>(sh + 8 * bq), v1 = *reinterpret_cast<const float4*>(sh + 8 * bq + 4);
+        const float x0 = sx[warp][c & 1][i * D + xo0], x1 = sx[warp][c & 1][i * D + xo1];
+        float s[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {                     // two chains per unit: the sum is on the critical path
+            float p0 = x0 * wx[0][jj], p1 = x1 * wx[1][jj];
+            p0 = fmaf(v0.x, w[0][jj], p0); p1 = fmaf(v0.y, w[1][jj], p1);
+            p0 = fmaf(v0.z, w[2][jj], p0); p1 = fmaf(v0.w, w[3][jj], p1);
+            p0 = fmaf(v1.x, w[4][jj], p0); p1 = fmaf(v1.y, w[5][jj], p1);
+            p0 = fmaf(v1.z, w[6][jj], p0); p1 = fmaf(v1.w, w[7][jj], p1);
+            s[jj] = p0 + p1;
+        }
+        // transpose-reduce over the 4 lanes of the unit block: after round 1 a lane keeps the two units of its parity, after
+        // round 2 its own unit 4a + bq = lane (3 SHFL + 6 selects instead of 8 SHFL and a 4-way pick)
+        const bool o1 = bq & 1, o2 = bq & 2;
+        const float r0 = (o1 ? s[1] : s[0]) + __shfl_xor_sync(0xffffffffu, o1 ? s[0] : s[1], 1);    // unit 0 / 1
+        const float r1 = (o1 ? s[3] : s[2]) + __shfl_xor_sync(0xffffffffu, o1 ? s[2] : s[3], 1);    // unit 2 / 3
+        const float mine = (o2 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, o2 ? r0 : r1, 2);
+        const float hn = rnn_tanh(mine + bj);
+        __syncwarp();
+        sh[lane] = hn;
+        states[((size_t)b * T + t) * 32 + lane] = hn;
+        if (t == T - 1) y[(size_t)b * 32 + lane] = hn;
     }
 }
 
@@ -531,6 +615,11 @@ int dnb_rnn_fwd(const float* x, const float* waa, const float* wax, const float*
     DNB_CHECK_ARG(x && waa && wax && ba && states && y, "rnn_fwd: null pointer");
     if (H > 256) return set_err(DNB_ERR_UNSUPPORTED, "rnn_fwd: hidden_dim %d > 256 not supported", H);
     int SB, threads;
+    if (H == 32 && D <= 8 && (T * D) % 4 == 0 && !(reinterpret_cast<uintptr_t>(x) & 15) && !getenv("DNB_RNN_NO_BLK")) {
+        rnn_fwd_blk_kernel<<<(B + RF_WARPS - 1) / RF_WARPS, RF_WARPS * 32, 0, S(stream)>>>(x, waa, wax, ba, states, y, B, T, D);
+        DNB_LAUNCH_CHECK("rnn_fwd");
+        return DNB_OK;
+    }
     if (H <= 32 && D <= 32 && !getenv("DNB_RNN_TILE_FWD")) {
         rnn_fwd_warp_kernel<<<(B + RF_WARPS - 1) / RF_WARPS, RF_WARPS * 32, 0, S(stream)>>>(x, waa, wax, ba, states, y, B, T, D, H);
         DNB_LAUNCH_CHECK("rnn_fwd");

@@ -290,6 +290,86 @@ rnn_chain_kernel(const float* __restrict__ states, const float* __restrict__ dy,
     }
 }
 
+// Blocked form of the chain for D <= 8 (see rnn_fwd_blk_kernel in embed_rnn.cu): lane (a, b) = (lane / 4, lane % 4) owns the
+// 8 x 4 block of Waa (inputs 8b .. 8b+7, units 4a .. 4a+3) and the 8 inputs' weights of dx column a; 2 LDS.128 + 10 SHFL per
+// step instead of 16 broadcast LDS.128.
+// The states arrive by per-warp bulk copies (chunks of RCB_CH steps, walking backwards, double buffered): a register ring of
+// global loads stalls its consumer on the long scoreboard every step (see rnn_fwd_blk_kernel).
+constexpr int RCB_WARPS = 4, RCB_CH = 32;
+__global__ void __launch_bounds__(RCB_WARPS * 32)
+rnn_chain_blk_kernel(const float* __restrict__ states, const float* __restrict__ dy, const float* __restrict__ waa,
+                     const float* __restrict__ wax, float* __restrict__ pre_out, float* __restrict__ dx, int B, int T, int D) {
+    __shared__ __align__(16) float scratch[RCB_WARPS][32];
+    __shared__ __align__(16) float shs[RCB_WARPS][2][RCB_CH * 32];
+    __shared__ __align__(8) uint64_t full[RCB_WARPS][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * RCB_WARPS + warp;
+    if (b >= B) return;
+    const int a = lane >> 2, bq = lane & 3;
+    float w[8][4], wxx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) w[i][jj] = __ldg(waa + (8 * bq + i) * 32 + 4 * a + jj);     // Waa[q][j]
+        wxx[i] = a < D ? __ldg(wax + (8 * bq + i) * D + a) : 0.f;                                   // Wax[q][d = a]
+    }
+    float* su = scratch[warp];
+    const float* hs = states + (size_t)b * T * 32;
+    const int nch = (T + RCB_CH - 1) / RCB_CH;
+    // chunk c (counted from the END of the sequence) = steps [lo, lo + n): lo = max(0, T - (c + 1) * RCB_CH)
+    auto fetch = [&](int c) {
+        const int hi = T - c * RCB_CH, lo = max(0, hi - RCB_CH);
+        const uint32_t bytes = (uint32_t)(hi - lo) * 128u;
+        tc::mbar_arrive_expect_tx(&full[warp][c & 1], bytes);
+        tc::bulk_load_1d(shs[warp][c & 1], hs + (size_t)lo * 32, bytes, &full[warp][c & 1]);
+    };
+    if (lane == 0) {
+        tc::mbar_init(&full[warp][0], 1); tc::mbar_init(&full[warp][1], 1);
+        tc::fence_barrier_init();
+        fetch(0);
+    }
+    __syncwarp();
+    float dh = __ldg(dy + (size_t)b * 32 + lane);                            // delta_y enters at t = T - 1 only
+    for (int t = T - 1; t >= 0; --t) {
+        const int c = (T - 1 - t) / RCB_CH;
+        const int lo = max(0, T - (c + 1) * RCB_CH);
+        if (t == T - 1 - c * RCB_CH) {
+            if (lane == 0 && c + 1 < nch) fetch(c + 1);
+            tc::mbar_wait_spin(&full[warp][c & 1], (c >> 1) & 1);
+        }
+        const float h = shs[warp][c & 1][(t - lo) * 32 + lane];
+        const float pre = dh * (1.f - h * h);                                // recurrent.py:226
+        pre_out[((size_t)b * T + t) * 32 + lane] = pre;
+        __syncwarp();
+        su[lane] = pre;
+        __syncwarp();
+        const float4 v0 = *reinterpret_cast<const float4*>(su + 8 * bq), v1 = *reinterpret_cast<const float4*>(su + 8 * bq + 4);
+        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float s[5];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            float p0 = v[0] * w[0][jj], p1 = v[1] * w[1][jj];
+#pragma unroll
+            for (int i = 2; i < 8; i += 2) { p0 = fmaf(v[i], w[i][jj], p0); p1 = fmaf(v[i + 1], w[i + 1][jj], p1); }
+            s[jj] = p0 + p1;
+        }
+        {
+            float p0 = v[0] * wxx[0], p1 = v[1] * wxx[1];
+#pragma unroll
+            for (int i = 2; i < 8; i += 2) { p0 = fmaf(v[i], wxx[i], p0); p1 = fmaf(v[i + 1], wxx[i + 1], p1); }
+            s[4] = p0 + p1;
+        }
+        // transpose-reduce over the 4 lanes of the unit block (see rnn_fwd_blk_kernel); the dx column needs the full sum
+        const bool o1 = bq & 1, o2 = bq & 2;
+        const float r0 = (o1 ? s[1] : s[0]) + __shfl_xor_sync(0xffffffffu, o1 ? s[0] : s[1], 1);
+        const float r1 = (o1 ? s[3] : s[2]) + __shfl_xor_sync(0xffffffffu, o1 ? s[2] : s[3], 1);
+        dh = (o2 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, o2 ? r0 : r1, 2);  // recurrent.py:251: unit 4a + bq = lane
+        s[4] += __shfl_xor_sync(0xffffffffu, s[4], 1);
+        s[4] += __shfl_xor_sync(0xffffffffu, s[4], 2);
+        if (bq == 0 && a < D) dx[((size_t)b * T + t) * D + a] = s[4];        // recurrent.py:252
+    }
+}
+
 static bool rl_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint32_t box_rows) {
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) return false;
@@ -323,7 +403,10 @@ int dnb_rnn_bwd_tc(const float* x, const float* states, const float* dy, const f
     DNB_CHECK_ARG(!((reinterpret_cast<uintptr_t>(states) | reinterpret_cast<uintptr_t>(ws)) & 15), "rnn_bwd_tc: buffers must be 16-byte aligned");
     cudaStream_t st = S(stream);
     float* pre = static_cast<float*>(ws);
-    rnn_chain_kernel<<<(B + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, st>>>(states, dy, waa, wax, pre, dx, B, T, D, H);
+    if (D <= 8 && !getenv("DNB_RNN_NO_BLK"))
+        rnn_chain_blk_kernel<<<(B + RCB_WARPS - 1) / RCB_WARPS, RCB_WARPS * 32, 0, st>>>(states, dy, waa, wax, pre, dx, B, T, D);
+    else
+        rnn_chain_kernel<<<(B + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, st>>>(states, dy, waa, wax, pre, dx, B, T, D, H);
     DNB_LAUNCH_CHECK("rnn_bwd_chain");
     RnnLagsParams p{};
     p.x = x; p.waa = waa; p.gwaa = gwaa; p.gwax = gwax; p.gba = gba;
