@@ -170,13 +170,13 @@ template <int OUT>
 __global__ void __launch_bounds__(256) head_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                       const float* __restrict__ w, float* __restrict__ gw,
                                                       const float* __restrict__ bvec, float* __restrict__ gb,
-                                                      int B, int in, float inv_m, float l1, float l2, float bl1, float bl2) {
+                                                      int B, int in, int rows, float inv_m, float l1, float l2, float bl1, float bl2) {
     constexpr int PITCH = 4 * OUT + 1;
     extern __shared__ __align__(128) uint8_t hsm[];
     float (*sd)[HD_MAXOUT] = reinterpret_cast<float (*)[HD_MAXOUT]>(hsm);                 // [HW_ROWS][16]
     float (*red)[32][PITCH] = reinterpret_cast<float (*)[32][PITCH]>(hsm + HW_ROWS * HD_MAXOUT * sizeof(float));   // [8][32][PITCH]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int b0 = blockIdx.y * HW_ROWS, nr = min(HW_ROWS, B - b0);
+    const int b0 = blockIdx.y * rows, nr = min(rows, B - b0);          // rows <= HW_ROWS batch rows per CTA
     const int in4 = in >> 2;
     const int q = blockIdx.x * 32 + lane;
     const bool qok = q < in4;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) head_dw_kernel(const float* __restrict__ 
         const int r = wid + 8 * u;
         xn[u] = (r < nr && qok) ? __ldg(xq + (size_t)r * in4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int e = threadIdx.x; e < HW_ROWS * HD_MAXOUT; e += 256) {
+    for (int e = threadIdx.x; e < rows * HD_MAXOUT; e += 256) {
         const int r = e / HD_MAXOUT, o = e % HD_MAXOUT;
         sd[r][o] = (r < nr && o < OUT) ? __ldg(dy + (size_t)(b0 + r) * OUT + o) : 0.f;
     }
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) head_dw_kernel(const float* __restrict__ 
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int r = min(r0 + 8 * u, HW_ROWS - 1);     // rows >= nr hold zeros in sd
+            const int r = min(r0 + 8 * u, rows - 1);        // rows >= nr hold zeros in sd
             float d[HD_MAXOUT];
 #pragma unroll
             for (int o4 = 0; o4 < (OUT + 3) / 4; ++o4) {
@@ -287,11 +287,16 @@ bool head_dx(const float* dy, const float* w, float* dx, int B, int in, int out,
 bool head_dw(const float* x, const float* dy, const float* w, float* gw, const float* b, float* gb, int B, int in, int out,
              float inv_m, float l1, float l2, float bl1, float bl2, cudaStream_t st) {
     if (!al16(x)) return false;
-    dim3 grid(((in >> 2) + 31) / 32, (B + HW_ROWS - 1) / HW_ROWS);
+    // rows per CTA: 512 on large batches (one atomic per (feature, out) and CTA), fewer when the grid would not fill the GPU
+    // (256 -> 10 at B = 1024: 4 CTAs of 512 rows took 20 us)
+    const int gx = ((in >> 2) + 31) / 32;
+    int rows = HW_ROWS;
+    while (rows > 64 && (long)gx * ((B + rows - 1) / rows) < 2L * kNumSMs) rows >>= 1;
+    dim3 grid(gx, (B + rows - 1) / rows);
     HD_DISPATCH(out, {
         const size_t smem = (HW_ROWS * HD_MAXOUT + 8 * 32 * (4 * O + 1)) * sizeof(float);
         if (smem > 48 * 1024) cudaFuncSetAttribute(head_dw_kernel<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        head_dw_kernel<O><<<grid, 256, smem, st>>>(x, dy, w, gw, b, gb, B, in, inv_m, l1, l2, bl1, bl2);
+        head_dw_kernel<O><<<grid, 256, smem, st>>>(x, dy, w, gw, b, gb, B, in, rows, inv_m, l1, l2, bl1, bl2);
     });
     return true;
 }
