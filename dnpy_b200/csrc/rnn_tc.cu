@@ -4,17 +4,19 @@
 //     pre(t) = (delta_y[t == T-1] + pre(t+1) . Waa) * (1 - h_t^2),      dx_t = pre(t) . Wax
 // and (b) runs an inner loop of up to trunc + 1 lags starting from S_0(t) = pre(t):
 //     gWaa += S_k(t) (x) h_{t-k-1},  gWax += S_k(t) (x) x_{t-k},  gba += S_k(t),   S_{k+1}(t) = (S_k(t) * (1 - h_{t-k-1}^2)) . Waa.
-// (a) is a serial recurrence per sample: rnn_chain_kernel (a warp per sample, as the forward) writes pre for every (b, t).
+// (a) is a serial recurrence per sample: rnn_chain_blk_kernel / rnn_chain_kernel (a warp per sample, as the forward) write pre
+// for every (b, t).
 // (b) has NO dependency between different (b, t): over the B*T flat rows r = b*T + t it is trunc chained
 // [rows x 32] x [32 x 32] products plus one long reduction — tensor-core work.  rnn_lags_tc_kernel, per tile of 128 rows
 // (thread = row = TMEM lane):
 //   * S_0 = the pre tile (TMA, 128B swizzle); for each lag the thread scales its row by g = 1 - h(row-k-1)^2 (h tile by
 //     TMA with an 8-row halo), writes it as the K-major A operand, ONE thread issues 4 tcgen05.mma.kind::tf32 (M = 128,
 //     N = 32, K = 8) against the resident Waa^T, and the row comes back through tcgen05.ld;
-//   * lag sum: both gradients pair S_k(t) with data of row t - k, so W(u) = sum_k S_k(u + k) is accumulated TRANSPOSED in
-//     shared memory (Wt[i][u], a read-modify-write per lag: lanes run along u, conflict free) and the reduction over rows is
-//     ONE M = 64 MMA chain per tile with K = rows:  D2[m][i] += sum_u HXt[m][u] * Wt[i][u],  HXt rows = h(u-1) (32) | x(u)
-//     (D) | ones: gWaa^T, gWax^T and gba accumulate in TMEM over all tiles of the CTA and leave by atomics at the end;
+//   * lag sum: both gradients pair S_k(t) with data of row t - k, so W(u) = sum_k S_k(u + k) is accumulated in the pre tile's
+//     own rows (a 128-bit read-modify-write of row t - k - 1 per lag, one thread per row, lags separated by the block barrier),
+//     transposed once per tile (Wt[i][u]), and the reduction over rows is ONE M = 64 MMA chain per tile with K = rows:
+//     D2[m][i] += sum_u HXt[m][u] * Wt[i][u],  HXt rows = h(u-1) (32) | x(u) (D) | ones: gWaa^T, gWax^T and gba accumulate in
+//     TMEM over all tiles of the CTA and leave by atomics at the end;
 //   * a tile OWNS its first 128 - trunc rows (its W(u) is complete there); tiles advance by that many rows, the lag chain
 //     of the halo rows is recomputed by the next tile.
 #include "common.cuh"
