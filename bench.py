@@ -147,6 +147,10 @@ def algo_work(layer, kernel, B):
         if "fwd" in kernel:
             return B * t * (d + hd) * s, 2.0 * B * t * hd * (hd + d)
         k = min(t, (layer.bptt_truncate if layer.bptt_truncate is not None else t) + 1)
+        if kernel == "rnn_bwd_chain":       # the serial chain of the tensor-core backward: states in, pre + dx out
+            return B * t * (2 * hd + d) * s, 2.0 * B * t * hd * (hd + d)
+        if kernel == "rnn_bwd_lags_tc":     # pre + states + x in; (k - 1) lag products + the reduction against h | x | 1
+            return B * t * (2 * hd + d) * s, 2.0 * B * t * hd * ((k - 1) * hd + hd + d + 1)
         # literal truncated BPTT (recurrent.py:228-247): per step the dh chain (2 H*H) + dx (H*D) + k inner steps of
         # gWaa / gWax outer products and the s <- s*(1-h^2) Waa product
         return B * t * (2 * d + hd) * s, 2.0 * B * t * (hd * hd + hd * d + k * (2 * hd * hd + hd * d))
