@@ -51,6 +51,12 @@ def test_pure_host_entry_points():
     assert lib.dnb_maxpool2d_bwd_ws_bytes(g, _lib.ROUTE_PER_SAMPLE) == 0
     assert lib.dnb_loss_ws_bytes(10) == 14 * 4
     assert lib.dnb_embedding_bwd_ws_bytes(5, 7, 3) == (7 + 15 * (1 + 32)) * 4        # last[V] + mean[L*D] + 32 batch-slice partials
+    assert lib.dnb_rnn_bwd_tc_ws_bytes(2, 3, 32) == 768                               # pre[B*T*H] fp32, rounded up to 256 B
+    # the tensor-core variants are math-mode gated: fp32 never takes them (no device or driver needed to answer)
+    assert lib.dnb_rnn_bwd_tc_supported(256, 8, 32, 4, _lib.MATH_FP32) == 0
+    gc = _lib.Win(8, 1, 28, 28, 32, 26, 26, 3, 3, 1, 1, 0, 0, 0, 0)
+    gp = _lib.Win(8, 32, 26, 26, 32, 12, 12, 3, 3, 2, 2, 0, 0, 0, 0)
+    assert lib.dnb_conv_pool_act_tc_supported(gc, gp, _lib.MATH_FP32) == 0
 
 
 def test_no_cpu_fallback_without_device():
