@@ -120,3 +120,49 @@ def test_block_diagonal_image_group_gemm_equals_the_convolution():
         for p in range(G):
             want = conv[p, :, 4 * chunk:4 * chunk + rows, :NC].reshape(F, rows * NC)
             assert np.allclose(Dm[p * F:(p + 1) * F], want, rtol=1e-12, atol=1e-12)
+
+
+def _pool_window_bookkeeping(win, nansafe):
+    """The fused kernels' 3x3 window walk (fused_cpa.cu cpa_walk, tc_conv_c1p.cu c1p_pool_chunk): per conv row the 3-max and the
+    FIRST column equal to it, rows combined with a strict > (an earlier row keeps a tie).  Returns (value, offset, nan_seen)."""
+    best, idx, nan_seen = None, 0, False
+    for i in range(3):
+        c0, c1, c2 = win[i]
+        if nansafe:                                            # np.argmax's sequential comparison: first NaN wins and sticks
+            hb, hj = c0, 0
+            if c1 > hb or (c1 != c1 and hb == hb): hb, hj = c1, 1
+            if c2 > hb or (c2 != c2 and hb == hb): hb, hj = c2, 2
+        else:                                                  # max.NaN + first-equal
+            hb = np.nan if (c0 != c0 or c1 != c1 or c2 != c2) else max(c0, c1, c2)
+            hj = 0 if c0 == hb else (1 if c1 == hb else 2)
+        if i == 0:
+            best, idx = hb, hj
+        else:
+            take = (hb > best or (hb != hb and best == best)) if nansafe else (hb > best)
+            if not nansafe:
+                nan_seen = nan_seen or best != best or hb != hb
+                best = np.nan if (best != best or hb != hb) else max(best, hb)
+            elif take:
+                best = hb
+            if take:
+                idx = 3 * i + hj
+    return best, idx, nan_seen or (best != best)
+
+
+def test_row_wise_max_with_strict_row_combination_is_numpy_argmax():
+    rs = np.random.RandomState(3)
+    for trial in range(4000):
+        win = rs.randint(-2, 3, (3, 3)).astype(np.float64)     # many ties
+        if trial % 5 == 0:
+            win[rs.randint(3), rs.randint(3)] = np.nan
+        if trial % 11 == 0:
+            win[rs.randint(3), rs.randint(3)] = np.nan
+        want = int(np.argmax(win.reshape(9)))
+        val, idx, nan_seen = _pool_window_bookkeeping(win, nansafe=False)
+        if np.isnan(win).any():
+            assert nan_seen                                    # the fast path only DETECTS it; the kernel then repeats NANSAFE
+            val, idx, _ = _pool_window_bookkeeping(win, nansafe=True)
+            assert np.isnan(val)
+        else:
+            assert not nan_seen and val == win.reshape(9)[want]
+        assert idx == want, (win, idx, want)
